@@ -1,0 +1,128 @@
+"""The oracle (CPU restatement) against fixtures produced by the unmodified reference
+(`oracle/make_golden.py`, run in the build container).  CPU only."""
+import json
+import os
+
+import numpy as np
+import torch
+
+from oracle import frontend, ncsnpp as o_ncsnpp, sampler as o_sampler, snrnet as o_snrnet
+from oracle.topology import NCSNppConfig, param_specs, snrnet_param_specs
+from snr_aligned_diffse_b200.synth import synth_state_dict
+
+
+def _c(a):
+    return torch.from_numpy(np.ascontiguousarray(a))
+
+
+def test_param_inventory_matches_reference(golden_dir):
+    ref = json.load(open(os.path.join(golden_dir, "ncsnpp_param_specs.json")))
+    mine = param_specs(NCSNppConfig())
+    assert list(mine.keys()) == list(ref.keys())
+    assert all(tuple(ref[k]) == tuple(v) for k, v in mine.items())
+    assert sum(int(np.prod(v)) for v in mine.values()) == 65590822
+    ema = json.load(open(os.path.join(golden_dir, "ncsnpp_ema_order.json")))
+    # EMA shadow list == requires_grad parameters in registration order (Fourier W is frozen)
+    assert ema == [k for k in mine if k != "dnn.all_modules.0.W"]
+
+
+def test_scalars(golden_dir):
+    z = np.load(os.path.join(golden_dir, "scalars.npz"))
+    assert np.array_equal(z["t_30"], o_sampler.T_30)
+    for fs, r, idx, t, nfac in z["rows"]:
+        o_idx, o_t, o_nf = o_sampler.v3_scalars(float(np.float32(r)), float(fs), 1.0)
+        assert o_idx == int(idx) and o_t == t and abs(o_nf - nfac) < 1e-7
+
+
+def test_frontend(golden_dir):
+    z = np.load(os.path.join(golden_dir, "frontend.npz"))
+    wave = _c(z["wave"])
+    L = wave.shape[1]
+    S = frontend.stft(wave)
+    assert S.shape == (2, 256, frontend.n_frames(L))
+    assert torch.equal(torch.view_as_real(S), torch.view_as_real(_c(z["stft"])))
+    Y = frontend.pad_spec(frontend.spec_fwd(S).unsqueeze(1))
+    assert Y.shape[-1] == frontend.padded_frames(L) == 64
+    assert torch.equal(torch.view_as_real(Y), torch.view_as_real(_c(z["spec"])))
+    back = frontend.spec_back(Y.squeeze(1))
+    assert torch.allclose(torch.view_as_real(back), torch.view_as_real(_c(z["spec_back"])), atol=0, rtol=0)
+    assert torch.equal(frontend.istft(back, L), _c(z["istft"]))
+    # independent direct-DFT statement (explicit reflect / OLA indices) agrees with torch.stft/istft
+    d = frontend.dft_stft(z["wave"][0])
+    assert np.abs(d - z["stft"][0]).max() < 2e-6
+    di = frontend.dft_istft(z["spec_back"][0], L)
+    assert np.abs(di - z["istft"][0]).max() < 1e-6
+    assert torch.equal(o_snrnet.snr_features(wave[:1]), _c(z["snr_feat"]))
+
+
+def test_frontend_edge_lengths():
+    # ragged / boundary lengths: frame count, padded frame count, exact zero padding, round trip
+    for L in (256, 257, 383, 384, 8191, 8192, 8193):  # reflect padding needs L > n_fft//2
+        w = torch.randn(1, L, generator=torch.Generator().manual_seed(L))
+        S = frontend.stft(w)
+        assert S.shape[-1] == 1 + L // 128
+        Y = frontend.pad_spec(S.unsqueeze(1))
+        assert Y.shape[-1] % 64 == 0 and Y.shape[-1] - S.shape[-1] < 64
+        assert Y[..., S.shape[-1]:].abs().sum() == 0
+        rt = frontend.istft(frontend.spec_back(frontend.spec_fwd(S)), L)
+        assert (rt - w).abs().max() < 1e-4
+        d = frontend.dft_stft(w[0].numpy())
+        assert np.abs(d - S[0].numpy()).max() < 1e-4
+
+
+def test_fir(golden_dir):
+    z = np.load(os.path.join(golden_dir, "fir.npz"))
+    x = _c(z["x"])
+    assert torch.allclose(o_ncsnpp.fir_upsample_2d(x), _c(z["up"]), atol=1e-6)
+    assert torch.allclose(o_ncsnpp.fir_downsample_2d(x), _c(z["down"]), atol=1e-6)
+    # separable closed forms on an odd-sized map
+    x = torch.randn(1, 1, 3, 5)
+    xp = torch.nn.functional.pad(x, (1, 1, 1, 1))
+    up = o_ncsnpp.fir_upsample_2d(x)
+    r = torch.zeros(1, 1, 6, 5)
+    r[:, :, 0::2] = (xp[:, :, 0:3, 1:6] + 3 * xp[:, :, 1:4, 1:6]) / 4
+    r[:, :, 1::2] = (3 * xp[:, :, 1:4, 1:6] + xp[:, :, 2:5, 1:6]) / 4
+    rp = torch.nn.functional.pad(r, (1, 1, 0, 0))
+    e = torch.zeros(1, 1, 6, 10)
+    e[..., 0::2] = (rp[..., 0:5] + 3 * rp[..., 1:6]) / 4
+    e[..., 1::2] = (3 * rp[..., 1:6] + rp[..., 2:7]) / 4
+    assert torch.allclose(up, e, atol=1e-6)
+
+
+def test_snrnet(golden_dir):
+    z = np.load(os.path.join(golden_dir, "snrnet.npz"))
+    sd = synth_state_dict(snrnet_param_specs(), seed=1)
+    out = o_snrnet.snrnet_forward(sd, _c(z["feat"]))
+    assert torch.allclose(out, _c(z["out"]), atol=1e-6)
+
+
+def test_ncsnpp_forward(golden_dir):
+    z = np.load(os.path.join(golden_dir, "ncsnpp_forward.npz"))
+    sd = synth_state_dict(param_specs(NCSNppConfig()), seed=0)
+    with torch.no_grad():
+        out = o_ncsnpp.ncsnpp_forward(sd, _c(z["x"]), _c(z["t"]))
+    ref = _c(z["out"])
+    assert out.shape == ref.shape == (2, 1, 256, 64)
+    assert (out - ref).abs().max() <= 1e-4 * ref.abs().max()
+
+
+def test_enhance_v3(golden_dir):
+    z = np.load(os.path.join(golden_dir, "enhance_v3.npz"))
+    sd = synth_state_dict(param_specs(NCSNppConfig()), seed=0)
+    o = o_sampler.enhance_v3(sd, _c(z["y"]), _c(z["Z"]), float(z["ratio"]), 0.17783, sigma_max=1.0)
+    assert o["t"] == float(z["t"]) and abs(o["norm_factor"] - float(z["norm_factor"])) < 1e-7
+    ref = _c(z["x_hat"])
+    assert o["x_hat"].shape == ref.shape
+    assert (o["x_hat"] - ref).abs().max() <= 1e-4 * ref.abs().max()
+
+
+def test_pc_sampler(golden_dir):
+    z = np.load(os.path.join(golden_dir, "pc_ouve.npz"))
+    sd = synth_state_dict(param_specs(NCSNppConfig()), seed=0)
+    noises = [n for n in _c(z["noises"])]
+    out, nfe = o_sampler.pc_sample(sd, _c(z["Y"]), o_sampler.OUVE(1.5, 0.05, 0.5, N=2), noises, N=2, eps=0.03, snr=0.5)
+    ref = _c(z["out"])
+    assert nfe == int(z["nfe"]) == 4
+    assert (out - ref).abs().max() <= 1e-4 * ref.abs().max()
+    b = np.load(os.path.join(golden_dir, "bbed.npz"))
+    assert torch.allclose(o_sampler.BBED(0.999, 2.6, 0.52).std(_c(b["t"])), _c(b["std"]), atol=1e-7)
