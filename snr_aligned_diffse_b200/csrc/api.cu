@@ -1,0 +1,137 @@
+// C-ABI entry points for the stand-alone operators (declared in include/snrse_b200.h).
+// The NCSN++ executor entry points live in engine.cu, the SNR estimator's in snrnet.cu.
+#include <stdarg.h>
+
+#include <vector>
+
+#include "kernels.h"
+
+static thread_local char g_err[512] = "";
+
+void snrse_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+static cudaStream_t S(void* s) { return static_cast<cudaStream_t>(s); }
+
+static ActView mk_view(const void* p, int B, int H, int W, int C, int ld) {
+    ActView v;
+    v.ptr = const_cast<bf16*>(static_cast<const bf16*>(p));
+    v.B = B; v.H = H; v.W = W; v.C = C; v.ld = ld;
+    return v;
+}
+
+extern "C" {
+
+int snrse_version(void) { return 100; }
+const char* snrse_last_error(void) { return g_err; }
+
+// 0 when the current device is a Blackwell B200-class GPU (compute capability 10.x); the kernels are sm_100a-only.
+int snrse_device_check(void) {
+    int dev = 0;
+    cudaDeviceProp prop;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) {
+        snrse_set_error("no CUDA device available: the B200 library has no CPU fallback");
+        return SNRSE_ERR_CUDA;
+    }
+    if (prop.major != 10) {
+        snrse_set_error("device %s is sm_%d%d; this library is built for sm_100a only", prop.name, prop.major, prop.minor);
+        return SNRSE_ERR_UNSUPPORTED;
+    }
+    return SNRSE_OK;
+}
+
+int snrse_stft(const float* wave, const int* len, const float* scale, int scale_is_divisor, void* out, int B,
+               int lstride, int tpad, int transform, float alpha, float beta, int planar, void* stream) {
+    SNRSE_CHECK_ARG(wave && out, "stft: null pointer");
+    return stft_launch(wave, len, scale, scale_is_divisor, static_cast<float*>(out), B, lstride, tpad, transform, alpha,
+                       beta, planar, S(stream));
+}
+
+int64_t snrse_istft_workspace_bytes(int B, int tpad) { return (int64_t)B * tpad * 512 * 4; }
+
+int snrse_istft(const void* spec, const int* len, const float* scale, float* wave, void* workspace, int B, int lstride,
+                int tpad, int transform, float alpha, float beta, void* stream) {
+    SNRSE_CHECK_ARG(spec && wave && workspace, "istft: null pointer");
+    return istft_launch(static_cast<const float2*>(spec), len, scale, wave, static_cast<float*>(workspace), B, lstride,
+                        tpad, transform, alpha, beta, S(stream));
+}
+
+int snrse_absmax(const float* wave, const int* len, int B, int lstride, float* out, void* stream) {
+    SNRSE_CHECK_ARG(wave && out, "absmax: null pointer");
+    return absmax_launch(wave, len, B, lstride, out, S(stream));
+}
+
+int snrse_v3_scalars(const float* ratio, const float* peak, double snr_scale, float nf_const, const double* t30,
+                     float* t_out, float* nf_out, int* idx_out, int B, void* stream) {
+    SNRSE_CHECK_ARG(ratio && peak && t30 && t_out && nf_out, "v3_scalars: null pointer");
+    return v3_scalars_launch(ratio, peak, snr_scale, nf_const, t30, t_out, nf_out, idx_out, B, S(stream));
+}
+
+int snrse_snr_ratio(const float* g, float* ratio, int B, void* stream) { return snr_ratio_launch(g, ratio, B, S(stream)); }
+
+int snrse_lincomb(const void* x, const void* y, const void* sc, const void* z, const float* a, const float* b,
+                  const float* c, const float* d, void* out_mean, void* out_x, int B, int64_t n, void* stream) {
+    return lincomb_launch(static_cast<const float2*>(x), static_cast<const float2*>(y), static_cast<const float2*>(sc),
+                          static_cast<const float2*>(z), a, b, c, d, static_cast<float2*>(out_mean),
+                          static_cast<float2*>(out_x), B, n, S(stream));
+}
+
+// ---- single-operator entry points (NHWC bf16), used by the parity tests and usable as drop-in ops
+int snrse_conv_nhwc(const void* x0, int c0, int taps0, const void* x1, int c1, const void* wt, int n, const float* bias,
+                    const float* tbias, int tb_stride, const void* res, float scale, void* out, int B, int H, int W,
+                    int impl, void* stream) {
+    SNRSE_CHECK_ARG(x0 && wt && out, "conv_nhwc: null pointer");
+    ActView a0 = mk_view(x0, B, H, W, c0, c0), a1, r;
+    if (x1) a1 = mk_view(x1, B, H, W, c1, c1);
+    if (res) r = mk_view(res, B, H, W, n, n);
+    if (impl == 1) {
+        SNRSE_CHECK_ARG(n <= 256, "conv_nhwc: CUDA-core cross-check path handles N <= 256");
+        return conv_simt_launch(&a0, taps0, x1 ? &a1 : nullptr, static_cast<const bf16*>(wt), n, bias, tbias, tb_stride,
+                                res ? &r : nullptr, scale, static_cast<bf16*>(out), n, S(stream));
+    }
+    ConvGemmPlan p;
+    SNRSE_TRY(conv_gemm_make_plan(&p, &a0, taps0, x1 ? &a1 : nullptr, static_cast<const bf16*>(wt), n, 0, 0, bias, tbias,
+                                  tb_stride, res ? &r : nullptr, scale, out, n, 0));
+    return conv_gemm_launch(&p, S(stream));
+}
+
+int64_t snrse_groupnorm_workspace_bytes(int B) { return (int64_t)B * (gn_max_chunks() * 64 + 1024) * 4; }
+
+int snrse_groupnorm_nhwc(const void* x, const float* gamma, const float* beta, void* out, int B, int H, int W, int C,
+                         int silu, float eps, void* workspace, void* stream) {
+    SNRSE_CHECK_ARG(x && gamma && beta && out && workspace, "groupnorm: null pointer");
+    const ActView vx = mk_view(x, B, H, W, C, C), vo = mk_view(out, B, H, W, C, C);
+    float* partial = static_cast<float*>(workspace);
+    float* scsh = partial + (int64_t)B * gn_max_chunks() * 64;
+    const int64_t hw = (int64_t)H * W;
+    int chunks = (int)(hw / 256 < 1 ? 1 : (hw / 256 > gn_max_chunks() ? gn_max_chunks() : hw / 256));
+    SNRSE_TRY(gn_stats_launch(&vx, partial, chunks, S(stream)));
+    SNRSE_TRY(gn_finalize_launch(partial, chunks, B, C, hw * (C / 32), gamma, beta, eps, scsh, S(stream)));
+    return gn_apply_launch(&vx, scsh, silu, &vo, S(stream));
+}
+
+int snrse_fir_nhwc(const void* x, void* out, int B, int H, int W, int C, int up, void* stream) {
+    SNRSE_CHECK_ARG(x && out, "fir: null pointer");
+    const ActView vx = mk_view(x, B, H, W, C, C);
+    const ActView vo = up ? mk_view(out, B, 2 * H, 2 * W, C, C) : mk_view(out, B, H / 2, W / 2, C, C);
+    return up ? fir_up2_launch(&vx, &vo, S(stream)) : fir_down2_launch(&vx, &vo, S(stream));
+}
+
+int snrse_fir_f4(const float* x, float* out, int B, int H, int W, int up, void* stream) {
+    SNRSE_CHECK_ARG(x && out, "fir_f4: null pointer");
+    return up ? fir_up2_f4_launch(x, out, B, H, W, S(stream)) : fir_down2_f4_launch(x, out, B, H, W, S(stream));
+}
+
+int snrse_attention_nhwc(const void* q, const void* k, const void* v, float* scores, void* out, int B, int n, int C,
+                         void* stream) {
+    SNRSE_CHECK_ARG(q && k && v && scores && out, "attention: null pointer");
+    const ActView vq = mk_view(q, B, 1, n, C, C), vk = mk_view(k, B, 1, n, C, C), vv = mk_view(v, B, 1, n, C, C),
+                  vo = mk_view(out, B, 1, n, C, C);
+    return attention_launch(&vq, &vk, &vv, scores, &vo, S(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,139 @@
+// Single-head self-attention core of `AttnBlockpp` (sgmse-bbed/sgmse/backbones/ncsnpp_utils/layerspp.py:84-88):
+//   w = softmax_j( q_i . k_j / sqrt(C) ),  o_i = sum_j w_ij v_j     over all n = H*W positions of one image.
+// q, k, v come from the NIN projections (tcgen05 GEMMs); this file holds the score / softmax / mix
+// kernels.  0.1 % of the network FLOPs, so they run on CUDA cores in fp32:
+//   scores  S = scale * Q K^T        (64x64 tiles, fp32 accumulate)  -> f32 [B, n, n] workspace
+//   softmax rows in place            (one warp per row)
+//   mix     O = S V                  (64x64 tiles)                    -> bf16 view
+#include "kernels.h"
+
+namespace {
+
+constexpr int TS = 64, TK = 32;
+
+__global__ void __launch_bounds__(256)
+attn_scores_kernel(const bf16* __restrict__ q, int q_ld, const bf16* __restrict__ k, int k_ld, int n, int C, float scale,
+                   float* __restrict__ S) {
+    __shared__ float qs[TS][TK + 1], ks[TS][TK + 1];
+    const int b = blockIdx.z, i0 = blockIdx.y * TS, j0 = blockIdx.x * TS;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const bf16* qb = q + (int64_t)b * n * q_ld;
+    const bf16* kb = k + (int64_t)b * n * k_ld;
+    float acc[4][4] = {};
+    for (int c0 = 0; c0 < C; c0 += TK) {
+        for (int e = threadIdx.x; e < TS * TK; e += 256) {
+            const int r = e / TK, c = e % TK;
+            qs[r][c] = (i0 + r < n) ? __bfloat162float(qb[(int64_t)(i0 + r) * q_ld + c0 + c]) : 0.f;
+            ks[r][c] = (j0 + r < n) ? __bfloat162float(kb[(int64_t)(j0 + r) * k_ld + c0 + c]) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int c = 0; c < TK; ++c) {
+            float a[4], bb[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                a[u] = qs[ty * 4 + u][c];
+                bb[u] = ks[tx * 4 + u][c];
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int v = 0; v < 4; ++v) acc[u][v] = fmaf(a[u], bb[v], acc[u][v]);
+        }
+        __syncthreads();
+    }
+    float* Sb = S + (int64_t)b * n * n;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const int i = i0 + ty * 4 + u;
+        if (i >= n) continue;
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+            const int j = j0 + tx * 4 + v;
+            if (j < n) Sb[(int64_t)i * n + j] = acc[u][v] * scale;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+attn_softmax_kernel(float* __restrict__ S, int n, int64_t rows) {
+    const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    float* p = S + row * n;
+    float m = -INFINITY;
+    for (int j = lane; j < n; j += 32) m = fmaxf(m, p[j]);
+    m = warp_max(m);
+    float sum = 0.f;
+    for (int j = lane; j < n; j += 32) {
+        const float e = __expf(p[j] - m);
+        p[j] = e;
+        sum += e;
+    }
+    sum = warp_sum(sum);
+    const float inv = 1.0f / sum;
+    for (int j = lane; j < n; j += 32) p[j] *= inv;
+}
+
+__global__ void __launch_bounds__(256)
+attn_mix_kernel(const float* __restrict__ S, const bf16* __restrict__ v, int v_ld, int n, int C, bf16* __restrict__ o,
+                int o_ld) {
+    __shared__ float ps[TS][TK + 1], vs[TK][TS + 1];
+    const int b = blockIdx.z, i0 = blockIdx.y * TS, c0 = blockIdx.x * TS;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const float* Sb = S + (int64_t)b * n * n;
+    const bf16* vb = v + (int64_t)b * n * v_ld;
+    float acc[4][4] = {};
+    for (int j0 = 0; j0 < n; j0 += TK) {
+        for (int e = threadIdx.x; e < TS * TK; e += 256) {
+            const int r = e / TK, c = e % TK;
+            ps[r][c] = (i0 + r < n && j0 + c < n) ? Sb[(int64_t)(i0 + r) * n + j0 + c] : 0.f;
+            const int jr = e / TS, cc = e % TS;
+            vs[jr][cc] = (j0 + jr < n && c0 + cc < C) ? __bfloat162float(vb[(int64_t)(j0 + jr) * v_ld + c0 + cc]) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int j = 0; j < TK; ++j) {
+            float a[4], bb[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                a[u] = ps[ty * 4 + u][j];
+                bb[u] = vs[j][tx * 4 + u];
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int w = 0; w < 4; ++w) acc[u][w] = fmaf(a[u], bb[w], acc[u][w]);
+        }
+        __syncthreads();
+    }
+    bf16* ob = o + (int64_t)b * n * o_ld;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const int i = i0 + ty * 4 + u;
+        if (i >= n) continue;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            const int c = c0 + tx * 4 + w;
+            if (c < C) ob[(int64_t)i * o_ld + c] = __float2bfloat16(acc[u][w]);
+        }
+    }
+}
+
+}  // namespace
+
+int attention_launch(const ActView* q, const ActView* k, const ActView* v, float* scores, const ActView* o,
+                     cudaStream_t s) {
+    const int n = q->H * q->W, C = q->C, B = q->B;
+    SNRSE_CHECK_ARG(C % TK == 0, "attention: C must be a multiple of %d", TK);
+    dim3 g1(cdiv(n, TS), cdiv(n, TS), B);
+    attn_scores_kernel<<<g1, 256, 0, s>>>(q->ptr, q->ld, k->ptr, k->ld, n, C, rsqrtf((float)C), scores);
+    SNRSE_LAUNCH_CHECK();
+    const int64_t rows = (int64_t)B * n;
+    attn_softmax_kernel<<<(unsigned)cdiv64(rows, 8), 256, 0, s>>>(scores, n, rows);
+    SNRSE_LAUNCH_CHECK();
+    dim3 g3(cdiv(C, TS), cdiv(n, TS), B);
+    attn_mix_kernel<<<g3, 256, 0, s>>>(scores, v->ptr, v->ld, n, C, o->ptr, o->ld);
+    SNRSE_LAUNCH_CHECK();
+    return SNRSE_OK;
+}

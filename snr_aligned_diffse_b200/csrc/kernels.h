@@ -1,0 +1,109 @@
+// Host-side launcher declarations shared by the C-ABI layer (api.cu) and the NCSN++ executor (engine.cu).
+// All launchers enqueue on the given stream, never allocate, never synchronise (graph-capturable).
+#pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+
+// A view of an activation tensor in NHWC order: element (b,h,w,c) lives at
+// ptr[((b*H + h)*W + w)*ld + c].  ld > C when the tensor is a channel slice of a concat buffer.
+struct ActView {
+    bf16* ptr;
+    int B, H, W, C, ld;
+};
+
+// ----------------------------------------------------------------------------- conv_gemm.cu
+// Implicit-GEMM convolution on tcgen05:  out[m, n] = epilogue( sum_k A[m, k] * Wt[n, k] )
+//   m = output pixel (b,h,w);  k = (tap, cin) of segment 0 followed by cin of segment 1 (1x1);
+//   epilogue: (+bias[n]) (+tbias[b*tb_stride + n]) (+res[m, n]) * scale  -> bf16 or f32.
+struct ConvGemmPlan {
+    CUtensorMap mapA0, mapA1, mapB;
+    int taps0;       // 9 (3x3, pad 1) or 1
+    int c0_chunks;   // Cin0 / 64
+    int c1_chunks;   // Cin1 / 64 (0: no second segment)
+    int B, H, W;     // output pixels
+    int th_log2, tw_log2, tiles_h, tiles_w;
+    int N, n_tile;   // output columns, columns per CTA (64 / 128 / 256)
+    int b_batched;   // 1: operand B has one matrix per batch item (attention), 0: shared weights
+    const float* bias;   // [N] or null
+    const float* tbias;  // [B, tb_stride] or null
+    int tb_stride;
+    const bf16* res;  // residual view or null
+    int res_ld;
+    float scale;
+    void* out;
+    int out_ld;
+    int out_f32;  // 0: bf16, 1: f32
+    int stages;
+    int smem_bytes;
+};
+// a0: segment-0 input view (taps0 taps); a1: optional segment-1 input (1 tap, may be null).
+// wt: [n_rows, Ktot] bf16, K-major, Ktot = (taps0*C0 + C1); for b_batched the matrix of batch b starts at
+// wt + b*wt_batch_stride elements.
+int conv_gemm_make_plan(ConvGemmPlan* p, const ActView* a0, int taps0, const ActView* a1, const bf16* wt, int n_rows,
+                        int64_t wt_batch_stride, int b_batched, const float* bias, const float* tbias, int tb_stride,
+                        const ActView* res, float scale, void* out, int out_ld, int out_f32);
+int conv_gemm_launch(const ConvGemmPlan* p, cudaStream_t s);
+
+// ----------------------------------------------------------------------------- conv_simt.cu
+// Reference-grade direct convolution on CUDA cores (debug / cross-check path, fp32 accumulate).
+int conv_simt_launch(const ActView* a0, int taps0, const ActView* a1, const bf16* wt, int N, const float* bias,
+                     const float* tbias, int tb_stride, const ActView* res, float scale, bf16* out, int out_ld,
+                     cudaStream_t s);
+// x4: [B,H,W,4] f32 -> out bf16 view, 3x3 pad 1, w: [Cout][3][3][4] f32
+int conv_in4_launch(const float* x4, const float* w, const float* bias, const ActView* out, cudaStream_t s);
+// a: bf16 view (C) -> out4 [B,H,W,4] f32 = conv3x3(a) + bias (+ addend4), w: [4][3][3][C] f32
+int conv_out4_launch(const ActView* a, const float* w, const float* bias, const float* addend4, float* out4,
+                     cudaStream_t s);
+// out = h + W[C x 4] * p4 + bias      (Combine 'sum' with a 1x1 conv on the 4-channel input pyramid)
+int combine4_launch(const float* p4, const ActView* h, const float* w, const float* bias, const ActView* out,
+                    cudaStream_t s);
+
+// ----------------------------------------------------------------------------- norm.cu
+int gn_max_chunks();
+// partial: [B][chunks][32][2] f32; scsh: [B][2][C] f32 (scale, shift)
+int gn_stats_launch(const ActView* x, float* partial, int chunks, cudaStream_t s);
+int gn_finalize_launch(const float* partial, int chunks, int B, int C, int64_t count_per_group, const float* gamma,
+                       const float* beta, float eps, float* scsh, cudaStream_t s);
+int gn_apply_launch(const ActView* x, const float* scsh, int silu, const ActView* out, cudaStream_t s);
+
+// ----------------------------------------------------------------------------- fir.cu
+int fir_up2_launch(const ActView* x, const ActView* out, cudaStream_t s);
+int fir_down2_launch(const ActView* x, const ActView* out, cudaStream_t s);
+int fir_up2_f4_launch(const float* x, float* out, int B, int H, int W, cudaStream_t s);      // in [B,H,W,4]
+int fir_down2_f4_launch(const float* x, float* out, int B, int H, int W, cudaStream_t s);    // in [B,H,W,4]
+
+// ----------------------------------------------------------------------------- attention.cu
+// q,k,v: [B, n, C] bf16 views (tokens = H*W); scores: [B, n, n] f32 workspace; o: bf16 view.
+int attention_launch(const ActView* q, const ActView* k, const ActView* v, float* scores, const ActView* o,
+                     cudaStream_t s);
+
+// ----------------------------------------------------------------------------- temb.cu
+// t: [B]; fourier_w [nf]; w1 [4nf][2nf], b1; w2 [4nf][4nf], b2; dense_w [rows][4nf], dense_b [rows]
+// act_temb: [B][4nf] scratch; tb_out: [B][rows]
+int temb_launch(const float* t, int B, int nf, const float* fourier_w, const float* w1, const float* b1,
+                const float* w2, const float* b2, const float* dense_w, const float* dense_b, int rows, float* scratch,
+                float* tb_out, cudaStream_t s);
+
+// ----------------------------------------------------------------------------- sampler.cu
+// x, y, out: complex64 [B, F*T]; x4: [B,F,T,4] f32 = (re x, im x, re y, im y)
+int pack_input_launch(const float2* x, const float2* y, float* x4, int B, int64_t n, cudaStream_t s);
+// out = alpha_b * xres + beta_b * (Wout * (p4 / t_b) + bout); mode 0: alpha=0,beta=1; 1: sebridge precond; 2: alpha=0,beta=-1
+int final_launch(const float* p4, const float* t, const float* w, const float* bias, const float2* xres, float2* out,
+                 int B, int64_t n, int mode, cudaStream_t s);
+// out_mean = a*x + b*y + c*s ; out_x = out_mean + d*z   (per-batch coefficient arrays, any pointer may alias)
+int lincomb_launch(const float2* x, const float2* y, const float2* sc, const float2* z, const float* a, const float* b,
+                   const float* c, const float* d, float2* out_mean, float2* out_x, int B, int64_t n, cudaStream_t s);
+
+// SNR -> (snapped t, norm factor): ratio[b] = noise/clean amplitude ratio, peak[b] = max|y|, t30: 30 doubles (device)
+int v3_scalars_launch(const float* ratio, const float* peak, double snr_scale, float nf_const, const double* t30,
+                      float* t_out, float* nf_out, int* idx_out, int B, cudaStream_t s);
+// n/(s+n) sigmoid output of the SNR estimator -> n/s  (model.py:720-721)
+int snr_ratio_launch(const float* g, float* ratio, int B, cudaStream_t s);
+
+// ----------------------------------------------------------------------------- stft.cu
+int stft_launch(const float* wave, const int* len, const float* scale, int scale_is_divisor, float* out, int B,
+                int lstride, int tpad, int transform, float alpha, float beta, int planar, cudaStream_t s);
+int absmax_launch(const float* wave, const int* len, int B, int lstride, float* out, cudaStream_t s);
+int istft_launch(const float2* spec, const int* len, const float* scale, float* wave, float* frames_ws, int B,
+                 int lstride, int tpad, int transform, float alpha, float beta, cudaStream_t s);

@@ -1,0 +1,134 @@
+// Element-wise kernels of the sampler (a7, a8, a18 of SURVEY 8a), complex64 state [B, F*T]:
+//   pack_input : dnn_input = cat([x, y]) as 4 real channels (model.py:483, ncsnpp.py:253-254)
+//   final      : h / t -> 1x1 conv 4->2 -> complex (ncsnpp.py:398-403) fused with the head:
+//                  mode 0  raw network output
+//                  mode 1  sebridge preconditioning  c_skip*x + c_out*dnn  (model.py:537-541)
+//                  mode 2  bbed score  -dnn  (model.py:488-489)
+//   lincomb    : x_mean = a*x + b*y + c*s,  x' = x_mean + d*z   -- covers prior sampling
+//                (sdes.py:225-232), annealed Langevin (correctors.py:69-81) and the reverse-diffusion
+//                predictor (predictors.py:75-80, sdes.py:73-91,132-140) with host-computed coefficients.
+#include "kernels.h"
+
+namespace {
+
+__global__ void __launch_bounds__(256)
+pack_input_kernel(const float2* __restrict__ x, const float2* __restrict__ y, float4* __restrict__ x4, int64_t total) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const float2 a = x[i], b = y[i];
+    x4[i] = make_float4(a.x, a.y, b.x, b.y);
+}
+
+__global__ void __launch_bounds__(256)
+final_kernel(const float4* __restrict__ p4, const float* __restrict__ t, const float* __restrict__ w,
+             const float* __restrict__ bias, const float2* __restrict__ xres, float2* __restrict__ out, int64_t n,
+             int mode) {
+    const int b = blockIdx.y;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float tb = t[b];
+    const float4 p = p4[(int64_t)b * n + i];
+    const float hx = p.x / tb, hy = p.y / tb, hz = p.z / tb, hw = p.w / tb;
+    float re = bias[0] + w[0] * hx + w[1] * hy + w[2] * hz + w[3] * hw;
+    float im = bias[1] + w[4] * hx + w[5] * hy + w[6] * hz + w[7] * hw;
+    if (mode == 1) {
+        const float eps = 0.001f, sd = 0.5f;
+        const float c_skip = sd * sd / ((tb - eps) * (tb - eps) + sd * sd);
+        const float c_out = (sd * (tb - eps)) / sqrtf(sd * sd + tb * tb);
+        const float2 xr = xres[(int64_t)b * n + i];
+        re = c_skip * xr.x + c_out * re;
+        im = c_skip * xr.y + c_out * im;
+    } else if (mode == 2) {
+        re = -re;
+        im = -im;
+    }
+    out[(int64_t)b * n + i] = make_float2(re, im);
+}
+
+__global__ void __launch_bounds__(256)
+lincomb_kernel(const float2* __restrict__ x, const float2* __restrict__ y, const float2* __restrict__ sc,
+               const float2* __restrict__ z, const float* __restrict__ a, const float* __restrict__ bq,
+               const float* __restrict__ c, const float* __restrict__ d, float2* out_mean, float2* out_x, int64_t n) {
+    const int b = blockIdx.y;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int64_t o = (int64_t)b * n + i;
+    float re = 0.f, im = 0.f;
+    if (x) { const float2 v = x[o]; const float k = a[b]; re = k * v.x; im = k * v.y; }
+    if (y) { const float2 v = y[o]; const float k = bq[b]; re = fmaf(k, v.x, re); im = fmaf(k, v.y, im); }
+    if (sc) { const float2 v = sc[o]; const float k = c[b]; re = fmaf(k, v.x, re); im = fmaf(k, v.y, im); }
+    if (out_mean) out_mean[o] = make_float2(re, im);
+    if (z) { const float2 v = z[o]; const float k = d[b]; re = fmaf(k, v.x, re); im = fmaf(k, v.y, im); }
+    if (out_x) out_x[o] = make_float2(re, im);
+}
+
+// model.py:726-740 / 811-817 on device (no host sync): t_raw = ratio / (10^0.25 fixed_snr); snap to the
+// nearest of the 30 float64 grid points (first minimum, like numpy argmin); normfac evaluated in
+// float32 exactly as the reference's tensor arithmetic does.
+__global__ void v3_scalars_kernel(const float* __restrict__ ratio, const float* __restrict__ peak, double snr_scale,
+                                  float nf_const, const double* __restrict__ t30, float* __restrict__ t_out,
+                                  float* __restrict__ nf_out, int* __restrict__ idx_out, int B) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const float t_raw = ratio[b] / (float)snr_scale;
+    int best = 0;
+    double bd = fabs(t30[0] - (double)t_raw);
+    for (int i = 1; i < 30; ++i) {
+        const double d = fabs(t30[i] - (double)t_raw);
+        if (d < bd) {
+            bd = d;
+            best = i;
+        }
+    }
+    const double t = t30[best];
+    const float est = (float)(snr_scale * t);
+    const float nf = nf_const / sqrtf(1.0f + est * est);
+    t_out[b] = (float)t;
+    nf_out[b] = peak[b] * nf;
+    if (idx_out) idx_out[b] = best;
+}
+
+__global__ void snr_ratio_kernel(const float* __restrict__ g, float* __restrict__ ratio, int B) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < B) ratio[b] = g[b] / (1.0f - g[b]);
+}
+
+}  // namespace
+
+int v3_scalars_launch(const float* ratio, const float* peak, double snr_scale, float nf_const, const double* t30,
+                      float* t_out, float* nf_out, int* idx_out, int B, cudaStream_t s) {
+    v3_scalars_kernel<<<cdiv(B, 128), 128, 0, s>>>(ratio, peak, snr_scale, nf_const, t30, t_out, nf_out, idx_out, B);
+    SNRSE_LAUNCH_CHECK();
+    return SNRSE_OK;
+}
+
+int snr_ratio_launch(const float* g, float* ratio, int B, cudaStream_t s) {
+    snr_ratio_kernel<<<cdiv(B, 128), 128, 0, s>>>(g, ratio, B);
+    SNRSE_LAUNCH_CHECK();
+    return SNRSE_OK;
+}
+
+int pack_input_launch(const float2* x, const float2* y, float* x4, int B, int64_t n, cudaStream_t s) {
+    const int64_t total = (int64_t)B * n;
+    pack_input_kernel<<<(unsigned)cdiv64(total, 256), 256, 0, s>>>(x, y, reinterpret_cast<float4*>(x4), total);
+    SNRSE_LAUNCH_CHECK();
+    return SNRSE_OK;
+}
+
+int final_launch(const float* p4, const float* t, const float* w, const float* bias, const float2* xres, float2* out,
+                 int B, int64_t n, int mode, cudaStream_t s) {
+    SNRSE_CHECK_ARG(mode >= 0 && mode <= 2, "final: bad mode %d", mode);
+    SNRSE_CHECK_ARG(mode != 1 || xres, "final: mode 1 needs the residual state");
+    dim3 grid((unsigned)cdiv64(n, 256), B);
+    final_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const float4*>(p4), t, w, bias, xres, out, n, mode);
+    SNRSE_LAUNCH_CHECK();
+    return SNRSE_OK;
+}
+
+int lincomb_launch(const float2* x, const float2* y, const float2* sc, const float2* z, const float* a, const float* b,
+                   const float* c, const float* d, float2* out_mean, float2* out_x, int B, int64_t n, cudaStream_t s) {
+    dim3 grid((unsigned)cdiv64(n, 256), B);
+    lincomb_kernel<<<grid, 256, 0, s>>>(x, y, sc, z, a, b, c, d, out_mean, out_x, n);
+    SNRSE_LAUNCH_CHECK();
+    return SNRSE_OK;
+}

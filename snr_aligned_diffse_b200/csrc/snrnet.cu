@@ -1,0 +1,307 @@
+// SNR estimator forward pass (reduced PESQNet) on CUDA cores, fp32.
+// Replaces `SNRNet.forward` (sgmse-bbed/sgmse/backbones/snrnet.py:47-97): the STFT is split into
+// 16-frame clusters; per cluster conv5x5(2->32,p2) -> maxpool 2x2 -> conv3x3(32->32,p1) -> maxpool (2,1)
+// -> four (64 x k) convolutions, k = 1,2,4,8, each max-pooled over time -> 128 features; a BiLSTM(128->128)
+// runs over the clusters; [mean, unbiased std, min, max] over clusters -> Linear(1024->1) -> sigmoid.
+// ~1.2 MMAC per STFT frame (0.1 % of the score network): plain SIMT kernels, no tensor cores.
+#include "kernels.h"
+
+namespace {
+
+struct SnrParam {
+    const char* name;
+    int64_t numel;
+};
+const SnrParam kParams[] = {
+    {"dnn.conv5x5_1.weight", 32 * 2 * 25},        {"dnn.conv5x5_1.bias", 32},
+    {"dnn.conv3x3_1.weight", 32 * 32 * 9},        {"dnn.conv3x3_1.bias", 32},
+    {"dnn.convt_1.weight", 32 * 32 * 64 * 1},     {"dnn.convt_1.bias", 32},
+    {"dnn.convt_2.weight", 32 * 32 * 64 * 2},     {"dnn.convt_2.bias", 32},
+    {"dnn.convt_3.weight", 32 * 32 * 64 * 4},     {"dnn.convt_3.bias", 32},
+    {"dnn.convt_4.weight", 32 * 32 * 64 * 8},     {"dnn.convt_4.bias", 32},
+    {"dnn.blstm.weight_ih_l0", 512 * 128},        {"dnn.blstm.weight_hh_l0", 512 * 128},
+    {"dnn.blstm.bias_ih_l0", 512},                {"dnn.blstm.bias_hh_l0", 512},
+    {"dnn.blstm.weight_ih_l0_reverse", 512 * 128}, {"dnn.blstm.weight_hh_l0_reverse", 512 * 128},
+    {"dnn.blstm.bias_ih_l0_reverse", 512},        {"dnn.blstm.bias_hh_l0_reverse", 512},
+    {"dnn.fc.weight", 1024},                      {"dnn.fc.bias", 1},
+};
+constexpr int kNumParams = sizeof(kParams) / sizeof(kParams[0]);
+
+int64_t param_offset(int i) {  // bytes, 256-aligned slots
+    int64_t off = 0;
+    for (int j = 0; j < i; ++j) off += (kParams[j].numel * 4 + 255) / 256 * 256;
+    return off;
+}
+const float* P(const void* blob, int i) { return reinterpret_cast<const float*>(static_cast<const uint8_t*>(blob) + param_offset(i)); }
+
+// ---- conv5x5 (2->32, pad 2) + maxpool 2x2.  feat [B][2][256][T16] -> a1 [NC][32][128][8], NC = B*T16/16
+__global__ void __launch_bounds__(256)
+snr_conv5_pool_kernel(const float* __restrict__ feat, const float* __restrict__ w, const float* __restrict__ bias,
+                      float* __restrict__ a1, int T16) {
+    __shared__ float sw[32 * 50];
+    __shared__ float sx[2][20][20];  // input patch: 16 freq rows (+4 halo) x 16 frames (+4 halo)
+    const int nc = blockIdx.y, clusters = T16 / 16;
+    const int b = nc / clusters, cl = nc % clusters;
+    const int f0 = blockIdx.x * 16;  // 16 input rows -> 8 pooled rows
+    for (int i = threadIdx.x; i < 32 * 50; i += 256) sw[i] = w[i];
+    for (int i = threadIdx.x; i < 2 * 20 * 20; i += 256) {
+        const int c = i / 400, r = (i / 20) % 20, t = i % 20;
+        const int f = f0 + r - 2, tt = t - 2;
+        float v = 0.f;
+        if (f >= 0 && f < 256 && tt >= 0 && tt < 16) v = feat[(((int64_t)b * 2 + c) * 256 + f) * T16 + cl * 16 + tt];
+        sx[c][r][t] = v;
+    }
+    __syncthreads();
+    // 32 co x 8 pooled rows x 8 pooled cols = 2048 outputs, 8 per thread
+    for (int o = threadIdx.x; o < 2048; o += 256) {
+        const int co = o >> 6, pr = (o >> 3) & 7, pc = o & 7;
+        float best = -INFINITY;
+#pragma unroll
+        for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+            for (int dx = 0; dx < 2; ++dx) {
+                float acc = bias[co];
+                const int r0 = pr * 2 + dy, c0 = pc * 2 + dx;
+                for (int c = 0; c < 2; ++c)
+#pragma unroll
+                    for (int ky = 0; ky < 5; ++ky)
+#pragma unroll
+                        for (int kx = 0; kx < 5; ++kx)
+                            acc = fmaf(sx[c][r0 + ky][c0 + kx], sw[co * 50 + c * 25 + ky * 5 + kx], acc);
+                best = fmaxf(best, acc);
+            }
+        a1[(((int64_t)nc * 32 + co) * 128 + (f0 / 2 + pr)) * 8 + pc] = best;
+    }
+}
+
+// ---- conv3x3 (32->32, pad 1) + maxpool (2,1).  a1 [NC][32][128][8] -> a2 [NC][32][64][8]
+__global__ void __launch_bounds__(256)
+snr_conv3_pool_kernel(const float* __restrict__ a1, const float* __restrict__ w, const float* __restrict__ bias,
+                      float* __restrict__ a2) {
+    __shared__ float sw[32 * 32 * 9];   // 36 KB
+    __shared__ float sx[32][6][10];     // 4 input rows (+2 halo) x 8 cols (+2 halo), 7.5 KB
+    const int nc = blockIdx.y, f0 = blockIdx.x * 4;  // 4 conv rows -> 2 pooled rows
+    for (int i = threadIdx.x; i < 32 * 32 * 9; i += 256) sw[i] = w[i];
+    for (int i = threadIdx.x; i < 32 * 60; i += 256) {
+        const int c = i / 60, r = (i / 10) % 6, t = i % 10;
+        const int f = f0 + r - 1, tt = t - 1;
+        float v = 0.f;
+        if (f >= 0 && f < 128 && tt >= 0 && tt < 8) v = a1[(((int64_t)nc * 32 + c) * 128 + f) * 8 + tt];
+        sx[c][r][t] = v;
+    }
+    __syncthreads();
+    // 32 co x 2 pooled rows x 8 cols = 512 outputs, 2 per thread
+    for (int o = threadIdx.x; o < 512; o += 256) {
+        const int co = o >> 4, pr = (o >> 3) & 1, pc = o & 7;
+        float best = -INFINITY;
+#pragma unroll
+        for (int dy = 0; dy < 2; ++dy) {
+            float acc = bias[co];
+            const int r0 = pr * 2 + dy;
+            for (int c = 0; c < 32; ++c)
+#pragma unroll
+                for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                    for (int kx = 0; kx < 3; ++kx)
+                        acc = fmaf(sx[c][r0 + ky][pc + kx], sw[(co * 32 + c) * 9 + ky * 3 + kx], acc);
+            best = fmaxf(best, acc);
+        }
+        a2[(((int64_t)nc * 32 + co) * 64 + (f0 / 2 + pr)) * 8 + pc] = best;
+    }
+}
+
+// ---- four (64 x k) convolutions + max over time.  a2 [NC][32][64][8] -> feats [NC][128]
+struct ConvtW {
+    const float* w[4];
+    const float* b[4];
+};
+__global__ void __launch_bounds__(256)
+snr_convt_kernel(const float* __restrict__ a2, ConvtW cw, float* __restrict__ feats) {
+    extern __shared__ float sx[];  // [32*64][8]
+    const int nc = blockIdx.x;
+    for (int i = threadIdx.x; i < 32 * 64 * 8; i += 256) sx[i] = a2[(int64_t)nc * 16384 + i];
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int pair = warp; pair < 128; pair += 8) {
+        const int ki = pair >> 5, co = pair & 31;
+        const int k = 1 << ki;           // 1, 2, 4, 8
+        const int nout = 9 - k;          // 8, 7, 5, 1 output frames
+        const float* wr = cw.w[ki] + (int64_t)co * 2048 * k;  // [ci*64+f][dt]
+        float acc[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) acc[t] = 0.f;
+        for (int r = lane; r < 2048; r += 32) {  // r = ci*64 + f
+            const float* xr = sx + r * 8;
+            for (int dt = 0; dt < k; ++dt) {
+                const float wv = wr[r * k + dt];
+#pragma unroll
+                for (int t = 0; t < 8; ++t)
+                    if (t < nout) acc[t] = fmaf(xr[t + dt], wv, acc[t]);
+            }
+        }
+        float best = -INFINITY;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+            const float v = warp_sum(acc[t]);
+            if (t < nout) best = fmaxf(best, v);
+        }
+        if (lane == 0) feats[(int64_t)nc * 128 + ki * 32 + co] = best + cw.b[ki][co];
+    }
+}
+
+// ---- LSTM input projections for both directions: pre[dir][B*S][512] = W_ih x + b_ih + b_hh
+__global__ void __launch_bounds__(256)
+snr_lstm_pre_kernel(const float* __restrict__ feats, const float* __restrict__ wih0, const float* __restrict__ bih0,
+                    const float* __restrict__ bhh0, const float* __restrict__ wih1, const float* __restrict__ bih1,
+                    const float* __restrict__ bhh1, float* __restrict__ pre, int64_t rows) {
+    __shared__ float sx[128];
+    const int64_t row = blockIdx.x;
+    if (threadIdx.x < 128) sx[threadIdx.x] = feats[row * 128 + threadIdx.x];
+    __syncthreads();
+    for (int o = threadIdx.x; o < 1024; o += 256) {
+        const int dir = o >> 9, g = o & 511;
+        const float* wr = (dir ? wih1 : wih0) + (int64_t)g * 128;
+        float acc = (dir ? bih1 : bih0)[g] + (dir ? bhh1 : bhh0)[g];
+        for (int j = 0; j < 128; ++j) acc = fmaf(wr[j], sx[j], acc);
+        pre[((int64_t)dir * rows + row) * 512 + g] = acc;
+    }
+}
+
+// ---- recurrence: one block per (batch item, direction); thread g owns gate row g of W_hh
+// (64 weights in registers, 64 in shared memory).  Gate order i, f, g, o (torch.nn.LSTM).
+__global__ void __launch_bounds__(512, 1)
+snr_lstm_rec_kernel(const float* __restrict__ pre, const float* __restrict__ whh0, const float* __restrict__ whh1,
+                    float* __restrict__ hout, int S, int64_t rows) {
+    extern __shared__ float sm[];
+    float* sw = sm;                  // [64][512]  second half of every W_hh row, transposed
+    float* sh = sm + 64 * 512;       // [128] h
+    float* sg = sh + 128;            // [512] gates
+    const int b = blockIdx.x, dir = blockIdx.y, g = threadIdx.x;
+    const float* wr = (dir ? whh1 : whh0) + (int64_t)g * 128;
+    float wreg[64];
+#pragma unroll
+    for (int j = 0; j < 64; ++j) wreg[j] = wr[j];
+    for (int j = 0; j < 64; ++j) sw[j * 512 + g] = wr[64 + j];
+    if (g < 128) sh[g] = 0.f;
+    float c = 0.f;
+    __syncthreads();
+    for (int step = 0; step < S; ++step) {
+        const int s = dir ? S - 1 - step : step;
+        float acc = pre[((int64_t)dir * rows + (int64_t)b * S + s) * 512 + g];
+#pragma unroll
+        for (int j = 0; j < 64; ++j) acc = fmaf(wreg[j], sh[j], acc);
+#pragma unroll 8
+        for (int j = 0; j < 64; ++j) acc = fmaf(sw[j * 512 + g], sh[64 + j], acc);
+        sg[g] = acc;
+        __syncthreads();
+        if (g < 128) {
+            const float ig = 1.f / (1.f + expf(-sg[g]));
+            const float fg = 1.f / (1.f + expf(-sg[128 + g]));
+            const float gg = tanhf(sg[256 + g]);
+            const float og = 1.f / (1.f + expf(-sg[384 + g]));
+            c = fg * c + ig * gg;
+            const float h = og * tanhf(c);
+            sh[g] = h;
+            hout[((int64_t)b * S + s) * 256 + dir * 128 + g] = h;
+        }
+        __syncthreads();
+    }
+}
+
+// ---- [mean, unbiased std, min, max] over clusters -> fc -> sigmoid
+__global__ void __launch_bounds__(256)
+snr_head_kernel(const float* __restrict__ hout, const float* __restrict__ fcw, const float* __restrict__ fcb,
+                float* __restrict__ out, int S) {
+    __shared__ float red[8];
+    const int b = blockIdx.x, j = threadIdx.x;
+    float sum = 0.f, mn = INFINITY, mx = -INFINITY;
+    for (int s = 0; s < S; ++s) {
+        const float v = hout[((int64_t)b * S + s) * 256 + j];
+        sum += v;
+        mn = fminf(mn, v);
+        mx = fmaxf(mx, v);
+    }
+    const float mean = sum / (float)S;
+    float ss = 0.f;
+    for (int s = 0; s < S; ++s) {
+        const float d = hout[((int64_t)b * S + s) * 256 + j] - mean;
+        ss = fmaf(d, d, ss);
+    }
+    const float sd = sqrtf(ss / (float)(S - 1));  // S == 1 -> NaN, as torch.std (snrnet.py:84)
+    float acc = mean * fcw[j] + sd * fcw[256 + j] + mn * fcw[512 + j] + mx * fcw[768 + j];
+    acc = warp_sum(acc);
+    if ((j & 31) == 0) red[j >> 5] = acc;
+    __syncthreads();
+    if (j == 0) {
+        float t = fcb[0];
+        for (int i = 0; i < 8; ++i) t += red[i];
+        out[b] = 1.f / (1.f + expf(-t));
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int snrse_snrnet_num_params(void) { return kNumParams; }
+
+int snrse_snrnet_param_info(int i, char* name, int name_cap, int64_t* offset, int64_t* numel, int* transform) {
+    SNRSE_CHECK_ARG(i >= 0 && i < kNumParams, "snrnet_param_info: index out of range");
+    const int n = (int)strlen(kParams[i].name);
+    SNRSE_CHECK_ARG(n + 1 <= name_cap, "snrnet_param_info: name buffer too small");
+    memcpy(name, kParams[i].name, n + 1);
+    *offset = param_offset(i);
+    *numel = kParams[i].numel;
+    *transform = 0;
+    return SNRSE_OK;
+}
+
+int64_t snrse_snrnet_weight_bytes(void) { return param_offset(kNumParams); }
+
+// a1 [NC][32][128][8] | a2 [NC][32][64][8] | feats [NC][128] | pre [2][NC][512] | hout [NC][256]
+int64_t snrse_snrnet_workspace_bytes(int B, int T16) {
+    const int64_t nc = (int64_t)B * (T16 / 16);
+    return nc * (32768 + 16384 + 128 + 1024 + 256) * 4;
+}
+
+int snrse_snrnet_forward(const void* weights, const float* feat, float* out, int B, int T16, void* workspace,
+                         void* stream) {
+    SNRSE_CHECK_ARG(weights && feat && out && workspace, "snrnet_forward: null pointer");
+    SNRSE_CHECK_ARG(B > 0 && T16 > 0 && T16 % 16 == 0, "snrnet_forward: T must be a positive multiple of 16");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int S = T16 / 16;
+    const int64_t nc = (int64_t)B * S;
+    float* a1 = static_cast<float*>(workspace);
+    float* a2 = a1 + nc * 32768;
+    float* feats = a2 + nc * 16384;
+    float* pre = feats + nc * 128;
+    float* hout = pre + nc * 1024;
+    static bool attr_set = false;
+    if (!attr_set) {
+        SNRSE_CUDA(cudaFuncSetAttribute(snr_convt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+        SNRSE_CUDA(cudaFuncSetAttribute(snr_lstm_rec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (64 * 512 + 128 + 512) * 4));
+        attr_set = true;
+    }
+    snr_conv5_pool_kernel<<<dim3(16, (unsigned)nc), 256, 0, s>>>(feat, P(weights, 0), P(weights, 1), a1, T16);
+    SNRSE_LAUNCH_CHECK();
+    snr_conv3_pool_kernel<<<dim3(32, (unsigned)nc), 256, 0, s>>>(a1, P(weights, 2), P(weights, 3), a2);
+    SNRSE_LAUNCH_CHECK();
+    ConvtW cw;
+    for (int i = 0; i < 4; ++i) {
+        cw.w[i] = P(weights, 4 + 2 * i);
+        cw.b[i] = P(weights, 5 + 2 * i);
+    }
+    snr_convt_kernel<<<(unsigned)nc, 256, 65536, s>>>(a2, cw, feats);
+    SNRSE_LAUNCH_CHECK();
+    snr_lstm_pre_kernel<<<(unsigned)nc, 256, 0, s>>>(feats, P(weights, 12), P(weights, 14), P(weights, 15), P(weights, 16),
+                                                     P(weights, 18), P(weights, 19), pre, nc);
+    SNRSE_LAUNCH_CHECK();
+    snr_lstm_rec_kernel<<<dim3(B, 2), 512, (64 * 512 + 128 + 512) * 4, s>>>(pre, P(weights, 13), P(weights, 17), hout, S, nc);
+    SNRSE_LAUNCH_CHECK();
+    snr_head_kernel<<<B, 256, 0, s>>>(hout, P(weights, 20), P(weights, 21), out, S);
+    SNRSE_LAUNCH_CHECK();
+    return SNRSE_OK;
+}
+
+}  // extern "C"

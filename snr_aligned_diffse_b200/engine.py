@@ -1,0 +1,171 @@
+"""Host-side owner of the native NCSN++ executor: weight packing, workspace, plans, CUDA graphs.
+
+The network itself (topology, kernels, buffer plan) lives in `csrc/engine.cu`; this module only
+moves a reference-format `state_dict` into the packed device blob the executor describes and
+hands torch-owned device memory to it.
+"""
+import ctypes
+from ctypes import byref, c_int, c_int64, c_void_p, create_string_buffer
+
+import torch
+
+from . import _lib
+
+PK_RAW_F32, PK_CONV3_K_BF16, PK_CONV1_K_BF16, PK_NIN_K_BF16, PK_CONV3_TAP_F32 = range(5)
+
+DEFAULT_CONFIG = dict(nf=128, ch_mult=(1, 1, 2, 2, 2, 2, 2), num_res_blocks=2, attn_resolutions=(16,), image_size=256)
+
+FLAG_KEEP_ALL = 1     # keep every activation (debug taps)
+FLAG_SIMT_CONV = 2    # CUDA-core cross-check convolutions instead of tcgen05
+
+MODE_RAW, MODE_SEBRIDGE, MODE_NEG = 0, 1, 2
+
+
+class NCSNppEngine:
+    """One packed copy of the weights on one GPU + per-(B,F,T) launch plans."""
+
+    def __init__(self, nf=128, ch_mult=(1, 1, 2, 2, 2, 2, 2), num_res_blocks=2, attn_resolutions=(16,),
+                 image_size=256, **unused):
+        self.lib = _lib.load()
+        self.cfg = dict(nf=nf, ch_mult=tuple(ch_mult), num_res_blocks=num_res_blocks,
+                        attn_resolutions=tuple(attn_resolutions), image_size=image_size)
+        cm = (c_int * len(ch_mult))(*ch_mult)
+        ar = (c_int * max(1, len(attn_resolutions)))(*attn_resolutions)
+        h = c_void_p()
+        _lib.check(self.lib.snrse_ncsnpp_create(byref(h), nf, cm, len(ch_mult), num_res_blocks, ar,
+                                                len(attn_resolutions), image_size), "ncsnpp_create")
+        self.h = h
+        self.blob = None
+        self.device = None
+        self._ws = {}       # (B,F,T) -> (workspace tensor, flags)
+        self._graphs = {}
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                self.lib.snrse_ncsnpp_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ weights
+    def param_table(self):
+        n = self.lib.snrse_ncsnpp_num_params(self.h)
+        out = []
+        name = create_string_buffer(256)
+        kind, acc = c_int(), c_int()
+        off, rs, ko = c_int64(), c_int64(), c_int64()
+        for i in range(n):
+            _lib.check(self.lib.snrse_ncsnpp_param_info(self.h, i, name, 256, byref(kind), byref(off), byref(rs),
+                                                        byref(ko), byref(acc)), "param_info")
+            out.append(dict(name=name.value.decode(), kind=kind.value, offset=off.value, row_stride=rs.value,
+                            k_offset=ko.value, accumulate=acc.value))
+        return out
+
+    def param_shapes(self):
+        """name -> shape of the reference state-dict tensor each table entry expects (table order)."""
+        out = {}
+        dims, nd = (c_int64 * 4)(), c_int()
+        for i, p in enumerate(self.param_table()):
+            _lib.check(self.lib.snrse_ncsnpp_param_shape(self.h, i, dims, byref(nd)), "param_shape")
+            out[p["name"]] = tuple(int(dims[j]) for j in range(nd.value))
+        return out
+
+    @property
+    def weight_bytes(self):
+        return int(self.lib.snrse_ncsnpp_weight_bytes(self.h))
+
+    def pack_state_dict(self, sd):
+        """Reference state dict (fp32, any device) -> packed host blob (uint8 tensor)."""
+        blob = torch.zeros(self.weight_bytes, dtype=torch.uint8)
+        f32 = blob.view(torch.float32)
+        b16 = blob.view(torch.bfloat16)
+        for p in self.param_table():
+            if p["name"] not in sd:
+                raise KeyError(f"state dict lacks {p['name']}")
+            w = sd[p["name"]].detach().to("cpu", torch.float32)
+            k, off = p["kind"], p["offset"]
+            if k == PK_RAW_F32:
+                flat = w.reshape(-1)
+                dst = f32[off // 4: off // 4 + flat.numel()]
+                if p["accumulate"]:
+                    dst += flat
+                else:
+                    dst.copy_(flat)
+                continue
+            if k == PK_CONV3_TAP_F32:
+                flat = w.permute(0, 2, 3, 1).reshape(-1)
+                f32[off // 4: off // 4 + flat.numel()].copy_(flat)
+                continue
+            if k == PK_CONV3_K_BF16:
+                rows = w.permute(0, 2, 3, 1).reshape(w.shape[0], -1)       # [cout][(r,s,cin)]
+            elif k == PK_CONV1_K_BF16:
+                rows = w.reshape(w.shape[0], w.shape[1])                    # [cout][cin]
+            elif k == PK_NIN_K_BF16:
+                rows = w.t()                                               # W[in,out] -> [out][in]
+            else:
+                raise ValueError(f"unknown pack kind {k}")
+            n, kk = rows.shape
+            rs, ko = p["row_stride"], p["k_offset"]
+            dst = b16[off // 2: off // 2 + n * rs].view(n, rs)
+            dst[:, ko:ko + kk].copy_(rows.to(torch.bfloat16))
+        return blob
+
+    def load_state_dict(self, sd, device="cuda"):
+        _lib.require_device()
+        self.device = torch.device(device)
+        self.blob = self.pack_state_dict(sd).to(self.device)
+        _lib.check(self.lib.snrse_ncsnpp_set_weights(self.h, _lib.ptr(self.blob)), "set_weights")
+        self._ws.clear()
+        self._graphs.clear()
+        return self
+
+    # ------------------------------------------------------------------ plans
+    def workspace_bytes(self, B, F, T, flags=0):
+        n = int(self.lib.snrse_ncsnpp_plan_bytes(self.h, B, F, T, flags))
+        if n < 0:
+            _lib.check(1, "plan")
+        return n
+
+    def prepare(self, B, F, T, flags=0):
+        key = (B, F, T)
+        cur = self._ws.get(key)
+        if cur is not None and cur[1] == flags:
+            return
+        if self.blob is None:
+            raise RuntimeError("load_state_dict() first")
+        n = self.workspace_bytes(B, F, T, flags)
+        ws = torch.empty(n + 1024, dtype=torch.uint8, device=self.device)
+        base = ws.data_ptr()
+        aligned = (base + 1023) // 1024 * 1024
+        _lib.check(self.lib.snrse_ncsnpp_plan_bind(self.h, B, F, T, c_void_p(aligned), n), "plan_bind")
+        self._ws[key] = (ws, flags)
+        self._graphs = {k: v for k, v in self._graphs.items() if k[:3] != key}
+
+    def forward(self, x, y, t, mode=MODE_RAW, out=None, flags=0):
+        """x, y: complex64 [B,F,T] (or [B,1,F,T]); t: float32 [B].  Enqueues on the current stream."""
+        assert x.is_cuda and x.dtype == torch.complex64 and y.dtype == torch.complex64
+        shape = x.shape
+        B, F, T = shape[0], shape[-2], shape[-1]
+        self.prepare(B, F, T, flags)
+        x = x.contiguous()
+        y = y.contiguous()
+        t = t.to(torch.float32).reshape(-1).contiguous()
+        assert t.numel() == B
+        if out is None:
+            out = torch.empty_like(x)
+        _lib.check(self.lib.snrse_ncsnpp_forward(self.h, B, F, T, _lib.ptr(x), _lib.ptr(y), _lib.ptr(t), _lib.ptr(out),
+                                                 mode, _lib.stream_ptr()), "ncsnpp_forward")
+        return out
+
+    def read_tap(self, B, F, T, module_idx):
+        dims = (c_int64 * 4)()
+        cap = B * 512 * F * T
+        buf = torch.empty(cap, dtype=torch.float32, device=self.device)
+        _lib.check(self.lib.snrse_ncsnpp_read_tap(self.h, B, F, T, module_idx, _lib.ptr(buf), cap, dims,
+                                                  _lib.stream_ptr()), "read_tap")
+        b, c, h, w = (int(d) for d in dims)
+        return buf[: b * c * h * w].view(b, c, h, w).clone()
+
+    def num_launch_groups(self, B, F, T):
+        return int(self.lib.snrse_ncsnpp_num_launch_groups(self.h, B, F, T))
