@@ -46,6 +46,8 @@ int snrse_stft(const float* wave, const int* len, const float* scale, int scale_
 int64_t snrse_istft_workspace_bytes(int B, int tpad);
 int snrse_istft(const void* spec, const int* len, const float* scale, float* wave, void* workspace, int B, int lstride,
                 int tpad, int transform, float alpha, float beta, void* stream);
+/* stand-alone spec_fwd (inverse=0) / spec_back (inverse=1) on n complex64 values (data_module.py:241-267) */
+int snrse_spec_transform(const void* in, void* out, int64_t n, int inverse, float alpha, float beta, void* stream);
 /* max|y| per utterance (model.py:715,726) */
 int snrse_absmax(const float* wave, const int* len, int B, int lstride, float* out, void* stream);
 

@@ -287,7 +287,8 @@ int conv_gemm_make_plan(ConvGemmPlan* p, const ActView* a0, int taps0, const Act
 int conv_gemm_launch(const ConvGemmPlan* p, cudaStream_t s) {
     static bool attr_set = false;
     if (!attr_set) {
-        SNRSE_CUDA(cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        // opt-in limit is 227 KB per block INCLUDING the kernel's static shared memory (barriers)
+        SNRSE_CUDA(cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr_set = true;
     }
     GemmArgs g;

@@ -191,7 +191,40 @@ absmax_kernel(const float* __restrict__ wave, const int* __restrict__ len, int l
     }
 }
 
+// stand-alone spec_fwd / spec_back (data_module.py:241-267) for callers that hold a raw STFT
+__global__ void __launch_bounds__(256)
+spec_transform_kernel(const float2* __restrict__ in, float2* __restrict__ out, int64_t n, int inverse, float alpha,
+                      float beta) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float2 z = in[i];
+    if (inverse) {
+        z.x /= beta;
+        z.y /= beta;
+        const float mag = sqrtf(z.x * z.x + z.y * z.y);
+        float g = 0.f;
+        if (mag > 0.f) g = (alpha == 0.5f) ? mag : powf(mag, 1.0f / alpha - 1.0f);
+        if (alpha == 1.0f) g = 1.0f;
+        z.x *= g;
+        z.y *= g;
+    } else {
+        const float mag = sqrtf(z.x * z.x + z.y * z.y);
+        float g = 0.f;
+        if (mag > 0.f) g = (alpha == 0.5f) ? beta / sqrtf(mag) : beta * powf(mag, alpha - 1.0f);
+        if (alpha == 1.0f) g = beta;
+        z.x *= g;
+        z.y *= g;
+    }
+    out[i] = z;
+}
+
 }  // namespace
+
+int spec_transform_launch(const float2* in, float2* out, int64_t n, int inverse, float alpha, float beta, cudaStream_t s) {
+    spec_transform_kernel<<<(unsigned)cdiv64(n, 256), 256, 0, s>>>(in, out, n, inverse, alpha, beta);
+    SNRSE_LAUNCH_CHECK();
+    return SNRSE_OK;
+}
 
 int stft_launch(const float* wave, const int* len, const float* scale, int scale_is_divisor, float* out, int B,
                 int lstride, int tpad, int transform, float alpha, float beta, int planar, cudaStream_t s) {
