@@ -29,6 +29,7 @@ extern "C" {
 int snrse_version(void);
 const char* snrse_last_error(void);       /* thread-local message of the last failing call */
 int snrse_device_check(void);             /* 0 iff the current device is compute capability 10.x */
+long long snrse_launch_count(void);       /* kernels launched by this library since it was loaded */
 
 /* ---------------------------------------------------------------- signal front / back end ------
  * snrse_stft: SpecsDataModule.stft + spec_fwd + pad_spec (data_module.py:241-254,291-293;
@@ -93,6 +94,10 @@ int snrse_ncsnpp_plan_bind(void* handle, int B, int F, int T, void* workspace, i
 int snrse_ncsnpp_forward(void* handle, int B, int F, int T, const void* x, const void* y, const float* t, void* out,
                          int mode, void* stream);
 int snrse_ncsnpp_num_launch_groups(void* handle, int B, int F, int T);
+/* measurement only: eager forward with CUDA events between launch groups (kind 1 = implicit-GEMM conv) */
+int snrse_ncsnpp_profile_forward(void* handle, int B, int F, int T, const void* x, const void* y, const float* t,
+                                 void* out, int mode, void* stream, int cap, int* kinds, double* flops, double* bytes,
+                                 float* ms, int* n_groups);
 int snrse_ncsnpp_read_tap(void* handle, int B, int F, int T, int module_idx, float* out, int64_t cap_elems,
                           int64_t* dims, void* stream);
 
@@ -120,6 +125,7 @@ int snrse_attention_nhwc(const void* q, const void* k, const void* v, float* sco
  * out: f32 [B] = noise/(speech+noise).  weights: packed blob, see snrse_snrnet_param_info. */
 int snrse_snrnet_num_params(void);
 int snrse_snrnet_param_info(int i, char* name, int name_cap, int64_t* offset, int64_t* numel, int* transform);
+int snrse_snrnet_param_shape(int i, int64_t* dims, int* ndim);
 int64_t snrse_snrnet_weight_bytes(void);
 int64_t snrse_snrnet_workspace_bytes(int B, int T16);
 int snrse_snrnet_forward(const void* weights, const float* feat, float* out, int B, int T16, void* workspace,

@@ -20,6 +20,7 @@ PROTOTYPES = {
     "snrse_version": (i32, []),
     "snrse_last_error": (c_char_p, []),
     "snrse_device_check": (i32, []),
+    "snrse_launch_count": (ctypes.c_longlong, []),
     "snrse_stft": (i32, [vp, vp, vp, i32, vp, i32, i32, i32, i32, f32, f32, i32, vp]),
     "snrse_istft_workspace_bytes": (i64, [i32, i32]),
     "snrse_istft": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, f32, vp]),
@@ -40,6 +41,7 @@ PROTOTYPES = {
     "snrse_ncsnpp_plan_bind": (i32, [vp, i32, i32, i32, vp, i64]),
     "snrse_ncsnpp_forward": (i32, [vp, i32, i32, i32, vp, vp, vp, vp, i32, vp]),
     "snrse_ncsnpp_num_launch_groups": (i32, [vp, i32, i32, i32]),
+    "snrse_ncsnpp_profile_forward": (i32, [vp, i32, i32, i32, vp, vp, vp, vp, i32, vp, i32, POINTER(i32), POINTER(f64), POINTER(f64), POINTER(f32), POINTER(i32)]),
     "snrse_ncsnpp_read_tap": (i32, [vp, i32, i32, i32, i32, vp, i64, POINTER(i64), vp]),
     "snrse_conv_nhwc": (i32, [vp, i32, i32, vp, i32, vp, i32, vp, vp, i32, vp, f32, vp, i32, i32, i32, i32, vp]),
     "snrse_groupnorm_workspace_bytes": (i64, [i32]),
@@ -49,6 +51,7 @@ PROTOTYPES = {
     "snrse_attention_nhwc": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, vp]),
     "snrse_snrnet_num_params": (i32, []),
     "snrse_snrnet_param_info": (i32, [i32, c_char_p, i32, POINTER(i64), POINTER(i64), POINTER(i32)]),
+    "snrse_snrnet_param_shape": (i32, [i32, POINTER(i64), POINTER(i32)]),
     "snrse_snrnet_weight_bytes": (i64, []),
     "snrse_snrnet_workspace_bytes": (i64, [i32, i32]),
     "snrse_snrnet_forward": (i32, [vp, vp, vp, i32, i32, vp, vp]),
@@ -79,9 +82,15 @@ def check(status, what=""):
         raise RuntimeError(f"libsnrse_b200 {what} failed (status {status}): {msg}")
 
 
+_device_ok = False
+
+
 def require_device():
-    """Raise unless the current CUDA device is a B200-class (sm_100) GPU."""
-    check(load().snrse_device_check(), "device check")
+    """Raise unless the current CUDA device is a B200-class (sm_100) GPU (checked once per process)."""
+    global _device_ok
+    if not _device_ok:
+        check(load().snrse_device_check(), "device check")
+        _device_ok = True
 
 
 def ptr(t):

@@ -7,6 +7,7 @@
 #include "kernels.h"
 
 static thread_local char g_err[512] = "";
+long long g_snrse_launches = 0;
 
 void snrse_set_error(const char* fmt, ...) {
     va_list ap;
@@ -27,6 +28,7 @@ static ActView mk_view(const void* p, int B, int H, int W, int C, int ld) {
 extern "C" {
 
 int snrse_version(void) { return 100; }
+long long snrse_launch_count(void) { return g_snrse_launches; }
 const char* snrse_last_error(void) { return g_err; }
 
 // 0 when the current device is a Blackwell B200-class GPU (compute capability 10.x); the kernels are sm_100a-only.

@@ -33,7 +33,13 @@ void snrse_set_error(const char* fmt, ...);
         }                                                                                     \
     } while (0)
 
-#define SNRSE_LAUNCH_CHECK() SNRSE_CUDA(cudaGetLastError())
+// every kernel launch in the library goes through this macro: it also counts launches (snrse_launch_count)
+extern long long g_snrse_launches;
+#define SNRSE_LAUNCH_CHECK()          \
+    do {                              \
+        ++g_snrse_launches;           \
+        SNRSE_CUDA(cudaGetLastError()); \
+    } while (0)
 
 #define SNRSE_TRY(call)              \
     do {                             \

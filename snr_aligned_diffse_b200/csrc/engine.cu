@@ -80,6 +80,14 @@ struct Plan {
     float2* out_ptr = nullptr;
     int mode = 0;
 
+    // per launch group: kind (LK_*), algorithmic flops and bytes -- read by the profiling entry point
+    struct Info { int kind; double flops, bytes; };
+    std::vector<Info> info;
+    void add(int kind, double flops, double bytes, std::function<int(cudaStream_t)> f) {
+        launches.push_back(std::move(f));
+        info.push_back(Info{kind, flops, bytes});
+    }
+
     int root(int id) const {
         while (tens[id].parent >= 0) id = tens[id].parent;
         return id;
@@ -303,6 +311,7 @@ int build_topology(Engine& e, int image_size) {
 // current step, (c) registers a builder that, once buffers are placed, appends the launch closures.
 // ------------------------------------------------------------------------------------------------
 const float INV_SQRT2 = 0.70710678118654752440f;
+enum { LK_OTHER = 0, LK_GEMM = 1, LK_GN = 2, LK_FIR = 3, LK_ATTN = 4, LK_THIN = 5, LK_HEAD = 6 };
 
 int rec_gemm(Plan& P, int a0, int taps0, int a1, int64_t w_off, int n_rows, int64_t bias_off, int tb_row, int res,
              float scale, int out) {
@@ -327,7 +336,8 @@ int rec_gemm(Plan& P, int a0, int taps0, int a1, int64_t w_off, int n_rows, int6
                 const bf16* w = e.wb(w_off) + (int64_t)n0 * ktot;
                 ActView r2 = vres;
                 if (res >= 0) r2.ptr += n0;
-                p.launches.push_back([=](cudaStream_t s) {
+                const double px1 = (double)va0.B * va0.H * va0.W;
+                p.add(LK_GEMM, 2.0 * px1 * nn * (double)ktot, 0.0, [=](cudaStream_t s) {
                     return conv_simt_launch(&va0, taps0, a1 >= 0 ? &va1 : nullptr, w, nn, bias ? bias + n0 : nullptr,
                                             tb ? tb + n0 : nullptr, tb_stride, res >= 0 ? &r2 : nullptr, scale,
                                             vout.ptr + n0, vout.ld, s);
@@ -338,7 +348,11 @@ int rec_gemm(Plan& P, int a0, int taps0, int a1, int64_t w_off, int n_rows, int6
         ConvGemmPlan g;
         SNRSE_TRY(conv_gemm_make_plan(&g, &va0, taps0, a1 >= 0 ? &va1 : nullptr, e.wb(w_off), n_rows, 0, 0, bias, tb,
                                       tb_stride, res >= 0 ? &vres : nullptr, scale, vout.ptr, vout.ld, 0));
-        p.launches.push_back([g](cudaStream_t s) { return conv_gemm_launch(&g, s); });
+        const double px = (double)va0.B * va0.H * va0.W;
+        const double kt = (double)taps0 * va0.C + (a1 >= 0 ? va1.C : 0);
+        // algorithmic bytes: each operand / result once (bf16), weights once
+        const double by = 2.0 * (px * (va0.C + (a1 >= 0 ? va1.C : 0) + n_rows + (res >= 0 ? n_rows : 0)) + kt * n_rows);
+        p.add(LK_GEMM, 2.0 * px * n_rows * kt, by, [g](cudaStream_t s) { return conv_gemm_launch(&g, s); });
         return SNRSE_OK;
     });
     return out;
@@ -361,7 +375,8 @@ int rec_gn(Plan& P, int x, int64_t g_off, int64_t b_off, int silu) {
         const float* gamma = e.wf(g_off);
         const float* beta = e.wf(b_off);
         const int64_t cnt = hw * (vx.C / 32);
-        p.launches.push_back([=](cudaStream_t s) {
+        const double el = (double)vx.B * hw * vx.C;
+        p.add(LK_GN, 0.0, 2.0 * el * 3, [=](cudaStream_t s) {   // read x twice (stats, apply) + write once, bf16
             SNRSE_TRY(gn_stats_launch(&vx, partial, chunks, s));
             SNRSE_TRY(gn_finalize_launch(partial, chunks, vx.B, vx.C, cnt, gamma, beta, 1e-6f, scsh, s));
             return gn_apply_launch(&vx, scsh, silu, &vo, s);
@@ -378,7 +393,8 @@ int rec_fir(Plan& P, int x, int up) {
     P.step++;
     P.builders.push_back([=](Plan& p) -> int {
         const ActView vx = p.view(x), vo = p.view(out);
-        p.launches.push_back([=](cudaStream_t s) { return up ? fir_up2_launch(&vx, &vo, s) : fir_down2_launch(&vx, &vo, s); });
+        const double el = (double)vx.B * vx.H * vx.W * vx.C + (double)vo.B * vo.H * vo.W * vo.C;
+        p.add(LK_FIR, 0.0, 2.0 * el, [=](cudaStream_t s) { return up ? fir_up2_launch(&vx, &vo, s) : fir_down2_launch(&vx, &vo, s); });
         return SNRSE_OK;
     });
     return out;
@@ -416,7 +432,8 @@ int rec_attn(Plan& P, const Mod& m, int x) {
         k.ptr += c;
         v.ptr += 2 * c;
         float* scores = p.fptr(sc);
-        p.launches.push_back([=](cudaStream_t s) { return attention_launch(&q, &k, &v, scores, &vo, s); });
+        const double nn = (double)q.H * q.W;
+        p.add(LK_ATTN, 4.0 * q.B * nn * nn * c, 2.0 * q.B * nn * c * 4, [=](cudaStream_t s) { return attention_launch(&q, &k, &v, scores, &vo, s); });
         return SNRSE_OK;
     });
     const int out = P.new_t(tx.B, tx.H, tx.W, c, 2);
@@ -445,7 +462,7 @@ int record_plan(Plan& P) {
         float* scr = p.fptr(p.t_tscr);
         const int64_t n = (int64_t)p.F * p.T;
         const Mod mf = e.mods[0], m1 = e.mods[1], m2 = e.mods[2];
-        p.launches.push_back([=, &e](cudaStream_t s) {
+        p.add(LK_HEAD, 0.0, (double)p.B * n * 32, [=, &e](cudaStream_t s) {
             SNRSE_TRY(pack_input_launch(pp->x_ptr, pp->y_ptr, x4, pp->B, n, s));
             return temb_launch(pp->t_ptr, pp->B, e.nf, e.wf(mf.o[0]), e.wf(m1.o[0]), e.wf(m1.o[1]), e.wf(m2.o[0]),
                                e.wf(m2.o[1]), e.wf(e.dense_w_off), e.wf(e.dense_b_off), e.dense_rows, scr, tb, s);
@@ -464,7 +481,8 @@ int record_plan(Plan& P) {
             Engine& e = *p.eng;
             const ActView vo = p.view(out);
             const float* x4 = p.fptr(p.t_x4);
-            p.launches.push_back([=, &e](cudaStream_t s) { return conv_in4_launch(x4, e.wf(m.o[0]), e.wf(m.o[1]), &vo, s); });
+            const double px = (double)vo.B * vo.H * vo.W;
+            p.add(LK_THIN, 2.0 * px * 36 * vo.C, px * (16 + 2.0 * vo.C), [=, &e](cudaStream_t s) { return conv_in4_launch(x4, e.wf(m.o[0]), e.wf(m.o[1]), &vo, s); });
             return SNRSE_OK;
         });
         P.taps[(int)mi] = h;
@@ -497,7 +515,8 @@ int record_plan(Plan& P) {
                 const float* sp = p.fptr(src);
                 float* dp = p.fptr(np);
                 const ActView vh = p.view(hin), vo = p.view(out);
-                p.launches.push_back([=, &e](cudaStream_t s) {
+                const double px = (double)vh.B * vh.H * vh.W;
+                p.add(LK_THIN, 2.0 * px * 4 * vh.C, px * (4.0 * vh.C + 16 + 64), [=, &e](cudaStream_t s) {
                     SNRSE_TRY(fir_down2_f4_launch(sp, dp, vh.B, ih, iw, s));
                     return combine4_launch(dp, &vh, e.wf(m.o[0]), e.wf(m.o[1]), &vo, s);
                 });
@@ -542,7 +561,8 @@ int record_plan(Plan& P) {
                 float* dst = p.fptr(np);
                 float* upp = up >= 0 ? p.fptr(up) : nullptr;
                 const float* pv = prev >= 0 ? p.fptr(prev) : nullptr;
-                p.launches.push_back([=, &e](cudaStream_t s) {
+                const double px = (double)va.B * va.H * va.W;
+                p.add(LK_THIN, 2.0 * px * 36 * va.C, px * (2.0 * va.C + 16 + (pv ? 20 : 0)), [=, &e](cudaStream_t s) {
                     if (pv) SNRSE_TRY(fir_up2_f4_launch(pv, upp, va.B, va.H / 2, va.W / 2, s));
                     return conv_out4_launch(&va, e.wf(mc.o[0]), e.wf(mc.o[1]), upp, dst, s);
                 });
@@ -570,7 +590,7 @@ int record_plan(Plan& P) {
         Plan* pp = &p;
         const float* pf = p.fptr(pyr);
         const int64_t n = (int64_t)p.F * p.T;
-        p.launches.push_back([=, &e](cudaStream_t s) {
+        p.add(LK_HEAD, 0.0, (double)p.B * n * 32, [=, &e](cudaStream_t s) {
             return final_launch(pf, pp->t_ptr, e.wf(e.out_w_off), e.wf(e.out_b_off), pp->x_ptr, pp->out_ptr, pp->B, n,
                                 pp->mode, s);
         });
@@ -704,6 +724,7 @@ int snrse_ncsnpp_set_weights(void* handle, const void* device_blob) {
     e->blob = static_cast<const uint8_t*>(device_blob);
     for (auto& kv : e->plans) {  // launch closures captured weight pointers: rebuild lazily
         kv.second->launches.clear();
+        kv.second->info.clear();
         kv.second->ws = nullptr;
     }
     return SNRSE_OK;
@@ -748,6 +769,7 @@ int snrse_ncsnpp_plan_bind(void* handle, int B, int F, int T, void* workspace, i
     SNRSE_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 1023) == 0, "plan_bind: workspace must be 1024-byte aligned");
     p->ws = static_cast<uint8_t*>(workspace);
     p->launches.clear();
+    p->info.clear();
     for (auto& b : p->builders) SNRSE_TRY(b(*p));
     return SNRSE_OK;
 }
@@ -766,6 +788,42 @@ int snrse_ncsnpp_forward(void* handle, int B, int F, int T, const void* x, const
     p->mode = mode;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     for (auto& l : p->launches) SNRSE_TRY(l(s));
+    return SNRSE_OK;
+}
+
+// Eager forward with a CUDA event between launch groups: per group kind (0 other, 1 implicit-GEMM conv,
+// 2 GroupNorm+SiLU, 3 FIR, 4 attention core, 5 thin convs, 6 pack/temb/head), algorithmic flops / bytes and
+// measured milliseconds on `stream`.  Synchronises the stream (measurement only; not graph-capturable).
+int snrse_ncsnpp_profile_forward(void* handle, int B, int F, int T, const void* x, const void* y, const float* t,
+                                 void* out, int mode, void* stream, int cap, int* kinds, double* flops, double* bytes,
+                                 float* ms, int* n_groups) {
+    Engine* e = static_cast<Engine*>(handle);
+    Plan* p = e ? find_plan(e, B, F, T) : nullptr;
+    SNRSE_CHECK_ARG(p && p->ws && !p->launches.empty(), "profile_forward: no bound plan");
+    const int n = (int)p->launches.size();
+    SNRSE_CHECK_ARG(cap >= n, "profile_forward: arrays too small (%d groups)", n);
+    p->x_ptr = static_cast<const float2*>(x);
+    p->y_ptr = static_cast<const float2*>(y);
+    p->t_ptr = t;
+    p->out_ptr = static_cast<float2*>(out);
+    p->mode = mode;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    std::vector<cudaEvent_t> ev(n + 1);
+    for (auto& v : ev) SNRSE_CUDA(cudaEventCreate(&v));
+    SNRSE_CUDA(cudaEventRecord(ev[0], s));
+    for (int i = 0; i < n; ++i) {
+        SNRSE_TRY(p->launches[i](s));
+        SNRSE_CUDA(cudaEventRecord(ev[i + 1], s));
+    }
+    SNRSE_CUDA(cudaStreamSynchronize(s));
+    for (int i = 0; i < n; ++i) {
+        SNRSE_CUDA(cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]));
+        kinds[i] = p->info[i].kind;
+        flops[i] = p->info[i].flops;
+        bytes[i] = p->info[i].bytes;
+    }
+    for (auto& v : ev) cudaEventDestroy(v);
+    *n_groups = n;
     return SNRSE_OK;
 }
 

@@ -10,20 +10,22 @@ namespace {
 
 struct SnrParam {
     const char* name;
+    int ndim;
+    int64_t dims[4];
     int64_t numel;
 };
 const SnrParam kParams[] = {
-    {"dnn.conv5x5_1.weight", 32 * 2 * 25},        {"dnn.conv5x5_1.bias", 32},
-    {"dnn.conv3x3_1.weight", 32 * 32 * 9},        {"dnn.conv3x3_1.bias", 32},
-    {"dnn.convt_1.weight", 32 * 32 * 64 * 1},     {"dnn.convt_1.bias", 32},
-    {"dnn.convt_2.weight", 32 * 32 * 64 * 2},     {"dnn.convt_2.bias", 32},
-    {"dnn.convt_3.weight", 32 * 32 * 64 * 4},     {"dnn.convt_3.bias", 32},
-    {"dnn.convt_4.weight", 32 * 32 * 64 * 8},     {"dnn.convt_4.bias", 32},
-    {"dnn.blstm.weight_ih_l0", 512 * 128},        {"dnn.blstm.weight_hh_l0", 512 * 128},
-    {"dnn.blstm.bias_ih_l0", 512},                {"dnn.blstm.bias_hh_l0", 512},
-    {"dnn.blstm.weight_ih_l0_reverse", 512 * 128}, {"dnn.blstm.weight_hh_l0_reverse", 512 * 128},
-    {"dnn.blstm.bias_ih_l0_reverse", 512},        {"dnn.blstm.bias_hh_l0_reverse", 512},
-    {"dnn.fc.weight", 1024},                      {"dnn.fc.bias", 1},
+    {"dnn.conv5x5_1.weight", 4, {32, 2, 5, 5}, 32 * 2 * 25},          {"dnn.conv5x5_1.bias", 1, {32, 1, 1, 1}, 32},
+    {"dnn.conv3x3_1.weight", 4, {32, 32, 3, 3}, 32 * 32 * 9},         {"dnn.conv3x3_1.bias", 1, {32, 1, 1, 1}, 32},
+    {"dnn.convt_1.weight", 4, {32, 32, 64, 1}, 32 * 32 * 64 * 1},     {"dnn.convt_1.bias", 1, {32, 1, 1, 1}, 32},
+    {"dnn.convt_2.weight", 4, {32, 32, 64, 2}, 32 * 32 * 64 * 2},     {"dnn.convt_2.bias", 1, {32, 1, 1, 1}, 32},
+    {"dnn.convt_3.weight", 4, {32, 32, 64, 4}, 32 * 32 * 64 * 4},     {"dnn.convt_3.bias", 1, {32, 1, 1, 1}, 32},
+    {"dnn.convt_4.weight", 4, {32, 32, 64, 8}, 32 * 32 * 64 * 8},     {"dnn.convt_4.bias", 1, {32, 1, 1, 1}, 32},
+    {"dnn.blstm.weight_ih_l0", 2, {512, 128, 1, 1}, 512 * 128},       {"dnn.blstm.weight_hh_l0", 2, {512, 128, 1, 1}, 512 * 128},
+    {"dnn.blstm.bias_ih_l0", 1, {512, 1, 1, 1}, 512},                 {"dnn.blstm.bias_hh_l0", 1, {512, 1, 1, 1}, 512},
+    {"dnn.blstm.weight_ih_l0_reverse", 2, {512, 128, 1, 1}, 512 * 128}, {"dnn.blstm.weight_hh_l0_reverse", 2, {512, 128, 1, 1}, 512 * 128},
+    {"dnn.blstm.bias_ih_l0_reverse", 1, {512, 1, 1, 1}, 512},         {"dnn.blstm.bias_hh_l0_reverse", 1, {512, 1, 1, 1}, 512},
+    {"dnn.fc.weight", 2, {1, 1024, 1, 1}, 1024},                      {"dnn.fc.bias", 1, {1, 1, 1, 1}, 1},
 };
 constexpr int kNumParams = sizeof(kParams) / sizeof(kParams[0]);
 
@@ -253,6 +255,13 @@ int snrse_snrnet_param_info(int i, char* name, int name_cap, int64_t* offset, in
     *offset = param_offset(i);
     *numel = kParams[i].numel;
     *transform = 0;
+    return SNRSE_OK;
+}
+
+int snrse_snrnet_param_shape(int i, int64_t* dims, int* ndim) {
+    SNRSE_CHECK_ARG(i >= 0 && i < kNumParams, "snrnet_param_shape: index out of range");
+    for (int j = 0; j < 4; ++j) dims[j] = kParams[i].dims[j];
+    *ndim = kParams[i].ndim;
     return SNRSE_OK;
 }
 

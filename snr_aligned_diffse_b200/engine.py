@@ -167,5 +167,21 @@ class NCSNppEngine:
         b, c, h, w = (int(d) for d in dims)
         return buf[: b * c * h * w].view(b, c, h, w).clone()
 
+    def profile_forward(self, x, y, t, mode=MODE_RAW):
+        """Eager forward with CUDA events between launch groups (measurement only).
+        Returns a list of dict(kind, flops, bytes, ms); kind 1 = implicit-GEMM convolution."""
+        from ctypes import c_double, c_float
+        B, F, T = x.shape[0], x.shape[-2], x.shape[-1]
+        self.prepare(B, F, T, 0)
+        n = self.num_launch_groups(B, F, T)
+        kinds, fl, by, ms = (c_int * n)(), (c_double * n)(), (c_double * n)(), (c_float * n)()
+        cnt = c_int()
+        out = torch.empty_like(x)
+        t = t.to(torch.float32).reshape(-1).contiguous()
+        _lib.check(self.lib.snrse_ncsnpp_profile_forward(self.h, B, F, T, _lib.ptr(x.contiguous()), _lib.ptr(y.contiguous()),
+                                                         _lib.ptr(t), _lib.ptr(out), mode, _lib.stream_ptr(), n, kinds,
+                                                         fl, by, ms, byref(cnt)), "profile_forward")
+        return [dict(kind=kinds[i], flops=fl[i], bytes=by[i], ms=ms[i]) for i in range(cnt.value)]
+
     def num_launch_groups(self, B, F, T):
         return int(self.lib.snrse_ncsnpp_num_launch_groups(self.h, B, F, T))

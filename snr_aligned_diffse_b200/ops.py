@@ -169,8 +169,14 @@ class SNRNetEngine:
         off, numel, tr = c_int64(), c_int64(), c_int()
         for i in range(self.lib.snrse_snrnet_num_params()):
             _lib.check(self.lib.snrse_snrnet_param_info(i, name, 256, byref(off), byref(numel), byref(tr)), "snrnet_param_info")
-            out.append(dict(name=name.value.decode(), offset=off.value, numel=numel.value))
+            dims, nd = (c_int64 * 4)(), c_int()
+            _lib.check(self.lib.snrse_snrnet_param_shape(i, dims, byref(nd)), "snrnet_param_shape")
+            out.append(dict(name=name.value.decode(), offset=off.value, numel=numel.value,
+                            shape=tuple(int(dims[j]) for j in range(nd.value))))
         return out
+
+    def param_shapes(self):
+        return {p["name"]: p["shape"] for p in self.param_table()}
 
     def load_state_dict(self, sd, device="cuda"):
         _lib.require_device()

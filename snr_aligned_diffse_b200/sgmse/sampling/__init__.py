@@ -1,0 +1,94 @@
+"""Sampler factories (mirror of sgmse-bbed/sgmse/sampling/__init__.py:28-171)."""
+import numpy as np
+import torch
+from scipy import integrate
+
+from .correctors import Corrector, CorrectorRegistry
+from .predictors import Predictor, PredictorRegistry, ReverseDiffusionPredictor
+
+__all__ = ['PredictorRegistry', 'CorrectorRegistry', 'Predictor', 'Corrector', 'get_pc_sampler', 'get_ode_sampler']
+
+
+def to_flattened_numpy(x):
+    return x.detach().cpu().numpy().reshape((-1,))
+
+
+def from_flattened_numpy(x, shape):
+    return torch.from_numpy(x.reshape(shape))
+
+
+def timesteps_space(sdeT, sdeN, eps, device, type='linear'):
+    return torch.linspace(sdeT, eps, sdeN, device=device)
+
+
+def get_pc_sampler(predictor_name, corrector_name, sde, score_fn, Y, Y_prior=None, denoise=True, eps=3e-2, snr=0.1,
+                   corrector_steps=1, probability_flow: bool = False, intermediate=False, timestep_type=None, **kwargs):
+    """Predictor-corrector sampler; returns a zero-argument callable -> (sample, nfe)."""
+    predictor_cls = PredictorRegistry.get_by_name(predictor_name)
+    corrector_cls = CorrectorRegistry.get_by_name(corrector_name)
+    predictor = predictor_cls(sde, score_fn, probability_flow=probability_flow)
+    corrector = corrector_cls(sde, score_fn, snr=snr, n_steps=corrector_steps)
+    if intermediate:
+        raise NotImplementedError("intermediate=True returns an undefined name in the reference "
+                                  "(sampling/__init__.py:77-78) and is not supported")
+    if not Y.is_cuda:
+        Y = Y.cuda()
+
+    def pc_sampler(Y_prior=Y_prior, timestep_type=timestep_type):
+        with torch.no_grad():
+            if Y_prior is None:
+                Y_prior = Y
+            xt, _ = sde.prior_sampling(Y_prior.shape, Y_prior if Y_prior.is_cuda else Y_prior.cuda())
+            # time grid on the host: every step's scalars are known before the first launch
+            timesteps = torch.linspace(sde.T, eps, sde.N)
+            xt_mean = xt
+            B = Y.shape[0]
+            for i in range(len(timesteps)):
+                t = timesteps[i]
+                stepsize = t - timesteps[i + 1] if i != len(timesteps) - 1 else timesteps[-1]
+                vec_t = torch.full((B,), float(t), dtype=torch.float32, device=Y.device)
+                xt, xt_mean = corrector.update_fn(xt, vec_t, Y)
+                xt, xt_mean = predictor.update_fn(xt, vec_t, Y, stepsize)
+            x_result = xt_mean if denoise else xt
+            ns = len(timesteps) * (corrector.n_steps + 1)
+            return x_result, ns
+
+    return pc_sampler
+
+
+def get_ode_sampler(sde, score_fn, y, Y_prior=None, inverse_scaler=None, denoise=True, rtol=1e-5, atol=1e-5,
+                    timestep_type=None, method='RK45', eps=3e-2, device='cuda', **kwargs):
+    """Probability-flow ODE sampler driven by scipy's RK45, host round trip per RHS evaluation as in the
+    reference (sampling/__init__.py:95-171)."""
+    if not y.is_cuda:
+        y = y.cuda()
+    predictor = ReverseDiffusionPredictor(sde, score_fn, probability_flow=False)
+    rsde = sde.reverse(score_fn, probability_flow=True)
+
+    def denoise_update_fn(x):
+        vec_eps = torch.ones(x.shape[0], device=x.device) * eps
+        _, x = predictor.update_fn(x, vec_eps, y, 0.03)
+        return x
+
+    def ode_sampler(z=None, Y_prior=Y_prior, **kw):
+        with torch.no_grad():
+            if Y_prior is None:
+                Y_prior = y
+            xt, _ = sde.prior_sampling(Y_prior.shape, Y_prior if Y_prior.is_cuda else Y_prior.cuda())
+
+            def ode_func(t, x):
+                x = from_flattened_numpy(x, y.shape).to(device).type(torch.complex64)
+                vec_t = torch.ones(y.shape[0], device=x.device) * t
+                return to_flattened_numpy(rsde.sde(x, vec_t, y)[0])
+
+            solution = integrate.solve_ivp(ode_func, (sde.T, eps), to_flattened_numpy(xt), rtol=rtol, atol=atol,
+                                           method=method, **kw)
+            nfe = solution.nfev
+            x = torch.tensor(solution.y[:, -1]).reshape(y.shape).to(device).type(torch.complex64)
+            if denoise:
+                x = denoise_update_fn(x)
+            if inverse_scaler is not None:
+                x = inverse_scaler(x)
+            return x, nfe
+
+    return ode_sampler

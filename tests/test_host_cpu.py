@@ -1,0 +1,162 @@
+"""CPU-only tests of the host side: the C ABI loads and exports every symbol the header declares, the
+native parameter table matches the reference inventory, the `sgmse` mirror keeps the reference's
+names / errors, checkpoints (Lightning layout + EMA) load without a GPU, utterance sharding."""
+import ctypes
+import json
+import os
+import re
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_abi_exports_every_declared_symbol():
+    from snr_aligned_diffse_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "snrse_b200.h")).read()
+    declared = set(re.findall(r"\b(snrse_[a-z0-9_]+)\s*\(", hdr))
+    lib = _lib.load()
+    assert declared, "no declarations found"
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+    assert declared == set(_lib.PROTOTYPES), declared ^ set(_lib.PROTOTYPES)
+    assert lib.snrse_version() == 100
+
+
+def test_product_has_no_oracle_or_fallback_imports():
+    pkg = os.path.join(ROOT, "snr_aligned_diffse_b200")
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if f.endswith(".py"):
+                src = open(os.path.join(dp, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f"{f} imports the oracle"
+                assert "/root/reference" not in src
+
+
+def test_native_param_table_matches_reference_inventory(golden_dir):
+    from snr_aligned_diffse_b200.engine import NCSNppEngine
+    ref = json.load(open(os.path.join(golden_dir, "ncsnpp_param_specs.json")))
+    eng = NCSNppEngine()
+    shapes = eng.param_shapes()
+    assert set(shapes) == set(ref)
+    assert all(tuple(shapes[k]) == tuple(ref[k]) for k in ref)
+    assert eng.lib.snrse_ncsnpp_num_modules(eng.h) == 77
+    # plan sizes are computable without a GPU and grow with the bucket
+    a, b = eng.workspace_bytes(1, 256, 64), eng.workspace_bytes(2, 256, 128)
+    assert 0 < a < b
+    with pytest.raises(RuntimeError):
+        eng.workspace_bytes(1, 256, 96)      # T must be a multiple of 64 (6 halvings, util/other.py:83-90)
+    with pytest.raises(RuntimeError):
+        eng.workspace_bytes(1, 128, 64)      # attention placement was built for F = image_size
+
+
+def test_weight_packing_layouts():
+    from snr_aligned_diffse_b200.engine import NCSNppEngine
+    from snr_aligned_diffse_b200.synth import synth_state_dict
+    eng = NCSNppEngine()
+    sd = synth_state_dict(eng.param_shapes(), seed=3)
+    blob = eng.pack_state_dict(sd)
+    tab = {p["name"]: p for p in eng.param_table()}
+    b16, f32 = blob.view(torch.bfloat16), blob.view(torch.float32)
+    # 3x3 conv: K-major rows [cout][(r*3+s)*Cin + cin]
+    p = tab["dnn.all_modules.4.Conv_0.weight"]
+    w = sd[p["name"]]
+    rows = b16[p["offset"] // 2: p["offset"] // 2 + 128 * p["row_stride"]].view(128, p["row_stride"])
+    assert rows[5, (1 * 3 + 2) * 128 + 7] == w[5, 7, 1, 2].to(torch.bfloat16)
+    # fused Conv_1 | Conv_2 rows and summed bias (layerspp.py:268-272)
+    p1, p2 = tab["dnn.all_modules.12.Conv_1.weight"], tab["dnn.all_modules.12.Conv_2.weight"]
+    assert p1["offset"] == p2["offset"] and p1["row_stride"] == 9 * 256 + 128 and p2["k_offset"] == 9 * 256
+    rows = b16[p1["offset"] // 2: p1["offset"] // 2 + 256 * p1["row_stride"]].view(256, p1["row_stride"])
+    assert rows[9, 9 * 256 + 100] == sd[p2["name"]][9, 100, 0, 0].to(torch.bfloat16)
+    pb = tab["dnn.all_modules.12.Conv_1.bias"]
+    got = f32[pb["offset"] // 4: pb["offset"] // 4 + 256]
+    assert torch.equal(got, sd["dnn.all_modules.12.Conv_1.bias"] + sd["dnn.all_modules.12.Conv_2.bias"])
+    # NIN W[in,out] -> rows [out][in]
+    pn = tab["dnn.all_modules.21.NIN_1.W"]
+    rows = b16[pn["offset"] // 2: pn["offset"] // 2 + 256 * 256].view(256, 256)
+    assert rows[3, 200] == sd[pn["name"]][200, 3].to(torch.bfloat16)
+
+
+def test_registries_and_constructor_errors():
+    from snr_aligned_diffse_b200.sgmse import sampling
+    from snr_aligned_diffse_b200.sgmse.backbones import BackboneRegistry
+    from snr_aligned_diffse_b200.sgmse.model import ScoreModel, t_30
+    from snr_aligned_diffse_b200.sgmse.sdes import SDERegistry
+    assert set(SDERegistry.get_all_names()) >= {"ouve", "bbed"}
+    assert set(BackboneRegistry.get_all_names()) >= {"ncsnpp", "snrnet"}
+    assert sampling.PredictorRegistry.get_all_names() == ['euler_maruyama', 'reverse_diffusion', 'none']
+    assert sampling.CorrectorRegistry.get_all_names() == ['langevin', 'ald', 'none']
+    with pytest.raises(ValueError):
+        SDERegistry.get_by_name("nope")
+    with pytest.raises(ValueError):
+        ScoreModel(backbone="nope", sde="ouve", theta=1.5, sigma_min=0.05, sigma_max=0.5)
+    with pytest.raises(NotImplementedError):
+        ScoreModel(backbone="ncsnpp", sde="ouve", theta=1.5, sigma_min=0.05, sigma_max=0.5, resblock_type="ddpm")
+    assert t_30.dtype == np.float64 and t_30[0] == pytest.approx(0.001) and t_30[-1] == 1.0
+    m = ScoreModel(backbone="ncsnpp", sde="ouve", model_type="sebridge_v3", snr_conditioned="fixed", theta=1.5,
+                   sigma_min=0.05, sigma_max=1.0)
+    with pytest.raises(NotImplementedError):
+        m.enhance(torch.zeros(1, 4000), torch.zeros(1, 4000))      # model.py:792-793
+    # eval.py pokes these attributes (eval.py:105-108)
+    assert m.sde.__class__.__name__ == "OUVESDE"
+    m.sde._T = 0.5
+    assert m.sde.T == 0.5
+    b = SDERegistry.get_by_name("bbed")(T_sampling=0.999, k=2.6, theta=0.52, N=30)
+    b.T = 0.5
+    assert b.copy().T == 0.5
+
+
+def test_lightning_checkpoint_with_ema_loads_on_cpu(tmp_path):
+    from snr_aligned_diffse_b200.sgmse.data_module import SpecsDataModule
+    from snr_aligned_diffse_b200.sgmse.model import ScoreModel
+    from snr_aligned_diffse_b200.synth import synth_state_dict
+    hp = dict(backbone="ncsnpp", sde="ouve", model_type="sebridge_v3", snr_conditioned="true", fixed_snr=0.31623,
+              theta=1.5, sigma_min=0.05, sigma_max=1.0, data_module_cls=SpecsDataModule, base_dir="/data")
+    probe = ScoreModel(**hp)
+    names = list(probe.dnn.param_shapes())
+    sd = synth_state_dict({"dnn." + k: v for k, v in probe.dnn.param_shapes().items()}, seed=5)
+    shadow = [sd["dnn." + n] * 0.5 for n in names if n != "all_modules.0.W"]
+    path = str(tmp_path / "m.ckpt")
+    torch.save({"state_dict": sd, "hyper_parameters": hp,
+                "ema": {"decay": 0.999, "num_updates": 7, "shadow_params": shadow, "collected_params": None}}, path)
+    m = ScoreModel.load_from_checkpoint(path, base_dir="", batch_size=16, num_workers=0, kwargs=dict(gpu=False))
+    assert m.fixed_snr == 0.31623 and m.data_module.base_dir == ""
+    key = "all_modules.4.Conv_0.weight"
+    assert torch.equal(m.dnn.state_dict()[key], sd["dnn." + key])
+    m.eval(no_ema=False)                                            # EMA weights become live (model.py:120-126)
+    assert torch.equal(m.dnn.state_dict()[key], sd["dnn." + key] * 0.5)
+    assert torch.equal(m.dnn.state_dict()["all_modules.0.W"], sd["dnn.all_modules.0.W"])   # frozen: not in EMA
+    m.train(True)
+    assert torch.equal(m.dnn.state_dict()[key], sd["dnn." + key])
+    m.eval(no_ema=True)
+    assert torch.equal(m.dnn.state_dict()[key], sd["dnn." + key])
+    assert m.cpu() is m and m.to("cuda") is m
+
+
+def test_missing_library_or_gpu_fails_loudly():
+    from snr_aligned_diffse_b200 import _lib, ops
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(RuntimeError):
+        _lib.require_device()
+    with pytest.raises((RuntimeError, AssertionError)):
+        ops.stft(torch.zeros(1, 4000))
+
+
+def test_sharding_lpt():
+    from snr_aligned_diffse_b200.shard import bucket_batches, lpt_shards, synthetic_lengths
+    L = synthetic_lengths(824, seed=0)
+    assert len(L) == 824 and L.min() >= 24000 and L.max() <= 160000
+    for g in (1, 2, 4, 8):
+        shards = lpt_shards(L, g)
+        flat = sorted(i for s in shards for i in s)
+        assert flat == list(range(824))                              # a partition: nothing lost, nothing doubled
+        loads = [sum(64 * (-(-(1 + L[i] // 128) // 64)) for i in s) for s in shards]
+        assert max(loads) - min(loads) <= 1280                       # within one longest utterance
+    batches = bucket_batches(L, list(range(824)), max_batch=16)
+    assert sorted(i for _, idx in batches for i in idx) == list(range(824))
+    for tpad, idx in batches:
+        assert len(idx) <= 16 and all(64 * (-(-(1 + L[i] // 128) // 64)) == tpad for i in idx)
