@@ -10,114 +10,143 @@
 namespace {
 
 // ------------------------------------------------------------------------------------------------
-// conv_in4: thread = (pixel quad, 8 output channels); block = strip of PIX pixels of one image row.
+// conv_in4: lane = pixel.  A thread keeps the 3x3x4 input patches of TWO pixels (rows r and r+4 of an
+// 8 x 32 pixel tile) in registers and walks the output channels 16 at a time; the weights of the current
+// (tap, cin) are broadcast from shared memory (4 LDS.128 per 32 FMA -> FMA-bound, not LDS-bound).
 // ------------------------------------------------------------------------------------------------
-constexpr int CI_PIX = 64;  // pixels per block along W
-
 template <int COUT>
-__global__ void __launch_bounds__(COUT / 8 * (CI_PIX / 4))
+__global__ void __launch_bounds__(128)
 conv_in4_kernel(const float4* __restrict__ x4, const float* __restrict__ w, const float* __restrict__ bias, bf16* out,
                 int H, int W, int ld) {
-    constexpr int TPP = COUT / 8;  // threads covering the channels of one pixel
-    __shared__ float4 s_in[3][CI_PIX + 2];
     __shared__ __align__(16) float s_w[36][COUT];  // [tap*4 + cin][cout]
-    const int b = blockIdx.z, h = blockIdx.y, w0 = blockIdx.x * CI_PIX;
-    const int tid = threadIdx.x, nthr = blockDim.x;
-    for (int i = tid; i < 36 * COUT; i += nthr) {
+    __shared__ float s_b[COUT];
+    const int b = blockIdx.z, h0 = blockIdx.y * 8, w0 = blockIdx.x * 32;
+    for (int i = threadIdx.x; i < 36 * COUT; i += 128) {
         const int co = i / 36, k = i % 36;  // global layout [cout][tap][cin]
         s_w[k][co] = w[i];
     }
-    for (int i = tid; i < 3 * (CI_PIX + 2); i += nthr) {
-        const int r = i / (CI_PIX + 2), c = i % (CI_PIX + 2);
-        const int hh = h + r - 1, ww = w0 + c - 1;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (hh >= 0 && hh < H && ww >= 0 && ww < W) v = x4[((int64_t)b * H + hh) * W + ww];
-        s_in[r][c] = v;
+    for (int i = threadIdx.x; i < COUT; i += 128) s_b[i] = bias[i];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ww = w0 + lane;
+    float xin[2][36];
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+        const int h = h0 + warp + 4 * p;
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                const int hh = h + r - 1, wx = ww + q - 1;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (hh >= 0 && hh < H && wx >= 0 && wx < W) v = __ldg(x4 + ((int64_t)b * H + hh) * W + wx);
+                xin[p][(r * 3 + q) * 4 + 0] = v.x;
+                xin[p][(r * 3 + q) * 4 + 1] = v.y;
+                xin[p][(r * 3 + q) * 4 + 2] = v.z;
+                xin[p][(r * 3 + q) * 4 + 3] = v.w;
+            }
     }
     __syncthreads();
-    const int cg = tid % TPP, pq = tid / TPP;  // channel group, pixel quad
-    float acc[4][8];
+    for (int c0 = 0; c0 < COUT; c0 += 16) {
+        float acc[2][16];
 #pragma unroll
-    for (int p = 0; p < 4; ++p)
+        for (int j = 0; j < 16; ++j) acc[0][j] = acc[1][j] = s_b[c0 + j];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[p][j] = bias[cg * 8 + j];
+        for (int k = 0; k < 36; ++k) {
+            float wv[16];
 #pragma unroll
-    for (int r = 0; r < 3; ++r) {
+            for (int q = 0; q < 4; ++q) {
+                const float4 t = *reinterpret_cast<const float4*>(&s_w[k][c0 + 4 * q]);
+                wv[4 * q] = t.x; wv[4 * q + 1] = t.y; wv[4 * q + 2] = t.z; wv[4 * q + 3] = t.w;
+            }
 #pragma unroll
-        for (int s = 0; s < 3; ++s) {
-            float4 xin[4];
-#pragma unroll
-            for (int p = 0; p < 4; ++p) xin[p] = s_in[r][pq * 4 + p + s];
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const float4 wa = *reinterpret_cast<const float4*>(&s_w[(r * 3 + s) * 4 + c][cg * 8]);
-                const float4 wb = *reinterpret_cast<const float4*>(&s_w[(r * 3 + s) * 4 + c][cg * 8 + 4]);
-                const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
-#pragma unroll
-                for (int p = 0; p < 4; ++p) {
-                    const float xv = c == 0 ? xin[p].x : (c == 1 ? xin[p].y : (c == 2 ? xin[p].z : xin[p].w));
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) acc[p][j] = fmaf(xv, wv[j], acc[p][j]);
-                }
+            for (int j = 0; j < 16; ++j) {
+                acc[0][j] = fmaf(xin[0][k], wv[j], acc[0][j]);
+                acc[1][j] = fmaf(xin[1][k], wv[j], acc[1][j]);
             }
         }
-    }
 #pragma unroll
-    for (int p = 0; p < 4; ++p) {
-        const int ww = w0 + pq * 4 + p;
-        if (ww < W) {
-            const int64_t pix = ((int64_t)b * H + h) * W + ww;
-            *reinterpret_cast<uint4*>(out + pix * ld + cg * 8) = pack8(acc[p]);
+        for (int p = 0; p < 2; ++p) {
+            const int h = h0 + warp + 4 * p;
+            if (h < H && ww < W) {
+                uint4* dst = reinterpret_cast<uint4*>(out + (((int64_t)b * H + h) * W + ww) * ld + c0);
+                dst[0] = pack8(acc[p]);
+                dst[1] = pack8(acc[p] + 8);
+            }
         }
     }
 }
 
 // ------------------------------------------------------------------------------------------------
-// conv_out4: lane = pixel (32 consecutive pixels along W per warp), weights broadcast from smem.
+// conv_out4: 8 x 32 pixel tile per block (128 threads, 2 pixels per thread).  The input patch is staged
+// through shared memory in 32-channel chunks, stored channel-pair-major so that lane = pixel reads are
+// bank-conflict free; weights of the chunk are broadcast.  Fused with the `pyramid + pyramid_h` add.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+constexpr int CO_TH = 8, CO_TW = 32, CO_CH = 32;
+__global__ void __launch_bounds__(128)
 conv_out4_kernel(const bf16* __restrict__ a, int ld, int C, const float* __restrict__ w, const float* __restrict__ bias,
                  const float4* __restrict__ addend, float4* __restrict__ out, int H, int W) {
-    extern __shared__ __align__(16) float s_w4[];  // [tap][c][4]
-    const int b = blockIdx.z;
-    for (int i = threadIdx.x; i < 9 * C * 4; i += blockDim.x) {
-        const int o = i / (9 * C), rem = i % (9 * C);  // global layout [4][tap][C]
-        s_w4[rem * 4 + o] = w[i];
-    }
-    __syncthreads();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int h = blockIdx.y * 8 + warp;
-    const int ww = blockIdx.x * 32 + lane;
-    if (h >= H || ww >= W) return;
-    float acc0 = bias[0], acc1 = bias[1], acc2 = bias[2], acc3 = bias[3];
-    for (int r = 0; r < 3; ++r) {
-        const int hh = h + r - 1;
-        if (hh < 0 || hh >= H) continue;
-        for (int s = 0; s < 3; ++s) {
-            const int wx = ww + s - 1;
-            if (wx < 0 || wx >= W) continue;
-            const uint4* src = reinterpret_cast<const uint4*>(a + (((int64_t)b * H + hh) * W + wx) * ld);
-            const float4* wt = reinterpret_cast<const float4*>(s_w4) + (r * 3 + s) * C;
-            for (int c8 = 0; c8 < C / 8; ++c8) {
-                float f[8];
-                unpack8(__ldg(src + c8), f);
+    __shared__ uint32_t s_x[CO_CH / 2][CO_TH + 2][CO_TW + 2];   // bf16 pairs, [c2][row][col]   21.8 KB
+    __shared__ __align__(16) float s_w[9][CO_CH][4];             // [tap][c][out]                4.6 KB
+    const int b = blockIdx.z, h0 = blockIdx.y * CO_TH, w0 = blockIdx.x * CO_TW;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float acc[2][4];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float4 wv = wt[c8 * 8 + j];
-                    acc0 = fmaf(f[j], wv.x, acc0);
-                    acc1 = fmaf(f[j], wv.y, acc1);
-                    acc2 = fmaf(f[j], wv.z, acc2);
-                    acc3 = fmaf(f[j], wv.w, acc3);
+    for (int p = 0; p < 2; ++p)
+#pragma unroll
+        for (int o = 0; o < 4; ++o) acc[p][o] = bias[o];
+    for (int c0 = 0; c0 < C; c0 += CO_CH) {
+        __syncthreads();
+        // stage weights of this chunk: global [4][tap][C]
+        for (int i = threadIdx.x; i < 9 * CO_CH * 4; i += 128) {
+            const int o = i & 3, c = (i >> 2) % CO_CH, tap = i / (4 * CO_CH);
+            s_w[tap][c][o] = w[((int64_t)o * 9 + tap) * C + c0 + c];
+        }
+        // stage the (8+2) x (32+2) pixel patch, 32 channels = 4 pieces of 16 B per pixel
+        for (int i = threadIdx.x; i < (CO_TH + 2) * (CO_TW + 2) * 4; i += 128) {
+            const int piece = i & 3, pix = i >> 2;
+            const int r = pix / (CO_TW + 2), c = pix % (CO_TW + 2);
+            const int hh = h0 + r - 1, wx = w0 + c - 1;
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (hh >= 0 && hh < H && wx >= 0 && wx < W)
+                v = __ldg(reinterpret_cast<const uint4*>(a + (((int64_t)b * H + hh) * W + wx) * ld + c0 + piece * 8));
+            s_x[piece * 4 + 0][r][c] = v.x;
+            s_x[piece * 4 + 1][r][c] = v.y;
+            s_x[piece * 4 + 2][r][c] = v.z;
+            s_x[piece * 4 + 3][r][c] = v.w;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+            const int dy = tap / 3, dx = tap % 3;
+#pragma unroll 4
+            for (int c2 = 0; c2 < CO_CH / 2; ++c2) {
+                const float4 wa = *reinterpret_cast<const float4*>(&s_w[tap][2 * c2][0]);
+                const float4 wb = *reinterpret_cast<const float4*>(&s_w[tap][2 * c2 + 1][0]);
+#pragma unroll
+                for (int p = 0; p < 2; ++p) {
+                    const uint32_t xv = s_x[c2][warp + 4 * p + dy][lane + dx];
+                    const float x0 = __uint_as_float(xv << 16), x1 = __uint_as_float(xv & 0xffff0000u);
+                    acc[p][0] = fmaf(x0, wa.x, fmaf(x1, wb.x, acc[p][0]));
+                    acc[p][1] = fmaf(x0, wa.y, fmaf(x1, wb.y, acc[p][1]));
+                    acc[p][2] = fmaf(x0, wa.z, fmaf(x1, wb.z, acc[p][2]));
+                    acc[p][3] = fmaf(x0, wa.w, fmaf(x1, wb.w, acc[p][3]));
                 }
             }
         }
     }
-    const int64_t pix = ((int64_t)b * H + h) * W + ww;
-    if (addend) {
-        const float4 ad = addend[pix];
-        acc0 += ad.x; acc1 += ad.y; acc2 += ad.z; acc3 += ad.w;
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+        const int h = h0 + warp + 4 * p, ww = w0 + lane;
+        if (h < H && ww < W) {
+            const int64_t pix = ((int64_t)b * H + h) * W + ww;
+            float4 r = make_float4(acc[p][0], acc[p][1], acc[p][2], acc[p][3]);
+            if (addend) {
+                const float4 ad = addend[pix];
+                r.x += ad.x; r.y += ad.y; r.z += ad.z; r.w += ad.w;
+            }
+            out[pix] = r;
+        }
     }
-    out[pix] = make_float4(acc0, acc1, acc2, acc3);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -211,33 +240,20 @@ conv_simt_kernel(const bf16* __restrict__ a0, int ld0, int C0, int taps0, const 
 }  // namespace
 
 int conv_in4_launch(const float* x4, const float* w, const float* bias, const ActView* out, cudaStream_t s) {
-    dim3 grid(cdiv(out->W, CI_PIX), out->H, out->B);
-    if (out->C == 128) {
-        conv_in4_kernel<128><<<grid, 128 / 8 * (CI_PIX / 4), 0, s>>>(reinterpret_cast<const float4*>(x4), w, bias,
-                                                                     out->ptr, out->H, out->W, out->ld);
-    } else if (out->C == 64) {
-        conv_in4_kernel<64><<<grid, 64 / 8 * (CI_PIX / 4), 0, s>>>(reinterpret_cast<const float4*>(x4), w, bias,
-                                                                   out->ptr, out->H, out->W, out->ld);
-    } else {
-        snrse_set_error("conv_in4: nf must be 64 or 128 (got %d)", out->C);
-        return SNRSE_ERR_UNSUPPORTED;
-    }
+    SNRSE_CHECK_ARG(out->C == 128, "conv_in4: nf must be 128 (got %d)", out->C);
+    dim3 grid(cdiv(out->W, 32), cdiv(out->H, 8), out->B);
+    conv_in4_kernel<128><<<grid, 128, 0, s>>>(reinterpret_cast<const float4*>(x4), w, bias, out->ptr, out->H, out->W,
+                                              out->ld);
     SNRSE_LAUNCH_CHECK();
     return SNRSE_OK;
 }
 
 int conv_out4_launch(const ActView* a, const float* w, const float* bias, const float* addend4, float* out4,
                      cudaStream_t s) {
-    SNRSE_CHECK_ARG(a->C % 8 == 0 && a->C <= 512, "conv_out4: unsupported channel count %d", a->C);
-    static bool attr_set = false;
-    if (!attr_set) {
-        SNRSE_CUDA(cudaFuncSetAttribute(conv_out4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 9 * 512 * 16));
-        attr_set = true;
-    }
-    dim3 grid(cdiv(a->W, 32), cdiv(a->H, 8), a->B);
-    conv_out4_kernel<<<grid, 256, 9 * a->C * 16, s>>>(a->ptr, a->ld, a->C, w, bias,
-                                                      reinterpret_cast<const float4*>(addend4),
-                                                      reinterpret_cast<float4*>(out4), a->H, a->W);
+    SNRSE_CHECK_ARG(a->C % CO_CH == 0 && a->ld % 8 == 0, "conv_out4: C must be a multiple of %d (got %d)", CO_CH, a->C);
+    dim3 grid(cdiv(a->W, CO_TW), cdiv(a->H, CO_TH), a->B);
+    conv_out4_kernel<<<grid, 128, 0, s>>>(a->ptr, a->ld, a->C, w, bias, reinterpret_cast<const float4*>(addend4),
+                                          reinterpret_cast<float4*>(out4), a->H, a->W);
     SNRSE_LAUNCH_CHECK();
     return SNRSE_OK;
 }

@@ -27,15 +27,24 @@ gn_stats_kernel(const bf16* __restrict__ x, int ld, int C, int64_t hw, int pix_p
     if (p1 > hw) p1 = hw;
     const bf16* base = x + (int64_t)b * hw * ld + vec * 8;
     float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
-    for (int64_t p = p0 + prow; p < p1; p += ppb) {
-        float f[8];
-        unpack8(__ldg(reinterpret_cast<const uint4*>(base + p * ld)), f);
+    for (int64_t p = p0 + prow; p < p1; p += 4 * ppb) {
+        uint4 v[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            s0 += f[j];
-            q0 = fmaf(f[j], f[j], q0);
-            s1 += f[4 + j];
-            q1 = fmaf(f[4 + j], f[4 + j], q1);
+        for (int u = 0; u < 4; ++u) {
+            const int64_t q = p + (int64_t)u * ppb;
+            v[u] = (q < p1) ? __ldg(reinterpret_cast<const uint4*>(base + q * ld)) : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            float f[8];
+            unpack8(v[u], f);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                s0 += f[j];
+                q0 = fmaf(f[j], f[j], q0);
+                s1 += f[4 + j];
+                q1 = fmaf(f[4 + j], f[4 + j], q1);
+            }
         }
     }
     // deterministic block reduction: [prow][half-vector] -> per half-vector -> per group
@@ -119,15 +128,28 @@ gn_apply_kernel(const bf16* __restrict__ x, int ld, int C, int64_t hw, const flo
     }
     const bf16* src = x + (int64_t)b * hw * ld + vec * 8;
     bf16* dst = out + (int64_t)b * hw * out_ld + vec * 8;
-    for (int64_t p = p0 + prow; p < p1; p += ppb) {
-        float f[8];
-        unpack8(__ldg(reinterpret_cast<const uint4*>(src + p * ld)), f);
+    // 4 pixels per thread per trip: all loads issued before the first use (memory-level parallelism)
+    for (int64_t p = p0 + prow; p < p1; p += 4 * ppb) {
+        uint4 v[4];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const float v = fmaf(f[j], sc[j], sh[j]);
-            f[j] = silu ? silu_f(v) : v;
+        for (int u = 0; u < 4; ++u) {
+            const int64_t q = p + (int64_t)u * ppb;
+            if (q < p1) v[u] = __ldg(reinterpret_cast<const uint4*>(src + q * ld));
         }
-        *reinterpret_cast<uint4*>(dst + p * out_ld) = pack8(f);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t q = p + (int64_t)u * ppb;
+            if (q < p1) {
+                float f[8];
+                unpack8(v[u], f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float t = fmaf(f[j], sc[j], sh[j]);
+                    f[j] = silu ? silu_f(t) : t;
+                }
+                *reinterpret_cast<uint4*>(dst + q * out_ld) = pack8(f);
+            }
+        }
     }
 }
 
@@ -162,8 +184,8 @@ int gn_apply_launch(const ActView* x, const float* scsh, int silu, const ActView
     const int64_t hw = (int64_t)x->H * x->W;
     const int nthr = gn_threads(x->C);
     const int ppb = nthr / (x->C / 8);
-    // ~4 pixels per thread-row, at least one pass
-    int64_t blocks_per_img = cdiv64(hw, (int64_t)ppb * 4);
+    // ~16 pixels per thread-row (4 trips of 4), at least one block
+    int64_t blocks_per_img = cdiv64(hw, (int64_t)ppb * 16);
     if (blocks_per_img < 1) blocks_per_img = 1;
     const int pix_per_block = (int)cdiv64(hw, blocks_per_img);
     dim3 grid((unsigned)blocks_per_img, x->B);

@@ -77,95 +77,151 @@ snr_conv5_pool_kernel(const float* __restrict__ feat, const float* __restrict__ 
 }
 
 // ---- conv3x3 (32->32, pad 1) + maxpool (2,1).  a1 [NC][32][128][8] -> a2 [NC][32][64][8]
+// Block = one cluster x 16 conv rows x all 32 output channels.  Thread = 4 output channels x a 2x2 patch of
+// conv outputs (-> 2 pooled values per channel): per input channel 16 activations + 9 weight vectors are
+// loaded for 144 FMA (register tiling keeps the kernel FMA-bound instead of LDS-bound).
+constexpr int C3_ROWS = 16;
 __global__ void __launch_bounds__(256)
 snr_conv3_pool_kernel(const float* __restrict__ a1, const float* __restrict__ w, const float* __restrict__ bias,
                       float* __restrict__ a2) {
-    __shared__ float sw[32 * 32 * 9];   // 36 KB
-    __shared__ float sx[32][6][10];     // 4 input rows (+2 halo) x 8 cols (+2 halo), 7.5 KB
-    const int nc = blockIdx.y, f0 = blockIdx.x * 4;  // 4 conv rows -> 2 pooled rows
-    for (int i = threadIdx.x; i < 32 * 32 * 9; i += 256) sw[i] = w[i];
-    for (int i = threadIdx.x; i < 32 * 60; i += 256) {
-        const int c = i / 60, r = (i / 10) % 6, t = i % 10;
+    extern __shared__ __align__(16) float sm3[];
+    float* sw = sm3;                       // [ci][k][co]   32*9*32 floats = 36 KB
+    float* sx = sm3 + 32 * 9 * 32;         // [ci][18][10]  23 KB
+    const int nc = blockIdx.y, f0 = blockIdx.x * C3_ROWS;
+    for (int i = threadIdx.x; i < 32 * 32 * 9; i += 256) {
+        const int co = i / 288, ci = (i / 9) % 32, k = i % 9;  // global [co][ci][3][3]
+        sw[(ci * 9 + k) * 32 + co] = w[i];
+    }
+    for (int i = threadIdx.x; i < 32 * 18 * 10; i += 256) {
+        const int c = i / 180, r = (i / 10) % 18, t = i % 10;
         const int f = f0 + r - 1, tt = t - 1;
         float v = 0.f;
         if (f >= 0 && f < 128 && tt >= 0 && tt < 8) v = a1[(((int64_t)nc * 32 + c) * 128 + f) * 8 + tt];
-        sx[c][r][t] = v;
+        sx[i] = v;
     }
     __syncthreads();
-    // 32 co x 2 pooled rows x 8 cols = 512 outputs, 2 per thread
-    for (int o = threadIdx.x; o < 512; o += 256) {
-        const int co = o >> 4, pr = (o >> 3) & 1, pc = o & 7;
-        float best = -INFINITY;
+    const int cg = threadIdx.x & 7, pg = threadIdx.x >> 3;  // channel group (4 co), position group
+    const int pr = pg >> 2, pc2 = pg & 3;                    // pooled row 0..7, column pair 0..3
+    float acc[4][4];                                         // [co][pos: (dy,dx)]
 #pragma unroll
-        for (int dy = 0; dy < 2; ++dy) {
-            float acc = bias[co];
-            const int r0 = pr * 2 + dy;
-            for (int c = 0; c < 32; ++c)
+    for (int j = 0; j < 4; ++j)
 #pragma unroll
-                for (int ky = 0; ky < 3; ++ky)
+        for (int q = 0; q < 4; ++q) acc[j][q] = bias[cg * 4 + j];
+    for (int ci = 0; ci < 32; ++ci) {
+        float xv[4][4];
 #pragma unroll
-                    for (int kx = 0; kx < 3; ++kx)
-                        acc = fmaf(sx[c][r0 + ky][pc + kx], sw[(co * 32 + c) * 9 + ky * 3 + kx], acc);
-            best = fmaxf(best, acc);
-        }
-        a2[(((int64_t)nc * 32 + co) * 64 + (f0 / 2 + pr)) * 8 + pc] = best;
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) xv[r][c] = sx[(ci * 18 + pr * 2 + r) * 10 + pc2 * 2 + c];
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const float4 wv = *reinterpret_cast<const float4*>(&sw[(ci * 9 + ky * 3 + kx) * 32 + cg * 4]);
+                const float ww[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+#pragma unroll
+                    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+                        for (int dx = 0; dx < 2; ++dx)
+                            acc[j][dy * 2 + dx] = fmaf(xv[dy + ky][dx + kx], ww[j], acc[j][dy * 2 + dx]);
+            }
     }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx)
+            a2[(((int64_t)nc * 32 + cg * 4 + j) * 64 + (f0 / 2 + pr)) * 8 + pc2 * 2 + dx] =
+                fmaxf(acc[j][dx], acc[j][2 + dx]);
 }
 
 // ---- four (64 x k) convolutions + max over time.  a2 [NC][32][64][8] -> feats [NC][128]
+// Block = 8 clusters x one kernel width k; warp = cluster, lane = output channel.  Per 32-row chunk of the
+// (ci,f) axis the activations [8][32][8] and weights [32][k][32 co] are staged in shared memory; a lane keeps
+// the <= 8 output-frame accumulators of its channel.
 struct ConvtW {
     const float* w[4];
     const float* b[4];
 };
 __global__ void __launch_bounds__(256)
-snr_convt_kernel(const float* __restrict__ a2, ConvtW cw, float* __restrict__ feats) {
-    extern __shared__ float sx[];  // [32*64][8]
-    const int nc = blockIdx.x;
-    for (int i = threadIdx.x; i < 32 * 64 * 8; i += 256) sx[i] = a2[(int64_t)nc * 16384 + i];
-    __syncthreads();
+snr_convt_kernel(const float* __restrict__ a2, ConvtW cw, float* __restrict__ feats, int64_t ncl) {
+    __shared__ __align__(16) float sx[8][32][8];     // [cluster][r][frame]      8 KB
+    __shared__ float sw[32 * 8 * 32];                // [r][dt][co]           <= 32 KB
+    const int ki = blockIdx.y, k = 1 << ki, nout = 9 - k;
+    const int64_t nc0 = (int64_t)blockIdx.x * 8;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int pair = warp; pair < 128; pair += 8) {
-        const int ki = pair >> 5, co = pair & 31;
-        const int k = 1 << ki;           // 1, 2, 4, 8
-        const int nout = 9 - k;          // 8, 7, 5, 1 output frames
-        const float* wr = cw.w[ki] + (int64_t)co * 2048 * k;  // [ci*64+f][dt]
-        float acc[8];
+    const float* wg = cw.w[ki];                      // [co][r (2048)][dt (k)]
+    float acc[8];
 #pragma unroll
-        for (int t = 0; t < 8; ++t) acc[t] = 0.f;
-        for (int r = lane; r < 2048; r += 32) {  // r = ci*64 + f
-            const float* xr = sx + r * 8;
-            for (int dt = 0; dt < k; ++dt) {
-                const float wv = wr[r * k + dt];
+    for (int t = 0; t < 8; ++t) acc[t] = 0.f;
+    for (int r0 = 0; r0 < 2048; r0 += 32) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < 8 * 32 * 8; i += 256) {
+            const int cl = i >> 8, rr = (i >> 3) & 31, t = i & 7;
+            const int64_t nc = nc0 + cl;
+            sx[cl][rr][t] = nc < ncl ? a2[nc * 16384 + (int64_t)(r0 + rr) * 8 + t] : 0.f;
+        }
+        for (int i = threadIdx.x; i < 32 * 32 * k; i += 256) {
+            const int co = i / (32 * k), rem = i % (32 * k);   // rem = rr*k + dt, contiguous in global
+            sw[rem * 32 + co] = wg[((int64_t)co * 2048 + r0) * k + rem];
+        }
+        __syncthreads();
+        for (int rr = 0; rr < 32; ++rr) {
+            const float4 xa = *reinterpret_cast<const float4*>(&sx[warp][rr][0]);
+            const float4 xb = *reinterpret_cast<const float4*>(&sx[warp][rr][4]);
+            const float xf[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
 #pragma unroll
-                for (int t = 0; t < 8; ++t)
-                    if (t < nout) acc[t] = fmaf(xr[t + dt], wv, acc[t]);
+            for (int dt = 0; dt < 8; ++dt) {
+                if (dt < k) {
+                    const float wv = sw[(rr * k + dt) * 32 + lane];
+#pragma unroll
+                    for (int t = 0; t + dt < 8; ++t) acc[t] = fmaf(xf[t + dt], wv, acc[t]);
+                }
             }
         }
-        float best = -INFINITY;
-#pragma unroll
-        for (int t = 0; t < 8; ++t) {
-            const float v = warp_sum(acc[t]);
-            if (t < nout) best = fmaxf(best, v);
-        }
-        if (lane == 0) feats[(int64_t)nc * 128 + ki * 32 + co] = best + cw.b[ki][co];
     }
+    float best = -INFINITY;
+#pragma unroll
+    for (int t = 0; t < 8; ++t)
+        if (t < nout) best = fmaxf(best, acc[t]);
+    const int64_t nc = nc0 + warp;
+    if (nc < ncl) feats[nc * 128 + ki * 32 + lane] = best + cw.b[ki][lane];
 }
 
 // ---- LSTM input projections for both directions: pre[dir][B*S][512] = W_ih x + b_ih + b_hh
+// Block = 8 rows (clusters); thread = 4 gate rows; a weight row is read once per 8 inputs.
 __global__ void __launch_bounds__(256)
 snr_lstm_pre_kernel(const float* __restrict__ feats, const float* __restrict__ wih0, const float* __restrict__ bih0,
                     const float* __restrict__ bhh0, const float* __restrict__ wih1, const float* __restrict__ bih1,
                     const float* __restrict__ bhh1, float* __restrict__ pre, int64_t rows) {
-    __shared__ float sx[128];
-    const int64_t row = blockIdx.x;
-    if (threadIdx.x < 128) sx[threadIdx.x] = feats[row * 128 + threadIdx.x];
+    __shared__ float sx[8][128];
+    const int64_t row0 = (int64_t)blockIdx.x * 8;
+    for (int i = threadIdx.x; i < 8 * 128; i += 256) {
+        const int64_t row = row0 + (i >> 7);
+        sx[i >> 7][i & 127] = row < rows ? feats[row * 128 + (i & 127)] : 0.f;
+    }
     __syncthreads();
     for (int o = threadIdx.x; o < 1024; o += 256) {
         const int dir = o >> 9, g = o & 511;
-        const float* wr = (dir ? wih1 : wih0) + (int64_t)g * 128;
-        float acc = (dir ? bih1 : bih0)[g] + (dir ? bhh1 : bhh0)[g];
-        for (int j = 0; j < 128; ++j) acc = fmaf(wr[j], sx[j], acc);
-        pre[((int64_t)dir * rows + row) * 512 + g] = acc;
+        const float4* wr = reinterpret_cast<const float4*>((dir ? wih1 : wih0) + (int64_t)g * 128);
+        const float b0 = (dir ? bih1 : bih0)[g] + (dir ? bhh1 : bhh0)[g];
+        float acc[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) acc[q] = b0;
+        for (int j = 0; j < 32; ++j) {
+            const float4 wv = __ldg(wr + j);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                acc[q] = fmaf(wv.x, sx[q][4 * j], acc[q]);
+                acc[q] = fmaf(wv.y, sx[q][4 * j + 1], acc[q]);
+                acc[q] = fmaf(wv.z, sx[q][4 * j + 2], acc[q]);
+                acc[q] = fmaf(wv.w, sx[q][4 * j + 3], acc[q]);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+            if (row0 + q < rows) pre[((int64_t)dir * rows + row0 + q) * 512 + g] = acc[q];
     }
 }
 
@@ -287,23 +343,25 @@ int snrse_snrnet_forward(const void* weights, const float* feat, float* out, int
     float* hout = pre + nc * 1024;
     static bool attr_set = false;
     if (!attr_set) {
-        SNRSE_CUDA(cudaFuncSetAttribute(snr_convt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+        SNRSE_CUDA(cudaFuncSetAttribute(snr_conv3_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (32 * 9 * 32 + 32 * 18 * 10) * 4));
         SNRSE_CUDA(cudaFuncSetAttribute(snr_lstm_rec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (64 * 512 + 128 + 512) * 4));
         attr_set = true;
     }
     snr_conv5_pool_kernel<<<dim3(16, (unsigned)nc), 256, 0, s>>>(feat, P(weights, 0), P(weights, 1), a1, T16);
     SNRSE_LAUNCH_CHECK();
-    snr_conv3_pool_kernel<<<dim3(32, (unsigned)nc), 256, 0, s>>>(a1, P(weights, 2), P(weights, 3), a2);
+    snr_conv3_pool_kernel<<<dim3(128 / C3_ROWS, (unsigned)nc), 256, (32 * 9 * 32 + 32 * 18 * 10) * 4, s>>>(
+        a1, P(weights, 2), P(weights, 3), a2);
     SNRSE_LAUNCH_CHECK();
     ConvtW cw;
     for (int i = 0; i < 4; ++i) {
         cw.w[i] = P(weights, 4 + 2 * i);
         cw.b[i] = P(weights, 5 + 2 * i);
     }
-    snr_convt_kernel<<<(unsigned)nc, 256, 65536, s>>>(a2, cw, feats);
+    snr_convt_kernel<<<dim3((unsigned)cdiv64(nc, 8), 4), 256, 0, s>>>(a2, cw, feats, nc);
     SNRSE_LAUNCH_CHECK();
-    snr_lstm_pre_kernel<<<(unsigned)nc, 256, 0, s>>>(feats, P(weights, 12), P(weights, 14), P(weights, 15), P(weights, 16),
+    snr_lstm_pre_kernel<<<(unsigned)cdiv64(nc, 8), 256, 0, s>>>(feats, P(weights, 12), P(weights, 14), P(weights, 15), P(weights, 16),
                                                      P(weights, 18), P(weights, 19), pre, nc);
     SNRSE_LAUNCH_CHECK();
     snr_lstm_rec_kernel<<<dim3(B, 2), 512, (64 * 512 + 128 + 512) * 4, s>>>(pre, P(weights, 13), P(weights, 17), hout, S, nc);
