@@ -45,6 +45,26 @@ int conv_gemm_make_plan(ConvGemmPlan* p, const ActView* a0, int taps0, const Act
                         const ActView* res, float scale, void* out, int out_ld, int out_f32);
 int conv_gemm_launch(const ConvGemmPlan* p, cudaStream_t s);
 
+// ----------------------------------------------------------------------------- conv_halo.cu
+// Persistent halo-reuse variant for 3x3 convolutions with W >= 16, H >= 8, N in {128, 256} (same epilogue).
+struct ConvHaloPlan {
+    CUtensorMap mapA0, mapA1, mapB;
+    int c0_chunks, c1_chunks, B, H, W, sub, tiles_h, tiles_w, n_tiles, N, na, nb, acc_bufs, grid, smem_bytes;
+    const float* bias;
+    const float* tbias;
+    int tb_stride;
+    const bf16* res;
+    int res_ld;
+    float scale;
+    bf16* out;
+    int out_ld;
+};
+bool conv_halo_eligible(const ActView* a0, int taps0, int n_rows);
+int conv_halo_make_plan(ConvHaloPlan* p, const ActView* a0, const ActView* a1, const bf16* wt, int n_rows,
+                        const float* bias, const float* tbias, int tb_stride, const ActView* res, float scale, bf16* out,
+                        int out_ld);
+int conv_halo_launch(const ConvHaloPlan* p, cudaStream_t s);
+
 // ----------------------------------------------------------------------------- conv_simt.cu
 // Reference-grade direct convolution on CUDA cores (debug / cross-check path, fp32 accumulate).
 int conv_simt_launch(const ActView* a0, int taps0, const ActView* a1, const bf16* wt, int N, const float* bias,

@@ -170,10 +170,14 @@ CONV_CASES = [
     (1, 256, 64, 128, 128, 9),
     (2, 16, 16, 256, 768, 1),
     (3, 4, 1, 256, 256, 1),
+    (16, 64, 64, 256, 256, 9),     # >= 148 super-tiles: two sub-tiles per weight tile, single TMEM buffer
+    (4, 128, 112, 128, 128, 9),    # two sub-tiles, double-buffered TMEM, W not a multiple of 16... (112 = 7*16)
+    (1, 24, 40, 128, 256, 9),      # ragged super-tiles (H % 16 != 0, W % 16 != 0)
+    (2, 8, 16, 512, 256, 9),       # H = 8: one sub-tile
 ]
 
 
-@pytest.mark.parametrize("impl", [0, 1], ids=["tcgen05", "cudacore"])
+@pytest.mark.parametrize("impl", [0, 2, 1], ids=["tcgen05", "tcgen05gen1", "cudacore"])
 @pytest.mark.parametrize("case", CONV_CASES)
 def test_conv_nhwc(ops, case, impl):
     B, H, W, Ci, Co, taps = case
@@ -192,7 +196,7 @@ def test_conv_nhwc(ops, case, impl):
     assert (err <= 2 ** -7 * ref.abs() + 2e-2 * ref.abs().mean()).all(), float(err.max())
 
 
-@pytest.mark.parametrize("impl", [0, 1], ids=["tcgen05", "cudacore"])
+@pytest.mark.parametrize("impl", [0, 2, 1], ids=["tcgen05", "tcgen05gen1", "cudacore"])
 def test_conv_fused_shortcut_residual_tbias(ops, impl):
     # Conv_1 (3x3) + Conv_2 (1x1 shortcut) in one K loop, then * 1/sqrt(2)  (layerspp.py:268-276)
     g = torch.Generator().manual_seed(7)
@@ -275,7 +279,7 @@ def _network_report(engine, sd, x, t, flags):
     return ref[:, 0], out.cpu(), rep
 
 
-@pytest.mark.parametrize("flags", [2, 0], ids=["cuda-core-conv", "tcgen05-conv"])
+@pytest.mark.parametrize("flags", [2, 4, 0], ids=["cuda-core-conv", "tcgen05gen1-conv", "tcgen05-conv"])
 def test_ncsnpp_forward_vs_golden(engine, sd, golden_dir, flags):
     z = np.load(os.path.join(golden_dir, "ncsnpp_forward.npz"))
     x, t = _c(z["x"]), _c(z["t"])

@@ -1,0 +1,80 @@
+#!/usr/bin/env python
+"""Micro-benchmark of the implicit-GEMM convolution kernels on the shapes of the 16 x 4 s workload.
+Usage: python tools/conv_bench.py [--impl 0,2] [--iters 20] [--only IDX]"""
+import argparse
+import json
+import math
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from snr_aligned_diffse_b200 import ops  # noqa: E402
+
+SHAPES = [  # B, H, W, Cin, Cout, Cshortcut
+    (16, 256, 512, 128, 128, 0),
+    (16, 256, 512, 128, 128, 256),
+    (16, 128, 256, 128, 128, 0),
+    (16, 64, 128, 256, 256, 0),
+    (16, 64, 128, 256, 256, 512),
+    (16, 32, 64, 256, 256, 0),
+    (16, 16, 32, 256, 256, 0),
+    (16, 8, 16, 256, 256, 0),
+    (16, 4, 8, 256, 256, 0),
+]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--impl", default="0,2")
+    ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--only", type=int, default=-1)
+    ap.add_argument("--debug", action="store_true")
+    args = ap.parse_args()
+    impls = [int(i) for i in args.impl.split(",")]
+    g = torch.Generator().manual_seed(0)
+    for idx, (B, H, W, Ci, Co, Cs) in enumerate(SHAPES):
+        if args.only >= 0 and idx != args.only:
+            continue
+        x = (torch.randn(B, H, W, Ci, generator=g) * 0.5).to(torch.bfloat16).cuda()
+        x1 = (torch.randn(B, H, W, Cs, generator=g) * 0.5).to(torch.bfloat16).cuda() if Cs else None
+        wt = (torch.randn(Co, 9 * Ci + Cs, generator=g) / math.sqrt(9 * Ci + Cs)).to(torch.bfloat16).cuda()
+        bias = torch.randn(Co, generator=g).cuda()
+        flops = 2.0 * B * H * W * Co * (9 * Ci + Cs)
+        row = dict(shape=(B, H, W, Ci, Co, Cs), gflop=flops / 1e9)
+        outs = {}
+        for impl in impls:
+            for _ in range(3):
+                out = ops.conv_nhwc(x, wt, 9, x1=x1, bias=bias, impl=impl)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(args.iters):
+                out = ops.conv_nhwc(x, wt, 9, x1=x1, bias=bias, impl=impl)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / args.iters
+            if impl == 0 and args.debug:
+                from snr_aligned_diffse_b200 import _lib
+                dbg = torch.zeros(148 * 8, dtype=torch.int64, device="cuda")
+                _lib.load().snrse_conv_halo_set_debug(_lib.ptr(dbg))
+                ops.conv_nhwc(x, wt, 9, x1=x1, bias=bias, impl=0)
+                torch.cuda.synchronize()
+                _lib.load().snrse_conv_halo_set_debug(None)
+                d = dbg.view(148, 8).double()
+                d = d[d[:, 3] > 0]
+                names = ["mma_wait_a", "mma_wait_b", "mma_wait_acc", "mma_total", "epi_wait_full", "epi_body", "prodA_wait", "prodB_wait"]
+                row["dbg_kcycles"] = {n: round(float(d[:, i].mean()) / 1e3, 1) for i, n in enumerate(names)}
+            row[f"impl{impl}_ms"] = round(ms, 4)
+            row[f"impl{impl}_tflops"] = round(flops / ms / 1e9, 1)
+            outs[impl] = out
+        if len(outs) == 2:
+            a, b = (outs[i].float() for i in impls)
+            row["max_diff"] = float((a - b).abs().max())
+        print(json.dumps(row), flush=True)
+
+
+if __name__ == "__main__":
+    main()
