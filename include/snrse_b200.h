@@ -86,7 +86,8 @@ int snrse_ncsnpp_param_info(void* handle, int i, char* name, int name_cap, int* 
 int snrse_ncsnpp_param_shape(void* handle, int i, int64_t* dims, int* ndim); /* shape of the state-dict tensor */
 int snrse_ncsnpp_set_weights(void* handle, const void* device_blob);
 /* Plan for inputs [B][F][T]: returns the workspace size (or -1).  flags bit0: keep all activations
- * (debug taps); bit1: CUDA-core cross-check convolutions instead of tcgen05; bit2: first-generation tcgen05 kernel only. */
+ * (debug taps); bit1: CUDA-core cross-check convolutions instead of tcgen05; bit2: first-generation tcgen05 kernel only;
+ * bit3: single-CTA halo kernel instead of the 2-CTA one. */
 int64_t snrse_ncsnpp_plan_bytes(void* handle, int B, int F, int T, int flags);
 int snrse_ncsnpp_plan_bind(void* handle, int B, int F, int T, void* workspace, int64_t bytes);
 /* x (state), y (noisy), out: complex64 [B][F][T]; t [B] f32.  mode 0: dnn(cat[x,y], t);
@@ -105,7 +106,8 @@ int snrse_ncsnpp_read_tap(void* handle, int B, int F, int T, int module_idx, flo
  * conv: ddpm_conv3x3 / ddpm_conv1x1 / NIN (ncsnpp_utils/layers.py:100-124,537-555) as implicit GEMM:
  *   out[b,h,w,n] = scale*( sum_{tap,c} x0[b,h+dh,w+dw,c]*wt[n][tap*c0+c] + sum_c x1[b,h,w,c]*wt[n][taps0*c0+c]
  *                          + bias[n] + tbias[b*tb_stride+n] + res[b,h,w,n] );
- *   impl 0: tcgen05 (halo-reuse persistent kernel when eligible), 1: CUDA cores, 2: first-generation tcgen05 kernel. */
+ *   impl 0: tcgen05 (2-CTA halo-reuse persistent kernel when eligible), 1: CUDA cores, 2: first-generation tcgen05
+ *   kernel, 3: single-CTA halo kernel. */
 int snrse_conv_nhwc(const void* x0, int c0, int taps0, const void* x1, int c1, const void* wt, int n, const float* bias,
                     const float* tbias, int tb_stride, const void* res, float scale, void* out, int B, int H, int W,
                     int impl, void* stream);

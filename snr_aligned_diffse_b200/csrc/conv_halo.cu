@@ -282,11 +282,17 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
 
 int g_num_sms = 0;
 long long* g_halo_dbg = nullptr;
+}  // namespace
+long long* g_halo_dbg_shared = nullptr;
+namespace {
 
 }  // namespace
 
 // measurement hook: device buffer of [grid][8] cycle counters filled by subsequent launches (null: off)
-extern "C" void snrse_conv_halo_set_debug(long long* dev_counters) { g_halo_dbg = dev_counters; }
+extern "C" void snrse_conv_halo_set_debug(long long* dev_counters) {
+    g_halo_dbg = dev_counters;
+    g_halo_dbg_shared = dev_counters;
+}
 
 bool conv_halo_eligible(const ActView* a0, int taps0, int n_rows) {
     return taps0 == 9 && a0->W >= 16 && a0->H >= 8 && (n_rows == 128 || n_rows == 256);

@@ -1,0 +1,441 @@
+// 2-CTA (cta_group::2) version of the persistent halo-reuse implicit-GEMM 3x3 convolution.
+//
+// Two CTAs of one TPC form a cluster: each owns one super-tile of pixels (its own halo copies = the M=128-row
+// halves of a 256-row MMA) and HALF of every weight tile (N/2 rows).  The leader CTA issues
+// tcgen05.mma.cta_group::2 (M=256 across the pair): per MMA every SM streams 4 KB of pixels + N/2*32 B of
+// weights from its shared memory instead of 4 KB + N*32 B.  Measured on the 1-CTA kernel: SS-mode MMAs are
+// paced by shared-memory operand reads at ~64 B/clk/SM (133 clk per M128xN128xK16 MMA instead of the 64 clk
+// tensor floor), so halving the weight stream is what lifts the tensor pipe (profiles/r01_conv_halo_notes.md).
+// TMA loads of both CTAs complete on the LEADER's full barriers (cta_group::2 loads), tcgen05.commit
+// multicasts to both CTAs' empty / accumulator-full barriers, the peer's epilogue releases the accumulator
+// by a remote mbarrier arrive.  Everything else is as in conv_halo.cu (text below).
+//
+// Persistent halo-reuse implicit-GEMM 3x3 convolution for sm_100a (tcgen05 + TMEM + TMA).
+//
+// Same contract as conv_gemm.cu (ddpm_conv3x3 of sgmse-bbed/sgmse/backbones/ncsnpp_utils/layers.py:118-124,
+// with the fused 1x1 shortcut / bias / time-embedding bias / residual epilogue of layerspp.py:262-276), but
+// organised around L2->SM traffic, which is what bounded the first kernel (profiles/r01_v1_conv_gemm_ncu.md:
+// 30 KB fetched per MMAC, tensor pipe 34 % active):
+//
+//   * Super-tile = (8*SUB) x 16 output pixels of one image, SUB in {1,2}: SUB accumulators of 128 rows x N
+//     columns live in TMEM and share every weight tile  -> weight traffic per pixel / SUB.
+//   * Input patch: for each 64-channel chunk only THREE TMA boxes are fetched, the column-shifted halo copies
+//     {64 ch, 16, 8*SUB+2 rows} at w0-1, w0, w0+1.  The three row taps of a copy are the SAME shared-memory
+//     buffer addressed (r + 8u) * 16 rows further down: the UMMA descriptor start address moves in steps of
+//     2 KB, a multiple of the 1 KB swizzle atom, so no data is duplicated  -> 9 -> 3*(8*SUB+2)/(8*SUB) loads.
+//   * Two independent TMA rings (A: halo copies, B: per-tap weight tiles) fed by two producer warps.
+//   * Persistent CTAs (one per SM) walk super-tiles round-robin; with SUB*N <= 256 the TMEM accumulator is
+//     double-buffered so the epilogue of tile i overlaps the main loop of tile i+1.
+//   Per MMAC this fetches ~13 KB (N=128) / ~11 KB (N=256) instead of 30 KB.
+//
+// Warp roles (12 warps): 0 = A producer, 1 = MMA issuer + TMEM owner, 2 = B producer, 3 = idle,
+// 4..11 = epilogue: TMEM lane quarter = warp & 3, column half = (warp - 4) >> 2.  Each epilogue warp owns a
+// private 4 KB staging tile (32 pixels x 64 channels, 128-byte swizzle): the residual arrives in it by TMA,
+// the warp adds accumulator / bias / time-embedding bias in place, and one elected lane sends it out with a
+// TMA store (full 128-byte lines, ragged edges clipped by the tensor map) -- no per-thread global accesses.
+#include <cuda.h>
+
+#include "kernels.h"
+#include "ptx.cuh"
+#include "tma_host.h"
+
+namespace {
+
+constexpr int HALO_THREADS = 384;
+constexpr int EPI_WARPS = 8;
+constexpr int MAX_A = 4, MAX_B = 8;
+constexpr int TW = 16, SUB_ROWS = 8;
+
+struct Halo2Args {
+    int c0_chunks, c1_chunks;
+    int H, W, B;
+    int sub;                       // sub-tiles per super-tile (1 or 2)
+    int tiles_h, tiles_w, n_tiles;
+    int N;                         // output channels == columns per accumulator (128 or 256)
+    int na, nb;                    // ring depths
+    int acc_bufs;                  // 1 or 2 TMEM accumulator sets
+    int stg_bufs;                  // 1 or 2 staging tiles per epilogue warp
+    int has_res;
+    const float* bias;
+    const float* tbias;
+    int tb_stride;
+    float scale;
+    long long* dbg;                // optional per-CTA cycle counters [grid][8] (measurement builds only)
+};
+
+#define DBG_T0() long long t0__ = g.dbg ? clock64() : 0
+#define DBG_ADD(acc) do { if (g.dbg) { const long long t1__ = clock64(); acc += t1__ - t0__; t0__ = t1__; } } while (0)
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(HALO_THREADS, 1)
+conv_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
+                 const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapOut,
+                 const __grid_constant__ CUtensorMap mapRes, const Halo2Args g) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t a_full[MAX_A], a_empty[MAX_A], b_full[MAX_B], b_empty[MAX_B];
+    __shared__ __align__(8) uint64_t acc_full[2], acc_empty[2], res_bar[EPI_WARPS];
+    __shared__ __align__(16) float bsum[EPI_WARPS][128];   // per epilogue warp: (bias + time-embedding bias) * scale
+    __shared__ uint32_t tmem_base_smem;
+
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // provably warp-uniform
+    const uint32_t rank = blockIdx.x & 1u;   // == %cluster_ctarank for cluster dims (2,1,1); 0 = leader (issues the MMAs)
+    const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+    const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t a_bytes = (uint32_t)(SUB_ROWS * g.sub + 2) * TW * 128;   // 20 KB / 36 KB, multiple of 1 KB
+    const uint32_t b_bytes = (uint32_t)(g.N / 2) * 128;   // this CTA's half of the weight tile
+    const uint32_t a_base = smem_base, b_base = smem_base + (uint32_t)g.na * a_bytes;
+    const uint32_t stg_base = b_base + (uint32_t)g.nb * b_bytes;
+    const int n_astage = 3 * g.c0_chunks + g.c1_chunks;   // halo copies consumed per tile
+    const uint32_t acc_cols = (uint32_t)(g.sub * g.N);
+    const uint32_t tmem_cols = acc_cols * (uint32_t)g.acc_bufs;  // 128/256/512: power of two
+
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int i = 0; i < g.na; ++i) {
+                ptx::mbar_init(ptx::smem_u32(&a_full[i]), 1);
+                ptx::mbar_init(ptx::smem_u32(&a_empty[i]), 1);
+            }
+            for (int i = 0; i < g.nb; ++i) {
+                ptx::mbar_init(ptx::smem_u32(&b_full[i]), 1);
+                ptx::mbar_init(ptx::smem_u32(&b_empty[i]), 1);
+            }
+            for (int i = 0; i < 2; ++i) {
+                ptx::mbar_init(ptx::smem_u32(&acc_full[i]), 1);
+                ptx::mbar_init(ptx::smem_u32(&acc_empty[i]), 2 * EPI_WARPS);   // one arrive per epilogue warp of BOTH CTAs
+            }
+            for (int i = 0; i < EPI_WARPS; ++i) ptx::mbar_init(ptx::smem_u32(&res_bar[i]), 1);
+            ptx::fence_barrier_init();
+        }
+        __syncwarp();
+        ptx::tmem_alloc2(ptx::smem_u32(&tmem_base_smem), tmem_cols);
+        ptx::tmem_relinquish2();
+    } else if (warp == 0 && lane == 0) {
+        ptx::prefetch_tensormap(&mapA0);
+        if (g.c1_chunks > 0) ptx::prefetch_tensormap(&mapA1);
+    } else if (warp == 2 && lane == 0) {
+        ptx::prefetch_tensormap(&mapB);
+    } else if (warp == 3 && lane == 0) {
+        ptx::prefetch_tensormap(&mapOut);
+        if (g.has_res) ptx::prefetch_tensormap(&mapRes);
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::cluster_sync();             // both CTAs' barriers are initialised before any remote signal
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_base_smem, 0);
+    const int tiles_per_img = g.tiles_h * g.tiles_w;
+    const int n_ctiles = (g.n_tiles + 1) >> 1;   // cluster tiles = pairs of super-tiles
+
+    if (warp == 0) {
+        // =========================== A producer: halo copies ===========================
+        {
+            const bool elected = ptx::elect_one();
+            uint32_t it = 0;   // running stage counter across tiles
+            long long w_a = 0;
+            DBG_T0();
+            const uint32_t fb0 = ptx::mapa_rank0(ptx::smem_u32(&a_full[0]));   // leader's barriers (8 B apart)
+            for (int ct = cluster_id; ct < n_ctiles; ct += n_clusters) {
+                const int tile = 2 * ct + (int)rank;
+                const int b = tile / tiles_per_img, rem = tile % tiles_per_img;   // tile == n_tiles -> b == B: zero fill
+                const int h0 = (rem / g.tiles_w) * SUB_ROWS * g.sub, w0 = (rem % g.tiles_w) * TW;
+                for (int j = 0; j < n_astage; ++j, ++it) {
+                    const uint32_t s = it % (uint32_t)g.na, ph = (it / (uint32_t)g.na) & 1u;
+                    if (g.dbg) t0__ = clock64();
+                    ptx::mbar_wait(ptx::smem_u32(&a_empty[s]), ph ^ 1u);
+                    DBG_ADD(w_a);
+                    const uint32_t fb = fb0 + 8u * s;
+                    const uint32_t dst = a_base + s * a_bytes;
+                    const bool seg0 = j < 3 * g.c0_chunks;
+                    const int c = seg0 ? j / 3 : j - 3 * g.c0_chunks, sh = seg0 ? j % 3 : 1;
+                    if (elected) {
+                        if (rank == 0) ptx::mbar_arrive_expect_tx(ptx::smem_u32(&a_full[s]), 2 * a_bytes);
+                        // chunk c, column shift dw = sh - 1 (segment 0); the 1x1 shortcut operand is unshifted
+                        if (seg0) ptx::tma_load_4d_2sm(dst, &mapA0, fb, c * 64, w0 + sh - 1, h0 - 1, b);
+                        else ptx::tma_load_4d_2sm(dst, &mapA1, fb, c * 64, w0, h0, b);
+                    }
+                    __syncwarp();
+                }
+            }
+            if (g.dbg && elected) g.dbg[blockIdx.x * 8 + 6] = w_a;
+        }
+    } else if (warp == 2) {
+        // =========================== B producer: weight tiles ===========================
+        {
+            const bool elected = ptx::elect_one();
+            uint32_t it = 0;
+            long long w_b = 0;
+            DBG_T0();
+            const uint32_t fb0 = ptx::mapa_rank0(ptx::smem_u32(&b_full[0]));
+            for (int ct = cluster_id; ct < n_ctiles; ct += n_clusters) {
+                for (int j = 0; j < n_astage; ++j) {
+                    const bool seg0 = j < 3 * g.c0_chunks;
+                    const int c = j / 3, sh = j % 3;
+                    const int ntap = seg0 ? 3 : 1;
+                    for (int r = 0; r < ntap; ++r, ++it) {
+                        const uint32_t s = it % (uint32_t)g.nb, ph = (it / (uint32_t)g.nb) & 1u;
+                        if (g.dbg) t0__ = clock64();
+                        ptx::mbar_wait(ptx::smem_u32(&b_empty[s]), ph ^ 1u);
+                        DBG_ADD(w_b);
+                        // K layout of the packed weights: [tap = r*3 + sh][cin], then the shortcut channels
+                        const int kb = seg0 ? ((r * 3 + sh) * g.c0_chunks + c) : (9 * g.c0_chunks + (j - 3 * g.c0_chunks));
+                        if (elected) {
+                            if (rank == 0) ptx::mbar_arrive_expect_tx(ptx::smem_u32(&b_full[s]), 2 * b_bytes);
+                            ptx::tma_load_3d_2sm(b_base + s * b_bytes, &mapB, fb0 + 8u * s, kb * 64, (int)rank * (g.N / 2), 0);
+                        }
+                        __syncwarp();
+                    }
+                }
+            }
+            if (g.dbg && elected) g.dbg[blockIdx.x * 8 + 7] = w_b;
+        }
+    } else if (warp == 1) {
+        // =========================== MMA issuer (leader CTA only) ===========================
+        // The whole warp walks the loops (uniform control flow, descriptors in uniform registers); one elected lane
+        // issues the MMAs and the commits.
+        if (rank == 0) {
+            const uint32_t idesc = ptx::umma_idesc_bf16(256, (uint32_t)g.N);
+            const bool elected = ptx::elect_one();
+            uint32_t ita = 0, itb = 0, itt = 0;
+            long long w_a = 0, w_b = 0, w_acc = 0;
+            const long long t_start = g.dbg ? clock64() : 0;
+            DBG_T0();
+            for (int ct = cluster_id; ct < n_ctiles; ct += n_clusters, ++itt) {
+                const uint32_t buf = g.acc_bufs == 2 ? (itt & 1u) : 0u;
+                const uint32_t use = g.acc_bufs == 2 ? (itt >> 1) : itt;   // how often this buffer was used before
+                if (g.dbg) t0__ = clock64();
+                ptx::mbar_wait(ptx::smem_u32(&acc_empty[buf]), (use & 1u) ^ 1u);
+                DBG_ADD(w_acc);
+                ptx::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + buf * acc_cols;
+                for (int j = 0; j < n_astage; ++j, ++ita) {
+                    const uint32_t sa = ita % (uint32_t)g.na, pha = (ita / (uint32_t)g.na) & 1u;
+                    if (g.dbg) t0__ = clock64();
+                    ptx::mbar_wait(ptx::smem_u32(&a_full[sa]), pha);
+                    DBG_ADD(w_a);
+                    const bool seg0 = j < 3 * g.c0_chunks;
+                    const int ntap = seg0 ? 3 : 1;
+                    for (int r = 0; r < ntap; ++r, ++itb) {
+                        const uint32_t sb = itb % (uint32_t)g.nb, phb = (itb / (uint32_t)g.nb) & 1u;
+                        if (g.dbg) t0__ = clock64();
+                        ptx::mbar_wait(ptx::smem_u32(&b_full[sb]), phb);
+                        DBG_ADD(w_b);
+                        ptx::tc_fence_after();
+                        const uint64_t db = ptx::umma_desc_k_sw128(b_base + sb * b_bytes);
+                        const uint32_t first = (j > 0 || r > 0) ? 1u : 0u;
+                        for (int u = 0; u < g.sub; ++u) {
+                            // rows (r + 8u) .. of the halo copy: 16 pixels x 128 B per row = 2 KB steps
+                            const uint64_t da = ptx::umma_desc_k_sw128(a_base + sa * a_bytes + (uint32_t)(r + SUB_ROWS * u) * (TW * 128));
+                            const uint32_t d = d_tmem + (uint32_t)(u * g.N);
+                            if (elected) {
+                                ptx::mma_bf16_ss_2sm(d, da, db, idesc, first);
+                                ptx::mma_bf16_ss_2sm(d, da + 2, db + 2, idesc, 1u);
+                                ptx::mma_bf16_ss_2sm(d, da + 4, db + 4, idesc, 1u);
+                                ptx::mma_bf16_ss_2sm(d, da + 6, db + 6, idesc, 1u);
+                            }
+                        }
+                        if (elected) ptx::mma_commit_2sm(ptx::smem_u32(&b_empty[sb]));
+                        __syncwarp();
+                    }
+                    if (elected) ptx::mma_commit_2sm(ptx::smem_u32(&a_empty[sa]));
+                }
+                if (elected) ptx::mma_commit_2sm(ptx::smem_u32(&acc_full[buf]));
+                __syncwarp();
+            }
+            if (g.dbg && elected) {
+                g.dbg[blockIdx.x * 8 + 0] = w_a;
+                g.dbg[blockIdx.x * 8 + 1] = w_b;
+                g.dbg[blockIdx.x * 8 + 2] = w_acc;
+                g.dbg[blockIdx.x * 8 + 3] = clock64() - t_start;
+            }
+        }
+    } else if (warp >= 4) {
+        // =========================== epilogue ===========================
+        const int e = warp - 4, quarter = warp & 3, half = e >> 2;
+        const int n_pass = g.N >> 7;                   // passes of 64 channels per column half
+        const int half_cols = g.N >> 1;
+        const bool elected = ptx::elect_one();
+        const uint32_t my_stg = stg_base + (uint32_t)(e * g.stg_bufs) * 4096u;
+        const uint32_t my_rbar = ptx::smem_u32(&res_bar[e]);
+        const uint32_t row_off = (uint32_t)lane * 128u, sw = (uint32_t)(lane & 7);
+        float* bs = bsum[e];
+        uint32_t itt = 0, cnt = 0, rphase = 0;
+        int last_b = -1;
+        long long w_full = 0, t_body = 0;
+        DBG_T0();
+        for (int ct = cluster_id; ct < n_ctiles; ct += n_clusters, ++itt) {
+            const int tile = 2 * ct + (int)rank;
+            const int b = tile / tiles_per_img, rem = tile % tiles_per_img;
+            const int h0 = (rem / g.tiles_w) * SUB_ROWS * g.sub, w0 = (rem % g.tiles_w) * TW;
+            const uint32_t buf = g.acc_bufs == 2 ? (itt & 1u) : 0u;
+            const uint32_t use = g.acc_bufs == 2 ? (itt >> 1) : itt;
+            if (b != last_b) {   // new image: refresh this warp's slice of the per-channel additive term
+                last_b = b;
+                const int bb = b < g.B ? b : g.B - 1;
+                __syncwarp();
+                for (int i = lane; i < half_cols; i += 32) {
+                    const int ch = half * half_cols + i;
+                    float v = g.bias ? __ldg(g.bias + ch) : 0.f;
+                    if (g.tbias) v += __ldg(g.tbias + (int64_t)bb * g.tb_stride + ch);
+                    bs[i] = v * g.scale;
+                }
+                __syncwarp();
+            }
+            if (g.dbg) t0__ = clock64();
+            ptx::mbar_wait(ptx::smem_u32(&acc_full[buf]), use & 1u);
+            DBG_ADD(w_full);
+            ptx::tc_fence_after();
+            for (int u = 0; u < g.sub; ++u) {
+                const int hrow = h0 + SUB_ROWS * u + 2 * quarter;   // this warp's two image rows (32 pixels)
+                for (int p = 0; p < n_pass; ++p, ++cnt) {
+                    const int cl = 64 * p, cbase = half * half_cols + cl;   // column within the half / the tensor
+                    const uint32_t stg = my_stg + (g.stg_bufs == 2 ? (cnt & 1u) * 4096u : 0u);
+                    // the TMA store that last read this staging tile has drained it
+                    if (elected) {
+                        if (g.stg_bufs == 2) ptx::bulk_wait_group_read<1>(); else ptx::bulk_wait_group_read<0>();
+                    }
+                    __syncwarp();
+                    if (g.has_res && elected) {
+                        ptx::mbar_arrive_expect_tx(my_rbar, 4096u);
+                        ptx::tma_load_4d(stg, &mapRes, my_rbar, cbase, w0, hrow, b);
+                    }
+                    uint32_t v[64];
+                    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * acc_cols + (uint32_t)(u * g.N + cbase);
+                    ptx::tmem_ld_32x32(taddr, v);
+                    ptx::tmem_ld_32x32(taddr + 32u, v + 32);
+                    ptx::tmem_ld_wait();
+                    if (g.has_res) {
+                        ptx::mbar_wait(my_rbar, rphase);
+                        rphase ^= 1u;
+                    }
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const float4 b0 = *reinterpret_cast<const float4*>(bs + cl + 8 * q);
+                        const float4 b1 = *reinterpret_cast<const float4*>(bs + cl + 8 * q + 4);
+                        float f[8];
+                        f[0] = fmaf(__uint_as_float(v[8 * q + 0]), g.scale, b0.x);
+                        f[1] = fmaf(__uint_as_float(v[8 * q + 1]), g.scale, b0.y);
+                        f[2] = fmaf(__uint_as_float(v[8 * q + 2]), g.scale, b0.z);
+                        f[3] = fmaf(__uint_as_float(v[8 * q + 3]), g.scale, b0.w);
+                        f[4] = fmaf(__uint_as_float(v[8 * q + 4]), g.scale, b1.x);
+                        f[5] = fmaf(__uint_as_float(v[8 * q + 5]), g.scale, b1.y);
+                        f[6] = fmaf(__uint_as_float(v[8 * q + 6]), g.scale, b1.z);
+                        f[7] = fmaf(__uint_as_float(v[8 * q + 7]), g.scale, b1.w);
+                        const uint32_t addr = stg + row_off + (((uint32_t)q ^ sw) << 4);   // 128-byte swizzle
+                        if (g.has_res) {
+                            float rr[8];
+                            unpack8(ptx::lds128(addr), rr);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) f[j] = fmaf(rr[j], g.scale, f[j]);
+                        }
+                        ptx::sts128(addr, pack8(f));
+                    }
+                    ptx::fence_proxy_async();
+                    __syncwarp();
+                    if (elected) {
+                        ptx::tma_store_4d(&mapOut, stg, cbase, w0, hrow, b);
+                        ptx::bulk_commit_group();
+                    }
+                }
+            }
+            // all TMEM reads of this accumulator set are complete: hand it back to the MMA warp
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive_remote(ptx::mapa_rank0(ptx::smem_u32(&acc_empty[buf])));
+            DBG_ADD(t_body);
+        }
+        if (elected) ptx::bulk_wait_group_read<0>();   // staging tiles must outlive the last stores' reads
+        if (g.dbg && threadIdx.x == 128) {
+            g.dbg[blockIdx.x * 8 + 4] = w_full;
+            g.dbg[blockIdx.x * 8 + 5] = t_body;
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::cluster_sync();             // the peer's TMEM / smem stay valid until the leader's last MMA retired
+    if (warp == 1) {
+        __syncwarp();
+        ptx::tmem_dealloc2(tmem_base, tmem_cols);
+    }
+}
+
+int g_num_sms2 = 0;
+}  // namespace
+extern long long* g_halo_dbg_shared;
+namespace {
+
+}  // namespace
+
+int conv_halo2_make_plan(ConvHaloPlan* p, const ActView* a0, const ActView* a1, const bf16* wt, int n_rows,
+                         const float* bias, const float* tbias, int tb_stride, const ActView* res, float scale, bf16* out,
+                         int out_ld) {
+    SNRSE_CHECK_ARG(conv_halo_eligible(a0, 9, n_rows), "conv_halo2: shape not eligible");
+    SNRSE_CHECK_ARG(a0->C % 64 == 0 && a0->ld % 8 == 0, "conv_halo2: Cin must be a multiple of 64");
+    SNRSE_CHECK_ARG(!a1 || (a1->C % 64 == 0 && a1->ld % 8 == 0 && a1->H == a0->H && a1->W == a0->W && a1->B == a0->B),
+                    "conv_halo2: bad shortcut operand");
+    SNRSE_CHECK_ARG(out_ld % 8 == 0 && (!res || res->ld % 8 == 0), "conv_halo2: pitches must be multiples of 8");
+    if (g_num_sms2 == 0) {
+        int dev = 0;
+        SNRSE_CUDA(cudaGetDevice(&dev));
+        SNRSE_CUDA(cudaDeviceGetAttribute(&g_num_sms2, cudaDevAttrMultiProcessorCount, dev));
+    }
+    memset(p, 0, sizeof(*p));
+    const int tiles_w = cdiv(a0->W, TW);
+    int sub = 2;
+    if (a0->H < 16 || (int64_t)a0->B * cdiv(a0->H, 16) * tiles_w < g_num_sms2) sub = 1;
+    p->sub = sub;
+    p->c0_chunks = a0->C / 64;
+    p->c1_chunks = a1 ? a1->C / 64 : 0;
+    p->B = a0->B; p->H = a0->H; p->W = a0->W;
+    p->tiles_h = cdiv(a0->H, SUB_ROWS * sub);
+    p->tiles_w = tiles_w;
+    p->n_tiles = a0->B * p->tiles_h * p->tiles_w;
+    p->N = n_rows;
+    p->acc_bufs = (sub * n_rows <= 256) ? 2 : 1;
+    const int a_bytes = (SUB_ROWS * sub + 2) * TW * 128, b_bytes = (n_rows / 2) * 128;
+    const int budget = 220 * 1024;   // dynamic shared memory (static: barriers + per-warp bias slices, ~4.3 KB)
+    int na = 3, stg = 2;
+    int nb = (budget - na * a_bytes - stg * EPI_WARPS * 4096) / b_bytes;
+    if (nb < 4) {
+        stg = 1;
+        nb = (budget - na * a_bytes - stg * EPI_WARPS * 4096) / b_bytes;
+    }
+    if (nb > MAX_B) nb = MAX_B;
+    SNRSE_CHECK_ARG(nb >= 4, "conv_halo2: shared memory budget");
+    p->na = na; p->nb = nb; p->stg_bufs = stg;
+    p->smem_bytes = na * a_bytes + nb * b_bytes + stg * EPI_WARPS * 4096 + 1024;
+    const int n_ctiles = (p->n_tiles + 1) / 2, max_clusters = g_num_sms2 / 2;
+    p->grid = 2 * (n_ctiles < max_clusters ? n_ctiles : max_clusters);
+    p->bias = bias; p->tbias = tbias; p->tb_stride = tb_stride;
+    p->res = res ? res->ptr : nullptr; p->res_ld = res ? res->ld : 0;
+    p->scale = scale; p->out = out; p->out_ld = out_ld;
+    const int box_h = SUB_ROWS * sub + 2;
+    SNRSE_TRY(tma_make_act_map(&p->mapA0, a0->ptr, a0->C, a0->W, a0->H, a0->B, a0->ld, 64, TW, box_h));
+    if (a1) SNRSE_TRY(tma_make_act_map(&p->mapA1, a1->ptr, a1->C, a1->W, a1->H, a1->B, a1->ld, 64, TW, box_h));
+    else p->mapA1 = p->mapA0;
+    const int64_t ktot = 64 * (int64_t)(9 * p->c0_chunks + p->c1_chunks);
+    SNRSE_TRY(tma_make_wt_map(&p->mapB, wt, ktot, n_rows, 1, ktot * n_rows, 64, n_rows / 2));
+    // epilogue tiles: 32 pixels (2 image rows x 16) x 64 channels
+    SNRSE_TRY(tma_make_act_map(&p->mapOut, out, n_rows, a0->W, a0->H, a0->B, out_ld, 64, TW, 2));
+    if (res) SNRSE_TRY(tma_make_act_map(&p->mapRes, res->ptr, n_rows, a0->W, a0->H, a0->B, res->ld, 64, TW, 2));
+    else p->mapRes = p->mapOut;
+    return SNRSE_OK;
+}
+
+int conv_halo2_launch(const ConvHaloPlan* p, cudaStream_t s) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        SNRSE_CUDA(cudaFuncSetAttribute(conv_halo2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024));
+        attr_set = true;
+    }
+    Halo2Args g;
+    g.c0_chunks = p->c0_chunks; g.c1_chunks = p->c1_chunks;
+    g.H = p->H; g.W = p->W; g.B = p->B;
+    g.sub = p->sub; g.tiles_h = p->tiles_h; g.tiles_w = p->tiles_w; g.n_tiles = p->n_tiles;
+    g.N = p->N; g.na = p->na; g.nb = p->nb; g.acc_bufs = p->acc_bufs; g.stg_bufs = p->stg_bufs;
+    g.has_res = p->res != nullptr;
+    g.bias = p->bias; g.tbias = p->tbias; g.tb_stride = p->tb_stride;
+    g.scale = p->scale;
+    g.dbg = g_halo_dbg_shared;
+    conv_halo2_kernel<<<p->grid, HALO_THREADS, p->smem_bytes, s>>>(p->mapA0, p->mapA1, p->mapB, p->mapOut, p->mapRes, g);
+    SNRSE_LAUNCH_CHECK();
+    return SNRSE_OK;
+}

@@ -351,9 +351,15 @@ int rec_gemm(Plan& P, int a0, int taps0, int a1, int64_t w_off, int n_rows, int6
         const double by = 2.0 * (px * (va0.C + (a1 >= 0 ? va1.C : 0) + n_rows + (res >= 0 ? n_rows : 0)) + kt * n_rows);
         if (!(p.flags & 4) && conv_halo_eligible(&va0, taps0, n_rows)) {
             ConvHaloPlan hp;
-            SNRSE_TRY(conv_halo_make_plan(&hp, &va0, a1 >= 0 ? &va1 : nullptr, e.wb(w_off), n_rows, bias, tb, tb_stride,
-                                          res >= 0 ? &vres : nullptr, scale, vout.ptr, vout.ld));
-            p.add(LK_GEMM, 2.0 * px * n_rows * kt, by, [hp](cudaStream_t s) { return conv_halo_launch(&hp, s); });
+            if (p.flags & 8) {   // single-CTA halo kernel
+                SNRSE_TRY(conv_halo_make_plan(&hp, &va0, a1 >= 0 ? &va1 : nullptr, e.wb(w_off), n_rows, bias, tb, tb_stride,
+                                              res >= 0 ? &vres : nullptr, scale, vout.ptr, vout.ld));
+                p.add(LK_GEMM, 2.0 * px * n_rows * kt, by, [hp](cudaStream_t s) { return conv_halo_launch(&hp, s); });
+            } else {             // 2-CTA (cta_group::2) halo kernel
+                SNRSE_TRY(conv_halo2_make_plan(&hp, &va0, a1 >= 0 ? &va1 : nullptr, e.wb(w_off), n_rows, bias, tb, tb_stride,
+                                               res >= 0 ? &vres : nullptr, scale, vout.ptr, vout.ld));
+                p.add(LK_GEMM, 2.0 * px * n_rows * kt, by, [hp](cudaStream_t s) { return conv_halo2_launch(&hp, s); });
+            }
             return SNRSE_OK;
         }
         ConvGemmPlan g;
@@ -738,7 +744,7 @@ int snrse_ncsnpp_set_weights(void* handle, const void* device_blob) {
 }
 
 // flags: bit0 = keep every activation alive (debug taps), bit1 = CUDA-core cross-check convolutions,
-//        bit2 = first-generation (non-halo) tcgen05 kernel for every convolution
+//        bit2 = first-generation (non-halo) tcgen05 kernel for every convolution, bit3 = single-CTA halo kernel
 int64_t snrse_ncsnpp_plan_bytes(void* handle, int B, int F, int T, int flags) {
     Engine* e = static_cast<Engine*>(handle);
     if (!e || B < 1 || F < 1 || T < 1 || (F % (1 << (e->n_levels - 1))) || (T % (1 << (e->n_levels - 1)))) {

@@ -48,8 +48,8 @@ int conv_gemm_launch(const ConvGemmPlan* p, cudaStream_t s);
 // ----------------------------------------------------------------------------- conv_halo.cu
 // Persistent halo-reuse variant for 3x3 convolutions with W >= 16, H >= 8, N in {128, 256} (same epilogue).
 struct ConvHaloPlan {
-    CUtensorMap mapA0, mapA1, mapB;
-    int c0_chunks, c1_chunks, B, H, W, sub, tiles_h, tiles_w, n_tiles, N, na, nb, acc_bufs, grid, smem_bytes;
+    CUtensorMap mapA0, mapA1, mapB, mapOut, mapRes;   // mapOut / mapRes: 2-CTA kernel only (TMA epilogue)
+    int c0_chunks, c1_chunks, B, H, W, sub, tiles_h, tiles_w, n_tiles, N, na, nb, acc_bufs, stg_bufs, grid, smem_bytes;
     const float* bias;
     const float* tbias;
     int tb_stride;
@@ -64,6 +64,11 @@ int conv_halo_make_plan(ConvHaloPlan* p, const ActView* a0, const ActView* a1, c
                         const float* bias, const float* tbias, int tb_stride, const ActView* res, float scale, bf16* out,
                         int out_ld);
 int conv_halo_launch(const ConvHaloPlan* p, cudaStream_t s);
+// 2-CTA (cta_group::2) version, same plan structure (conv_halo2.cu)
+int conv_halo2_make_plan(ConvHaloPlan* p, const ActView* a0, const ActView* a1, const bf16* wt, int n_rows,
+                         const float* bias, const float* tbias, int tb_stride, const ActView* res, float scale, bf16* out,
+                         int out_ld);
+int conv_halo2_launch(const ConvHaloPlan* p, cudaStream_t s);
 
 // ----------------------------------------------------------------------------- conv_simt.cu
 // Reference-grade direct convolution on CUDA cores (debug / cross-check path, fp32 accumulate).

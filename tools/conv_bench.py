@@ -56,17 +56,17 @@ def main():
             e1.record()
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / args.iters
-            if impl == 0 and args.debug:
+            if impl in (0, 3) and args.debug:
                 from snr_aligned_diffse_b200 import _lib
                 dbg = torch.zeros(148 * 8, dtype=torch.int64, device="cuda")
                 _lib.load().snrse_conv_halo_set_debug(_lib.ptr(dbg))
-                ops.conv_nhwc(x, wt, 9, x1=x1, bias=bias, impl=0)
+                ops.conv_nhwc(x, wt, 9, x1=x1, bias=bias, impl=impl)
                 torch.cuda.synchronize()
                 _lib.load().snrse_conv_halo_set_debug(None)
                 d = dbg.view(148, 8).double()
                 d = d[d[:, 3] > 0]
                 names = ["mma_wait_a", "mma_wait_b", "mma_wait_acc", "mma_total", "epi_wait_full", "epi_body", "prodA_wait", "prodB_wait"]
-                row["dbg_kcycles"] = {n: round(float(d[:, i].mean()) / 1e3, 1) for i, n in enumerate(names)}
+                row[f"dbg{impl}_kcycles"] = {n: round(float(d[:, i].mean()) / 1e3, 1) for i, n in enumerate(names)}
             row[f"impl{impl}_ms"] = round(ms, 4)
             row[f"impl{impl}_tflops"] = round(flops / ms / 1e9, 1)
             outs[impl] = out
