@@ -100,13 +100,14 @@ int snrse_conv_nhwc(const void* x0, int c0, int taps0, const void* x1, int c1, c
         return conv_simt_launch(&a0, taps0, x1 ? &a1 : nullptr, static_cast<const bf16*>(wt), n, bias, tbias, tb_stride,
                                 res ? &r : nullptr, scale, static_cast<bf16*>(out), n, S(stream));
     }
-    if ((impl == 0 || impl == 3) && conv_halo_eligible(&a0, taps0, n)) {
+    if (impl == 3 && conv_halo_eligible(&a0, taps0, n)) {
         ConvHaloPlan hp;
-        if (impl == 3) {
-            SNRSE_TRY(conv_halo_make_plan(&hp, &a0, x1 ? &a1 : nullptr, static_cast<const bf16*>(wt), n, bias, tbias,
-                                          tb_stride, res ? &r : nullptr, scale, static_cast<bf16*>(out), n));
-            return conv_halo_launch(&hp, S(stream));
-        }
+        SNRSE_TRY(conv_halo_make_plan(&hp, &a0, x1 ? &a1 : nullptr, static_cast<const bf16*>(wt), n, bias, tbias,
+                                      tb_stride, res ? &r : nullptr, scale, static_cast<bf16*>(out), n));
+        return conv_halo_launch(&hp, S(stream));
+    }
+    if (impl == 0 && conv_halo2_eligible(&a0, taps0, n)) {
+        ConvHaloPlan hp;
         SNRSE_TRY(conv_halo2_make_plan(&hp, &a0, x1 ? &a1 : nullptr, static_cast<const bf16*>(wt), n, bias, tbias, tb_stride,
                                        res ? &r : nullptr, scale, static_cast<bf16*>(out), n));
         return conv_halo2_launch(&hp, S(stream));

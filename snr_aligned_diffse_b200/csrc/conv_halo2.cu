@@ -1,39 +1,31 @@
-// 2-CTA (cta_group::2) version of the persistent halo-reuse implicit-GEMM 3x3 convolution.
-//
-// Two CTAs of one TPC form a cluster: each owns one super-tile of pixels (its own halo copies = the M=128-row
-// halves of a 256-row MMA) and HALF of every weight tile (N/2 rows).  The leader CTA issues
-// tcgen05.mma.cta_group::2 (M=256 across the pair): per MMA every SM streams 4 KB of pixels + N/2*32 B of
-// weights from its shared memory instead of 4 KB + N*32 B.  Measured on the 1-CTA kernel: SS-mode MMAs are
-// paced by shared-memory operand reads at ~64 B/clk/SM (133 clk per M128xN128xK16 MMA instead of the 64 clk
-// tensor floor), so halving the weight stream is what lifts the tensor pipe (profiles/r01_conv_halo_notes.md).
-// TMA loads of both CTAs complete on the LEADER's full barriers (cta_group::2 loads), tcgen05.commit
-// multicasts to both CTAs' empty / accumulator-full barriers, the peer's epilogue releases the accumulator
-// by a remote mbarrier arrive.  Everything else is as in conv_halo.cu (text below).
-//
-// Persistent halo-reuse implicit-GEMM 3x3 convolution for sm_100a (tcgen05 + TMEM + TMA).
+// Persistent 2-CTA (cta_group::2) implicit-GEMM 3x3 convolution for sm_100a (tcgen05 + TMEM + TMA).
 //
 // Same contract as conv_gemm.cu (ddpm_conv3x3 of sgmse-bbed/sgmse/backbones/ncsnpp_utils/layers.py:118-124,
-// with the fused 1x1 shortcut / bias / time-embedding bias / residual epilogue of layerspp.py:262-276), but
-// organised around L2->SM traffic, which is what bounded the first kernel (profiles/r01_v1_conv_gemm_ncu.md:
-// 30 KB fetched per MMAC, tensor pipe 34 % active):
+// with the fused 1x1 shortcut / bias / time-embedding bias / residual epilogue of layerspp.py:262-276).
+// Design facts it is built on (profiles/r01_mma_probe.md):
+//   * a single CTA with both operands in shared memory tops out at 60 % (N=128) / 75 % (N=256) of the tensor
+//     peak; a CTA pair (M=256 across two SMs, each SM streaming its 128 pixel rows and HALF of the weight tile)
+//     reaches 100 % at N=128 and N=256  -> two CTAs of one TPC form a cluster, the leader issues the MMAs;
+//   * a SWIZZLE_128B K-major UMMA descriptor may start at any 128-byte row of a TMA-written tile and use any
+//     multiple of 128 B as the stride between 8-row groups  -> ONE halo tile per 64-channel chunk serves all
+//     nine taps: sub-tile = 16 image rows x 8 pixels (M = 128, one 8-row group per image row), halo tile =
+//     [16*SUB+2 rows][10 pixels][64 ch]; tap (r,s) of sub-tile u is the same buffer addressed from row
+//     ((r + 16u)*10 + s) with a group stride of 10 rows (1280 B).  L2->SM traffic per output pixel drops from
+//     9 (first kernel) / 3.4 (three column-shifted copies) to 1.33 tile loads;
+//   * the MMA / TMA issue loops are warp-uniform (descriptors in uniform registers, one elected lane issues).
 //
-//   * Super-tile = (8*SUB) x 16 output pixels of one image, SUB in {1,2}: SUB accumulators of 128 rows x N
-//     columns live in TMEM and share every weight tile  -> weight traffic per pixel / SUB.
-//   * Input patch: for each 64-channel chunk only THREE TMA boxes are fetched, the column-shifted halo copies
-//     {64 ch, 16, 8*SUB+2 rows} at w0-1, w0, w0+1.  The three row taps of a copy are the SAME shared-memory
-//     buffer addressed (r + 8u) * 16 rows further down: the UMMA descriptor start address moves in steps of
-//     2 KB, a multiple of the 1 KB swizzle atom, so no data is duplicated  -> 9 -> 3*(8*SUB+2)/(8*SUB) loads.
-//   * Two independent TMA rings (A: halo copies, B: per-tap weight tiles) fed by two producer warps.
-//   * Persistent CTAs (one per SM) walk super-tiles round-robin; with SUB*N <= 256 the TMEM accumulator is
-//     double-buffered so the epilogue of tile i overlaps the main loop of tile i+1.
-//   Per MMAC this fetches ~13 KB (N=128) / ~11 KB (N=256) instead of 30 KB.
+// Super-tile = SUB (1 or 2) sub-tiles stacked in H sharing every weight tile; SUB accumulators of 128 lanes x N
+// columns per CTA in TMEM, double-buffered when SUB*N <= 256 so the epilogue of tile i overlaps tile i+1.
+// Two TMA rings: A (halo tiles, one per channel chunk) and B (per-tap weight tiles, N/2 rows per CTA); both
+// CTAs' loads complete on the LEADER's barriers, tcgen05.commit multicasts to both CTAs.
 //
-// Warp roles (12 warps): 0 = A producer, 1 = MMA issuer + TMEM owner, 2 = B producer, 3 = idle,
-// 4..11 = epilogue: TMEM lane quarter = warp & 3, column half = (warp - 4) >> 2.  Each epilogue warp owns a
-// private 4 KB staging tile (32 pixels x 64 channels, 128-byte swizzle): the residual arrives in it by TMA,
-// the warp adds accumulator / bias / time-embedding bias in place, and one elected lane sends it out with a
-// TMA store (full 128-byte lines, ragged edges clipped by the tensor map) -- no per-thread global accesses.
+// Warp roles (12 warps): 0..7 = epilogue (TMEM lane quarter = warp & 3: 4 image rows x 8 pixels; column half =
+// warp >> 2), 8 = A producer, 9 = B producer, 10 / 11 = MMA issuers of sub-tile 0 / 1 (11 owns TMEM).
+// Each epilogue warp owns private 4 KB staging tiles (32 pixels x 64 channels, 128-byte swizzle): the residual
+// arrives there by TMA, the warp adds accumulator / bias / time-embedding bias in place, one elected lane sends
+// it out with a TMA store (full 128-byte lines, ragged edges clipped by the tensor map).
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "kernels.h"
 #include "ptx.cuh"
@@ -43,8 +35,12 @@ namespace {
 
 constexpr int HALO_THREADS = 384;
 constexpr int EPI_WARPS = 8;
-constexpr int MAX_A = 4, MAX_B = 8;
-constexpr int TW = 16, SUB_ROWS = 8;
+// The warp scheduler favours the highest warp id of a sub-partition: the single-lane issue warps sit above the
+// epilogue warps so that their (few) instructions never queue behind epilogue arithmetic.
+constexpr int W_PROD_A = 8, W_PROD_B = 9, W_MMA0 = 10, W_MMA1 = 11;
+constexpr int MAX_A = 3, MAX_B = 8;
+constexpr int TW = 8, SUB_ROWS = 16, HALO_W = TW + 2;
+constexpr uint32_t ROW_B = 128;                       // one pixel = 64 bf16 channels = one swizzle row
 
 struct Halo2Args {
     int c0_chunks, c1_chunks;
@@ -66,10 +62,25 @@ struct Halo2Args {
 #define DBG_T0() long long t0__ = g.dbg ? clock64() : 0
 #define DBG_ADD(acc) do { if (g.dbg) { const long long t1__ = clock64(); acc += t1__ - t0__; t0__ = t1__; } } while (0)
 
+__host__ __device__ inline uint32_t halo_stage_bytes(int sub) {   // halo tile rounded up to the 1 KB swizzle atom
+    return (((uint32_t)(SUB_ROWS * sub + 2) * HALO_W * ROW_B) + 1023u) & ~1023u;
+}
+
+// K-major SWIZZLE_128B descriptor with an explicit 8-row-group stride (bytes); start may be any 128-byte row
+__device__ __forceinline__ uint64_t umma_desc_rows(uint32_t smem_addr, uint32_t group_stride) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(group_stride >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(HALO_THREADS, 1)
 conv_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
-                 const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapOut,
-                 const __grid_constant__ CUtensorMap mapRes, const Halo2Args g) {
+                  const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapOut,
+                  const __grid_constant__ CUtensorMap mapRes, const Halo2Args g) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t a_full[MAX_A], a_empty[MAX_A], b_full[MAX_B], b_empty[MAX_B];
     __shared__ __align__(8) uint64_t acc_full[2], acc_empty[2], res_bar[EPI_WARPS];
@@ -80,26 +91,27 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
     const uint32_t rank = blockIdx.x & 1u;   // == %cluster_ctarank for cluster dims (2,1,1); 0 = leader (issues the MMAs)
     const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
     const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t a_bytes = (uint32_t)(SUB_ROWS * g.sub + 2) * TW * 128;   // 20 KB / 36 KB, multiple of 1 KB
-    const uint32_t b_bytes = (uint32_t)(g.N / 2) * 128;   // this CTA's half of the weight tile
+    const uint32_t a_bytes = halo_stage_bytes(g.sub);                                   // ring slot
+    const uint32_t a_tx = (uint32_t)(SUB_ROWS * g.sub + 2) * HALO_W * ROW_B;            // bytes one TMA box delivers
+    const uint32_t b_bytes = (uint32_t)(g.N / 2) * ROW_B;   // this CTA's half of the weight tile
     const uint32_t a_base = smem_base, b_base = smem_base + (uint32_t)g.na * a_bytes;
     const uint32_t stg_base = b_base + (uint32_t)g.nb * b_bytes;
-    const int n_astage = 3 * g.c0_chunks + g.c1_chunks;   // halo copies consumed per tile
+    const int n_astage = g.c0_chunks + g.c1_chunks;   // halo tiles consumed per super-tile
     const uint32_t acc_cols = (uint32_t)(g.sub * g.N);
     const uint32_t tmem_cols = acc_cols * (uint32_t)g.acc_bufs;  // 128/256/512: power of two
 
-    if (warp == 1) {
+    if (warp == W_MMA1) {
         if (lane == 0) {
             for (int i = 0; i < g.na; ++i) {
                 ptx::mbar_init(ptx::smem_u32(&a_full[i]), 1);
-                ptx::mbar_init(ptx::smem_u32(&a_empty[i]), 1);
+                ptx::mbar_init(ptx::smem_u32(&a_empty[i]), (uint32_t)g.sub);   // one commit per issuing warp
             }
             for (int i = 0; i < g.nb; ++i) {
                 ptx::mbar_init(ptx::smem_u32(&b_full[i]), 1);
-                ptx::mbar_init(ptx::smem_u32(&b_empty[i]), 1);
+                ptx::mbar_init(ptx::smem_u32(&b_empty[i]), (uint32_t)g.sub);
             }
             for (int i = 0; i < 2; ++i) {
-                ptx::mbar_init(ptx::smem_u32(&acc_full[i]), 1);
+                ptx::mbar_init(ptx::smem_u32(&acc_full[i]), (uint32_t)g.sub);
                 ptx::mbar_init(ptx::smem_u32(&acc_empty[i]), 2 * EPI_WARPS);   // one arrive per epilogue warp of BOTH CTAs
             }
             for (int i = 0; i < EPI_WARPS; ++i) ptx::mbar_init(ptx::smem_u32(&res_bar[i]), 1);
@@ -108,12 +120,12 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
         __syncwarp();
         ptx::tmem_alloc2(ptx::smem_u32(&tmem_base_smem), tmem_cols);
         ptx::tmem_relinquish2();
-    } else if (warp == 0 && lane == 0) {
+    } else if (warp == W_PROD_A && lane == 0) {
         ptx::prefetch_tensormap(&mapA0);
         if (g.c1_chunks > 0) ptx::prefetch_tensormap(&mapA1);
-    } else if (warp == 2 && lane == 0) {
+    } else if (warp == W_PROD_B && lane == 0) {
         ptx::prefetch_tensormap(&mapB);
-    } else if (warp == 3 && lane == 0) {
+    } else if (warp == W_MMA0 && lane == 0) {
         ptx::prefetch_tensormap(&mapOut);
         if (g.has_res) ptx::prefetch_tensormap(&mapRes);
     }
@@ -125,73 +137,71 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
     const int tiles_per_img = g.tiles_h * g.tiles_w;
     const int n_ctiles = (g.n_tiles + 1) >> 1;   // cluster tiles = pairs of super-tiles
 
-    if (warp == 0) {
-        // =========================== A producer: halo copies ===========================
-        {
-            const bool elected = ptx::elect_one();
-            uint32_t it = 0;   // running stage counter across tiles
-            long long w_a = 0;
-            DBG_T0();
-            const uint32_t fb0 = ptx::mapa_rank0(ptx::smem_u32(&a_full[0]));   // leader's barriers (8 B apart)
-            for (int ct = cluster_id; ct < n_ctiles; ct += n_clusters) {
-                const int tile = 2 * ct + (int)rank;
-                const int b = tile / tiles_per_img, rem = tile % tiles_per_img;   // tile == n_tiles -> b == B: zero fill
-                const int h0 = (rem / g.tiles_w) * SUB_ROWS * g.sub, w0 = (rem % g.tiles_w) * TW;
-                for (int j = 0; j < n_astage; ++j, ++it) {
-                    const uint32_t s = it % (uint32_t)g.na, ph = (it / (uint32_t)g.na) & 1u;
+    if (warp == W_PROD_A) {
+        // =========================== A producer: one halo tile per channel chunk ===========================
+        const bool elected = ptx::elect_one();
+        uint32_t it = 0;   // running stage counter across tiles
+        long long w_a = 0;
+        DBG_T0();
+        const uint32_t fb0 = ptx::mapa_rank0(ptx::smem_u32(&a_full[0]));   // leader's barriers (8 B apart)
+        for (int ct = cluster_id; ct < n_ctiles; ct += n_clusters) {
+            const int tile = 2 * ct + (int)rank;
+            const int b = tile / tiles_per_img, rem = tile % tiles_per_img;   // tile == n_tiles -> b == B: zero fill
+            const int h0 = (rem / g.tiles_w) * SUB_ROWS * g.sub, w0 = (rem % g.tiles_w) * TW;
+            for (int j = 0; j < n_astage; ++j, ++it) {
+                const uint32_t s = it % (uint32_t)g.na, ph = (it / (uint32_t)g.na) & 1u;
+                if (g.dbg) t0__ = clock64();
+                ptx::mbar_wait(ptx::smem_u32(&a_empty[s]), ph ^ 1u);
+                DBG_ADD(w_a);
+                const uint32_t dst = a_base + s * a_bytes;
+                const bool seg0 = j < g.c0_chunks;
+                if (elected) {
+                    if (rank == 0) ptx::mbar_arrive_expect_tx(ptx::smem_u32(&a_full[s]), 2 * a_tx);
+                    // halo origin (w0-1, h0-1); rows / columns outside the image are zero-filled == conv padding
+                    if (seg0) ptx::tma_load_4d_2sm(dst, &mapA0, fb0 + 8u * s, j * 64, w0 - 1, h0 - 1, b);
+                    else ptx::tma_load_4d_2sm(dst, &mapA1, fb0 + 8u * s, (j - g.c0_chunks) * 64, w0 - 1, h0 - 1, b);
+                }
+                __syncwarp();
+            }
+        }
+        if (g.dbg && elected) g.dbg[blockIdx.x * 8 + 6] = w_a;
+    } else if (warp == W_PROD_B) {
+        // =========================== B producer: weight tiles ===========================
+        const bool elected = ptx::elect_one();
+        uint32_t it = 0;
+        long long w_b = 0;
+        DBG_T0();
+        const uint32_t fb0 = ptx::mapa_rank0(ptx::smem_u32(&b_full[0]));
+        for (int ct = cluster_id; ct < n_ctiles; ct += n_clusters) {
+            for (int j = 0; j < n_astage; ++j) {
+                const bool seg0 = j < g.c0_chunks;
+                const int ntap = seg0 ? 9 : 1;
+                for (int tap = 0; tap < ntap; ++tap, ++it) {
+                    const uint32_t s = it % (uint32_t)g.nb, ph = (it / (uint32_t)g.nb) & 1u;
                     if (g.dbg) t0__ = clock64();
-                    ptx::mbar_wait(ptx::smem_u32(&a_empty[s]), ph ^ 1u);
-                    DBG_ADD(w_a);
-                    const uint32_t fb = fb0 + 8u * s;
-                    const uint32_t dst = a_base + s * a_bytes;
-                    const bool seg0 = j < 3 * g.c0_chunks;
-                    const int c = seg0 ? j / 3 : j - 3 * g.c0_chunks, sh = seg0 ? j % 3 : 1;
+                    ptx::mbar_wait(ptx::smem_u32(&b_empty[s]), ph ^ 1u);
+                    DBG_ADD(w_b);
+                    // K layout of the packed weights: [tap = r*3 + s][cin], then the shortcut channels
+                    const int kb = seg0 ? (tap * g.c0_chunks + j) : (9 * g.c0_chunks + (j - g.c0_chunks));
                     if (elected) {
-                        if (rank == 0) ptx::mbar_arrive_expect_tx(ptx::smem_u32(&a_full[s]), 2 * a_bytes);
-                        // chunk c, column shift dw = sh - 1 (segment 0); the 1x1 shortcut operand is unshifted
-                        if (seg0) ptx::tma_load_4d_2sm(dst, &mapA0, fb, c * 64, w0 + sh - 1, h0 - 1, b);
-                        else ptx::tma_load_4d_2sm(dst, &mapA1, fb, c * 64, w0, h0, b);
+                        if (rank == 0) ptx::mbar_arrive_expect_tx(ptx::smem_u32(&b_full[s]), 2 * b_bytes);
+                        ptx::tma_load_3d_2sm(b_base + s * b_bytes, &mapB, fb0 + 8u * s, kb * 64, (int)rank * (g.N / 2), 0);
                     }
                     __syncwarp();
                 }
             }
-            if (g.dbg && elected) g.dbg[blockIdx.x * 8 + 6] = w_a;
         }
-    } else if (warp == 2) {
-        // =========================== B producer: weight tiles ===========================
-        {
-            const bool elected = ptx::elect_one();
-            uint32_t it = 0;
-            long long w_b = 0;
-            DBG_T0();
-            const uint32_t fb0 = ptx::mapa_rank0(ptx::smem_u32(&b_full[0]));
-            for (int ct = cluster_id; ct < n_ctiles; ct += n_clusters) {
-                for (int j = 0; j < n_astage; ++j) {
-                    const bool seg0 = j < 3 * g.c0_chunks;
-                    const int c = j / 3, sh = j % 3;
-                    const int ntap = seg0 ? 3 : 1;
-                    for (int r = 0; r < ntap; ++r, ++it) {
-                        const uint32_t s = it % (uint32_t)g.nb, ph = (it / (uint32_t)g.nb) & 1u;
-                        if (g.dbg) t0__ = clock64();
-                        ptx::mbar_wait(ptx::smem_u32(&b_empty[s]), ph ^ 1u);
-                        DBG_ADD(w_b);
-                        // K layout of the packed weights: [tap = r*3 + sh][cin], then the shortcut channels
-                        const int kb = seg0 ? ((r * 3 + sh) * g.c0_chunks + c) : (9 * g.c0_chunks + (j - 3 * g.c0_chunks));
-                        if (elected) {
-                            if (rank == 0) ptx::mbar_arrive_expect_tx(ptx::smem_u32(&b_full[s]), 2 * b_bytes);
-                            ptx::tma_load_3d_2sm(b_base + s * b_bytes, &mapB, fb0 + 8u * s, kb * 64, (int)rank * (g.N / 2), 0);
-                        }
-                        __syncwarp();
-                    }
-                }
-            }
-            if (g.dbg && elected) g.dbg[blockIdx.x * 8 + 7] = w_b;
-        }
-    } else if (warp == 1) {
-        // =========================== MMA issuer (leader CTA only) ===========================
-        // The whole warp walks the loops (uniform control flow, descriptors in uniform registers); one elected lane
-        // issues the MMAs and the commits.
-        if (rank == 0) {
+        if (g.dbg && elected) g.dbg[blockIdx.x * 8 + 7] = w_b;
+    } else if (warp >= W_MMA0) {
+        // =========================== MMA issuers (leader CTA only) ===========================
+        // One issuing warp per sub-tile (accumulator): measured (profiles/r01_mma_probe.md), the issuing thread's
+        // barrier waits do not overlap its own MMAs -- tcgen05.mma issue blocks while the pipe is busy -- so with
+        // 64-clock MMAs (N=128) a single issuer leaves the pipe idle ~30 % of the time.  Two independent streams
+        // into different accumulators interleave in the pipe and cover each other's waits; results do not depend
+        // on the interleaving.  The whole warp walks the loops (uniform control flow, descriptors in uniform
+        // registers); one elected lane issues the MMAs and the commits.
+        const int u = warp - W_MMA0;
+        if (rank == 0 && u < g.sub) {
             const uint32_t idesc = ptx::umma_idesc_bf16(256, (uint32_t)g.N);
             const bool elected = ptx::elect_one();
             uint32_t ita = 0, itb = 0, itt = 0;
@@ -204,35 +214,34 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
                 if (g.dbg) t0__ = clock64();
                 ptx::mbar_wait(ptx::smem_u32(&acc_empty[buf]), (use & 1u) ^ 1u);
                 DBG_ADD(w_acc);
-                ptx::tc_fence_after();
-                const uint32_t d_tmem = tmem_base + buf * acc_cols;
+                const uint32_t d = tmem_base + buf * acc_cols + (uint32_t)(u * g.N);
                 for (int j = 0; j < n_astage; ++j, ++ita) {
                     const uint32_t sa = ita % (uint32_t)g.na, pha = (ita / (uint32_t)g.na) & 1u;
                     if (g.dbg) t0__ = clock64();
                     ptx::mbar_wait(ptx::smem_u32(&a_full[sa]), pha);
                     DBG_ADD(w_a);
-                    const bool seg0 = j < 3 * g.c0_chunks;
-                    const int ntap = seg0 ? 3 : 1;
-                    for (int r = 0; r < ntap; ++r, ++itb) {
+                    const bool seg0 = j < g.c0_chunks;
+                    const int ntap = seg0 ? 9 : 1;
+                    for (int t = 0; t < ntap; ++t, ++itb) {
                         const uint32_t sb = itb % (uint32_t)g.nb, phb = (itb / (uint32_t)g.nb) & 1u;
+                        const uint32_t tap = seg0 ? (uint32_t)t : 4u;          // the 1x1 shortcut reads the centre tap
+                        const uint32_t r = tap / 3u, sft = tap - 3u * r;
+                        const uint64_t db = ptx::umma_desc_k_sw128(b_base + sb * b_bytes);
+                        const uint32_t acc = (j > 0 || t > 0) ? 1u : 0u;
+                        // first pixel row of this sub-tile's tap window in the halo tile
+                        const uint32_t row0 = (r + (uint32_t)(SUB_ROWS * u)) * HALO_W + sft;
+                        const uint64_t da = umma_desc_rows(a_base + sa * a_bytes + row0 * ROW_B, HALO_W * ROW_B);
                         if (g.dbg) t0__ = clock64();
                         ptx::mbar_wait(ptx::smem_u32(&b_full[sb]), phb);
                         DBG_ADD(w_b);
                         ptx::tc_fence_after();
-                        const uint64_t db = ptx::umma_desc_k_sw128(b_base + sb * b_bytes);
-                        const uint32_t first = (j > 0 || r > 0) ? 1u : 0u;
-                        for (int u = 0; u < g.sub; ++u) {
-                            // rows (r + 8u) .. of the halo copy: 16 pixels x 128 B per row = 2 KB steps
-                            const uint64_t da = ptx::umma_desc_k_sw128(a_base + sa * a_bytes + (uint32_t)(r + SUB_ROWS * u) * (TW * 128));
-                            const uint32_t d = d_tmem + (uint32_t)(u * g.N);
-                            if (elected) {
-                                ptx::mma_bf16_ss_2sm(d, da, db, idesc, first);
-                                ptx::mma_bf16_ss_2sm(d, da + 2, db + 2, idesc, 1u);
-                                ptx::mma_bf16_ss_2sm(d, da + 4, db + 4, idesc, 1u);
-                                ptx::mma_bf16_ss_2sm(d, da + 6, db + 6, idesc, 1u);
-                            }
+                        if (elected) {
+                            ptx::mma_bf16_ss_2sm(d, da, db, idesc, acc);
+                            ptx::mma_bf16_ss_2sm(d, da + 2, db + 2, idesc, 1u);
+                            ptx::mma_bf16_ss_2sm(d, da + 4, db + 4, idesc, 1u);
+                            ptx::mma_bf16_ss_2sm(d, da + 6, db + 6, idesc, 1u);
+                            ptx::mma_commit_2sm(ptx::smem_u32(&b_empty[sb]));
                         }
-                        if (elected) ptx::mma_commit_2sm(ptx::smem_u32(&b_empty[sb]));
                         __syncwarp();
                     }
                     if (elected) ptx::mma_commit_2sm(ptx::smem_u32(&a_empty[sa]));
@@ -240,22 +249,22 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
                 if (elected) ptx::mma_commit_2sm(ptx::smem_u32(&acc_full[buf]));
                 __syncwarp();
             }
-            if (g.dbg && elected) {
+            if (g.dbg && elected && u == 0) {
                 g.dbg[blockIdx.x * 8 + 0] = w_a;
                 g.dbg[blockIdx.x * 8 + 1] = w_b;
                 g.dbg[blockIdx.x * 8 + 2] = w_acc;
                 g.dbg[blockIdx.x * 8 + 3] = clock64() - t_start;
             }
         }
-    } else if (warp >= 4) {
+    } else if (warp < EPI_WARPS) {
         // =========================== epilogue ===========================
-        const int e = warp - 4, quarter = warp & 3, half = e >> 2;
+        const int e = warp, quarter = warp & 3, half = e >> 2;
         const int n_pass = g.N >> 7;                   // passes of 64 channels per column half
         const int half_cols = g.N >> 1;
         const bool elected = ptx::elect_one();
         const uint32_t my_stg = stg_base + (uint32_t)(e * g.stg_bufs) * 4096u;
         const uint32_t my_rbar = ptx::smem_u32(&res_bar[e]);
-        const uint32_t row_off = (uint32_t)lane * 128u, sw = (uint32_t)(lane & 7);
+        const uint32_t row_off = (uint32_t)lane * ROW_B, sw = (uint32_t)(lane & 7);
         float* bs = bsum[e];
         uint32_t itt = 0, cnt = 0, rphase = 0;
         int last_b = -1;
@@ -284,7 +293,7 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
             DBG_ADD(w_full);
             ptx::tc_fence_after();
             for (int u = 0; u < g.sub; ++u) {
-                const int hrow = h0 + SUB_ROWS * u + 2 * quarter;   // this warp's two image rows (32 pixels)
+                const int hrow = h0 + SUB_ROWS * u + 4 * quarter;   // this warp's four image rows (32 pixels)
                 for (int p = 0; p < n_pass; ++p, ++cnt) {
                     const int cl = 64 * p, cbase = half * half_cols + cl;   // column within the half / the tensor
                     const uint32_t stg = my_stg + (g.stg_bufs == 2 ? (cnt & 1u) * 4096u : 0u);
@@ -324,7 +333,7 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
                             float rr[8];
                             unpack8(ptx::lds128(addr), rr);
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) f[j] = fmaf(rr[j], g.scale, f[j]);
+                            for (int i = 0; i < 8; ++i) f[i] = fmaf(rr[i], g.scale, f[i]);
                         }
                         ptx::sts128(addr, pack8(f));
                     }
@@ -343,7 +352,7 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
             DBG_ADD(t_body);
         }
         if (elected) ptx::bulk_wait_group_read<0>();   // staging tiles must outlive the last stores' reads
-        if (g.dbg && threadIdx.x == 128) {
+        if (g.dbg && threadIdx.x == 0) {
             g.dbg[blockIdx.x * 8 + 4] = w_full;
             g.dbg[blockIdx.x * 8 + 5] = t_body;
         }
@@ -351,7 +360,7 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
     ptx::tc_fence_before();
     __syncthreads();
     ptx::cluster_sync();             // the peer's TMEM / smem stay valid until the leader's last MMA retired
-    if (warp == 1) {
+    if (warp == W_MMA1) {
         __syncwarp();
         ptx::tmem_dealloc2(tmem_base, tmem_cols);
     }
@@ -360,14 +369,15 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
 int g_num_sms2 = 0;
 }  // namespace
 extern long long* g_halo_dbg_shared;
-namespace {
 
-}  // namespace
+bool conv_halo2_eligible(const ActView* a0, int taps0, int n_rows) {
+    return taps0 == 9 && a0->W >= TW && a0->H >= 8 && (n_rows == 128 || n_rows == 256);
+}
 
 int conv_halo2_make_plan(ConvHaloPlan* p, const ActView* a0, const ActView* a1, const bf16* wt, int n_rows,
                          const float* bias, const float* tbias, int tb_stride, const ActView* res, float scale, bf16* out,
                          int out_ld) {
-    SNRSE_CHECK_ARG(conv_halo_eligible(a0, 9, n_rows), "conv_halo2: shape not eligible");
+    SNRSE_CHECK_ARG(conv_halo2_eligible(a0, 9, n_rows), "conv_halo2: shape not eligible");
     SNRSE_CHECK_ARG(a0->C % 64 == 0 && a0->ld % 8 == 0, "conv_halo2: Cin must be a multiple of 64");
     SNRSE_CHECK_ARG(!a1 || (a1->C % 64 == 0 && a1->ld % 8 == 0 && a1->H == a0->H && a1->W == a0->W && a1->B == a0->B),
                     "conv_halo2: bad shortcut operand");
@@ -380,7 +390,7 @@ int conv_halo2_make_plan(ConvHaloPlan* p, const ActView* a0, const ActView* a1, 
     memset(p, 0, sizeof(*p));
     const int tiles_w = cdiv(a0->W, TW);
     int sub = 2;
-    if (a0->H < 16 || (int64_t)a0->B * cdiv(a0->H, 16) * tiles_w < g_num_sms2) sub = 1;
+    if (a0->H < 2 * SUB_ROWS || (int64_t)a0->B * cdiv(a0->H, 2 * SUB_ROWS) * tiles_w < g_num_sms2) sub = 1;
     p->sub = sub;
     p->c0_chunks = a0->C / 64;
     p->c1_chunks = a1 ? a1->C / 64 : 0;
@@ -390,16 +400,18 @@ int conv_halo2_make_plan(ConvHaloPlan* p, const ActView* a0, const ActView* a1, 
     p->n_tiles = a0->B * p->tiles_h * p->tiles_w;
     p->N = n_rows;
     p->acc_bufs = (sub * n_rows <= 256) ? 2 : 1;
-    const int a_bytes = (SUB_ROWS * sub + 2) * TW * 128, b_bytes = (n_rows / 2) * 128;
+    const int a_bytes = (int)halo_stage_bytes(sub), b_bytes = (n_rows / 2) * 128;
     const int budget = 220 * 1024;   // dynamic shared memory (static: barriers + per-warp bias slices, ~4.3 KB)
-    int na = 3, stg = 2;
+    // one A slot feeds 9 taps x SUB x 4 MMAs (>= 2300 clk): two slots already hide the next tile's load
+    int na = 2, stg = 2;
     int nb = (budget - na * a_bytes - stg * EPI_WARPS * 4096) / b_bytes;
-    if (nb < 4) {
+    if (nb < 6) {
         stg = 1;
         nb = (budget - na * a_bytes - stg * EPI_WARPS * 4096) / b_bytes;
     }
     if (nb > MAX_B) nb = MAX_B;
     SNRSE_CHECK_ARG(nb >= 4, "conv_halo2: shared memory budget");
+    if (na < MAX_A && (budget - (na + 1) * a_bytes - stg * EPI_WARPS * 4096 - nb * b_bytes) >= 0) ++na;
     p->na = na; p->nb = nb; p->stg_bufs = stg;
     p->smem_bytes = na * a_bytes + nb * b_bytes + stg * EPI_WARPS * 4096 + 1024;
     const int n_ctiles = (p->n_tiles + 1) / 2, max_clusters = g_num_sms2 / 2;
@@ -408,14 +420,14 @@ int conv_halo2_make_plan(ConvHaloPlan* p, const ActView* a0, const ActView* a1, 
     p->res = res ? res->ptr : nullptr; p->res_ld = res ? res->ld : 0;
     p->scale = scale; p->out = out; p->out_ld = out_ld;
     const int box_h = SUB_ROWS * sub + 2;
-    SNRSE_TRY(tma_make_act_map(&p->mapA0, a0->ptr, a0->C, a0->W, a0->H, a0->B, a0->ld, 64, TW, box_h));
-    if (a1) SNRSE_TRY(tma_make_act_map(&p->mapA1, a1->ptr, a1->C, a1->W, a1->H, a1->B, a1->ld, 64, TW, box_h));
+    SNRSE_TRY(tma_make_act_map(&p->mapA0, a0->ptr, a0->C, a0->W, a0->H, a0->B, a0->ld, 64, HALO_W, box_h));
+    if (a1) SNRSE_TRY(tma_make_act_map(&p->mapA1, a1->ptr, a1->C, a1->W, a1->H, a1->B, a1->ld, 64, HALO_W, box_h));
     else p->mapA1 = p->mapA0;
     const int64_t ktot = 64 * (int64_t)(9 * p->c0_chunks + p->c1_chunks);
     SNRSE_TRY(tma_make_wt_map(&p->mapB, wt, ktot, n_rows, 1, ktot * n_rows, 64, n_rows / 2));
-    // epilogue tiles: 32 pixels (2 image rows x 16) x 64 channels
-    SNRSE_TRY(tma_make_act_map(&p->mapOut, out, n_rows, a0->W, a0->H, a0->B, out_ld, 64, TW, 2));
-    if (res) SNRSE_TRY(tma_make_act_map(&p->mapRes, res->ptr, n_rows, a0->W, a0->H, a0->B, res->ld, 64, TW, 2));
+    // epilogue tiles: 32 pixels (4 image rows x 8) x 64 channels
+    SNRSE_TRY(tma_make_act_map(&p->mapOut, out, n_rows, a0->W, a0->H, a0->B, out_ld, 64, TW, 4));
+    if (res) SNRSE_TRY(tma_make_act_map(&p->mapRes, res->ptr, n_rows, a0->W, a0->H, a0->B, res->ld, 64, TW, 4));
     else p->mapRes = p->mapOut;
     return SNRSE_OK;
 }

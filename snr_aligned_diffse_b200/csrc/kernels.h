@@ -64,7 +64,8 @@ int conv_halo_make_plan(ConvHaloPlan* p, const ActView* a0, const ActView* a1, c
                         const float* bias, const float* tbias, int tb_stride, const ActView* res, float scale, bf16* out,
                         int out_ld);
 int conv_halo_launch(const ConvHaloPlan* p, cudaStream_t s);
-// 2-CTA (cta_group::2) version, same plan structure (conv_halo2.cu)
+// 2-CTA (cta_group::2) single-halo-tile version, same plan structure (conv_halo2.cu): W >= 8, H >= 8
+bool conv_halo2_eligible(const ActView* a0, int taps0, int n_rows);
 int conv_halo2_make_plan(ConvHaloPlan* p, const ActView* a0, const ActView* a1, const bf16* wt, int n_rows,
                          const float* bias, const float* tbias, int tb_stride, const ActView* res, float scale, bf16* out,
                          int out_ld);

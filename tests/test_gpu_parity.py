@@ -174,6 +174,8 @@ CONV_CASES = [
     (4, 128, 112, 128, 128, 9),    # two sub-tiles, double-buffered TMEM, W not a multiple of 16... (112 = 7*16)
     (1, 24, 40, 128, 256, 9),      # ragged super-tiles (H % 16 != 0, W % 16 != 0)
     (2, 8, 16, 512, 256, 9),       # H = 8: one sub-tile
+    (2, 40, 12, 128, 128, 9),      # W % 8 != 0, H % 16 != 0 (8-pixel-wide halo tiles of the 2-CTA kernel)
+    (3, 72, 20, 128, 256, 9),      # odd number of super-tiles: the peer CTA of the last pair runs an all-padding tile
 ]
 
 

@@ -25,6 +25,9 @@ struct ProbeArgs {
     int traffic;    // 0 none, 1 bulk copies global->shared in a side warp, 2 = two side warps
     int same_addr;  // 1: every MMA reads the same operand addresses (no ring)
     int chunk;      // bulk copy size in bytes
+    int issuers;    // 1 or 2 issuing warps (each into its own accumulator)
+    int commit_every; // MMAs between commits (4 default)
+    int random_data;  // 0: zero operands, 1: pseudo-random bf16 operands in (-1, 1)
     const uint8_t* gsrc;
     long long* out; // per CTA: cycles, mma count, traffic bytes
 };
@@ -46,7 +49,7 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 template <int CG>
 __device__ __forceinline__ void probe_body(const ProbeArgs g) {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t done_bar, dummy_bar, tr_bar[2][4];
+    __shared__ __align__(8) uint64_t done_bar, done_bar2, dummy_bar, dummy_bar2, tr_bar[2][4];
     __shared__ uint32_t tmem_base_smem;
     __shared__ volatile int stop_flag;
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
@@ -57,6 +60,8 @@ __device__ __forceinline__ void probe_body(const ProbeArgs g) {
     if (threadIdx.x == 0) {
         ptx::mbar_init(ptx::smem_u32(&done_bar), 1);
         ptx::mbar_init(ptx::smem_u32(&dummy_bar), 1);
+        ptx::mbar_init(ptx::smem_u32(&done_bar2), 1);
+        ptx::mbar_init(ptx::smem_u32(&dummy_bar2), 1);
         for (int w = 0; w < 2; ++w)
             for (int i = 0; i < 4; ++i) ptx::mbar_init(ptx::smem_u32(&tr_bar[w][i]), 1);
         ptx::fence_barrier_init();
@@ -64,7 +69,15 @@ __device__ __forceinline__ void probe_body(const ProbeArgs g) {
     }
     // zero-fill operands so the accumulators stay finite
     for (uint32_t i = threadIdx.x * 16; i < 4 * 16384 + 4 * 32768; i += blockDim.x * 16)
-        asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(smem_base + i), "r"(0) : "memory");
+    {
+        uint32_t w = 0;
+        if (g.random_data) {   // two bf16 per word: sign + exponent 0x3e/0x3f + random mantissa
+            uint32_t h = (i * 2654435761u) ^ (blockIdx.x * 40503u);
+            h ^= h >> 13; h *= 0x5bd1e995u; h ^= h >> 15;
+            w = (h & 0x807f807fu) | 0x3e803e80u | ((h >> 3) & 0x01000100u);
+        }
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(smem_base + i), "r"(w), "r"(w * 3u | 0x3e003e00u & 0xbfffbfffu), "r"(w ^ 0x00550055u), "r"(w ^ 0x80008000u) : "memory");
+    }
     ptx::fence_proxy_async();
     __syncthreads();
     if (warp == 0) {
@@ -101,7 +114,9 @@ __device__ __forceinline__ void probe_body(const ProbeArgs g) {
                     else if (g.a_tmem) mma_bf16_ts(d, tmem_base + 480 + 8 * (k & 3), db + 2 * k, idesc, 1u);   // A: 8 columns per K16
                     else ptx::mma_bf16_ss(d, da + 2 * k, db + 2 * k, idesc, 1u);
                 }
-                if (CG == 2) ptx::mma_commit_2sm(ptx::smem_u32(&dummy_bar)); else ptx::mma_commit(ptx::smem_u32(&dummy_bar));
+                if ((it & ((g.commit_every >> 2) - 1)) == 0) {
+                    if (CG == 2) ptx::mma_commit_2sm(ptx::smem_u32(&dummy_bar)); else ptx::mma_commit(ptx::smem_u32(&dummy_bar));
+                }
             }
             __syncwarp();
         }
@@ -109,13 +124,36 @@ __device__ __forceinline__ void probe_body(const ProbeArgs g) {
             if (CG == 2) ptx::mma_commit_2sm(ptx::smem_u32(&done_bar)); else ptx::mma_commit(ptx::smem_u32(&done_bar));
         }
         ptx::mbar_wait(ptx::smem_u32(&done_bar), 0);
+        if (g.issuers == 2) ptx::mbar_wait(ptx::smem_u32(&done_bar2), 0);
         const long long t1 = clock64();
         if (elected) {
             stop_flag = 1;
             g.out[blockIdx.x * 4 + 0] = t1 - t0;
-            g.out[blockIdx.x * 4 + 1] = 4LL * g.n_iter;
+            g.out[blockIdx.x * 4 + 1] = 4LL * g.n_iter * g.issuers;
         }
-    } else if ((warp == 2 || warp == 3) && lane == 0 && g.traffic >= warp - 1) {
+    } else if (warp == 3 && g.issuers == 2 && rank == 0) {
+        const uint32_t idesc = ptx::umma_idesc_bf16((uint32_t)g.M, (uint32_t)g.N);
+        const bool elected = ptx::elect_one();
+        for (int it = 0; it < g.n_iter; ++it) {
+            const uint32_t st = (uint32_t)(it & 3);
+            const uint64_t da = ptx::umma_desc_k_sw128(a_base + st * 16384);
+            const uint64_t db = ptx::umma_desc_k_sw128(b_base + st * 32768);
+            const uint32_t d = tmem_base + 256u;
+            if (elected) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (CG == 2) ptx::mma_bf16_ss_2sm(d, da + 2 * k, db + 2 * k, idesc, 1u);
+                    else ptx::mma_bf16_ss(d, da + 2 * k, db + 2 * k, idesc, 1u);
+                }
+                if (CG == 2) ptx::mma_commit_2sm(ptx::smem_u32(&dummy_bar2)); else ptx::mma_commit(ptx::smem_u32(&dummy_bar2));
+            }
+            __syncwarp();
+        }
+        if (elected) {
+            if (CG == 2) ptx::mma_commit_2sm(ptx::smem_u32(&done_bar2)); else ptx::mma_commit(ptx::smem_u32(&done_bar2));
+        }
+        ptx::mbar_wait(ptx::smem_u32(&done_bar2), 0);
+    } else if ((warp == 2 || warp == 3) && lane == 0 && g.traffic >= warp - 1 && !(warp == 3 && g.issuers == 2)) {
         // side traffic: bulk copies global -> shared, 4 in flight
         const int w = warp - 2;
         const uint8_t* src = g.gsrc + ((size_t)blockIdx.x * 2 + w) * 65536;
@@ -149,8 +187,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) probe2(const
 
 #define CK(x) do { cudaError_t e__ = (x); if (e__ != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e__), __FILE__, __LINE__); exit(1); } } while (0)
 
-void run(int cg, int M, int N, int a_tmem, int traffic, int same_addr, int chunk, int grid, const uint8_t* gsrc, long long* dout) {
-    ProbeArgs g{M, N, 2048, a_tmem, traffic, same_addr, chunk, gsrc, dout};
+void run(int cg, int M, int N, int a_tmem, int traffic, int same_addr, int chunk, int grid, const uint8_t* gsrc, long long* dout,
+         int issuers = 1, int commit_every = 4, int random_data = 0, int n_iter = 2048) {
+    ProbeArgs g{M, N, n_iter, a_tmem, traffic, same_addr, chunk, issuers, commit_every, random_data, gsrc, dout};
     const int smem = 4 * 16384 + 4 * 32768 + 2 * 16384 + 1024;
     CK(cudaMemset(dout, 0, sizeof(long long) * 4 * 148));
     if (cg == 1) {
@@ -175,8 +214,8 @@ void run(int cg, int M, int N, int a_tmem, int traffic, int same_addr, int chunk
     const double per = cyc / n;
     const double macs = (double)M * N * 16;
     printf("{\"cg\": %d, \"M\": %d, \"N\": %d, \"a_tmem\": %d, \"traffic\": %d, \"same_addr\": %d, \"chunk\": %d, \"grid\": %d, "
-           "\"cycles_per_mma\": %.1f, \"max_cta_cycles_per_mma\": %.1f, \"mac_per_clk_per_sm\": %.0f, \"traffic_B_per_clk_per_sm\": %.1f}\n",
-           cg, M, N, a_tmem, traffic, same_addr, chunk, grid, per, cmax / (n / cnt), macs / per / cg,
+           "\"issuers\": %d, \"commit_every\": %d, \"random_data\": %d, \"n_iter\": %d, \"cycles_per_mma\": %.1f, \"max_cta_cycles_per_mma\": %.1f, \"mac_per_clk_per_sm\": %.0f, \"traffic_B_per_clk_per_sm\": %.1f}\n",
+           cg, M, N, a_tmem, traffic, same_addr, chunk, grid, issuers, commit_every, random_data, n_iter, per, cmax / (n / cnt), macs / per / cg,
            tb / (cyc / cnt) / grid);
     fflush(stdout);
 }
@@ -189,18 +228,11 @@ int main() {
     CK(cudaMalloc(&gsrc, 148 * 2 * 65536));
     CK(cudaMemset(gsrc, 0, 148 * 2 * 65536));
     CK(cudaMalloc(&dout, sizeof(long long) * 4 * 148));
-    for (int N : {64, 128, 192, 256}) run(1, 128, N, 0, 0, 0, 8192, 148, gsrc, dout);
-    run(1, 128, 256, 0, 0, 1, 8192, 148, gsrc, dout);
-    run(1, 64, 256, 0, 0, 0, 8192, 148, gsrc, dout);
-    for (int N : {64, 128, 256}) run(1, 128, N, 1, 0, 0, 8192, 148, gsrc, dout);   // A from TMEM
-    for (int N : {32, 64, 128, 256}) run(2, 256, N, 0, 0, 0, 8192, 148, gsrc, dout);   // CTA pair
-    run(2, 128, 256, 0, 0, 0, 8192, 148, gsrc, dout);
-    // with bulk-copy traffic into shared memory (1 or 2 side warps per CTA, 4 copies in flight each)
-    for (int tr : {1, 2}) {
-        for (int chunk : {4096, 16384}) {
-            run(1, 128, 256, 0, tr, 0, chunk, 148, gsrc, dout);
-            run(2, 256, 128, 0, tr, 0, chunk, 148, gsrc, dout);
-            run(2, 256, 256, 0, tr, 0, chunk, 148, gsrc, dout);
+    // data dependence (power): zero vs random operands, short and long runs
+    for (int rnd : {0, 1}) {
+        for (int n_iter : {2048, 65536}) {
+            run(2, 256, 128, 0, 0, 0, 8192, 148, gsrc, dout, 1, 4, rnd, n_iter);
+            run(2, 256, 256, 0, 0, 0, 8192, 148, gsrc, dout, 1, 4, rnd, n_iter);
         }
     }
     return 0;
