@@ -87,7 +87,7 @@ int snrse_ncsnpp_param_shape(void* handle, int i, int64_t* dims, int* ndim); /* 
 int snrse_ncsnpp_set_weights(void* handle, const void* device_blob);
 /* Plan for inputs [B][F][T]: returns the workspace size (or -1).  flags bit0: keep all activations
  * (debug taps); bit1: CUDA-core cross-check convolutions instead of tcgen05; bit2: first-generation tcgen05 kernel only;
- * bit3: single-CTA halo kernel instead of the 2-CTA one. */
+ * bit3: single-CTA halo kernel instead of the 2-CTA one; bit4: GroupNorm+SiLU as a separate pass (no in-kernel fusion). */
 int64_t snrse_ncsnpp_plan_bytes(void* handle, int B, int F, int T, int flags);
 int snrse_ncsnpp_plan_bind(void* handle, int B, int F, int T, void* workspace, int64_t bytes);
 /* x (state), y (noisy), out: complex64 [B][F][T]; t [B] f32.  mode 0: dnn(cat[x,y], t);
@@ -115,6 +115,14 @@ int snrse_conv_nhwc(const void* x0, int c0, int taps0, const void* x1, int c1, c
  * epilogue wait/body, producer waits); NULL switches it off */
 void snrse_conv_halo_set_debug(long long* dev_counters);
 /* GroupNorm(32, eps) (+SiLU) (ncsnpp_utils/layerspp.py:221,233,245,266) */
+/* GroupNorm(32 groups, eps) + SiLU + conv3x3 (+ optional 1x1 shortcut on x1, bias, per-sample tbias, residual,
+ * scale) as ONE pass: statistics kernel + convolution that normalises its operand in shared memory.  Replaces the
+ * nn.GroupNorm -> SiLU -> ddpm_conv3x3 chain of ResnetBlockBigGANpp (ncsnpp_utils/layerspp.py:245-271).
+ * workspace: snrse_groupnorm_workspace_bytes(B).  Needs W >= 8, H >= 8, n in {128, 256}, c0 % 128 == 0. */
+int snrse_gn_silu_conv3x3_nhwc(const void* x0, int c0, const float* gamma, const float* beta, float eps, const void* x1,
+                               int c1, const void* wt, int n, const float* bias, const float* tbias, int tb_stride,
+                               const void* res, float scale, void* out, int B, int H, int W, void* workspace,
+                               void* stream);
 int64_t snrse_groupnorm_workspace_bytes(int B);
 int snrse_groupnorm_nhwc(const void* x, const float* gamma, const float* beta, void* out, int B, int H, int W, int C,
                          int silu, float eps, void* workspace, void* stream);

@@ -109,7 +109,7 @@ int snrse_conv_nhwc(const void* x0, int c0, int taps0, const void* x1, int c1, c
     if (impl == 0 && conv_halo2_eligible(&a0, taps0, n)) {
         ConvHaloPlan hp;
         SNRSE_TRY(conv_halo2_make_plan(&hp, &a0, x1 ? &a1 : nullptr, static_cast<const bf16*>(wt), n, bias, tbias, tb_stride,
-                                       res ? &r : nullptr, scale, static_cast<bf16*>(out), n));
+                                       res ? &r : nullptr, scale, static_cast<bf16*>(out), n, nullptr));
         return conv_halo2_launch(&hp, S(stream));
     }
     ConvGemmPlan p;
@@ -131,6 +131,30 @@ int snrse_groupnorm_nhwc(const void* x, const float* gamma, const float* beta, v
     SNRSE_TRY(gn_stats_launch(&vx, partial, chunks, S(stream)));
     SNRSE_TRY(gn_finalize_launch(partial, chunks, B, C, hw * (C / 32), gamma, beta, eps, scsh, S(stream)));
     return gn_apply_launch(&vx, scsh, silu, &vo, S(stream));
+}
+
+// GroupNorm(32, eps) + SiLU + conv3x3 (+1x1 shortcut / bias / time-embedding bias / residual, * scale) with the
+// normalisation applied to the operand inside the convolution kernel: the body of ResnetBlockBigGANpp
+// (ncsnpp_utils/layerspp.py:245-271) without materialising the normalised activation.
+int snrse_gn_silu_conv3x3_nhwc(const void* x0, int c0, const float* gamma, const float* beta, float eps, const void* x1,
+                               int c1, const void* wt, int n, const float* bias, const float* tbias, int tb_stride,
+                               const void* res, float scale, void* out, int B, int H, int W, void* workspace,
+                               void* stream) {
+    SNRSE_CHECK_ARG(x0 && gamma && beta && wt && out && workspace, "gn_silu_conv3x3: null pointer");
+    ActView a0 = mk_view(x0, B, H, W, c0, c0), a1, r;
+    if (x1) a1 = mk_view(x1, B, H, W, c1, c1);
+    if (res) r = mk_view(res, B, H, W, n, n);
+    SNRSE_CHECK_ARG(conv_halo2_eligible(&a0, 9, n), "gn_silu_conv3x3: needs W >= 8, H >= 8, N in {128, 256}");
+    float* partial = static_cast<float*>(workspace);
+    float* scsh = partial + (int64_t)B * gn_max_chunks() * 64;
+    const int64_t hw = (int64_t)H * W;
+    int chunks = (int)(hw / 256 < 1 ? 1 : (hw / 256 > gn_max_chunks() ? gn_max_chunks() : hw / 256));
+    SNRSE_TRY(gn_stats_launch(&a0, partial, chunks, S(stream)));
+    SNRSE_TRY(gn_finalize_launch(partial, chunks, B, c0, hw * (c0 / 32), gamma, beta, eps, scsh, S(stream)));
+    ConvHaloPlan hp;
+    SNRSE_TRY(conv_halo2_make_plan(&hp, &a0, x1 ? &a1 : nullptr, static_cast<const bf16*>(wt), n, bias, tbias, tb_stride,
+                                   res ? &r : nullptr, scale, static_cast<bf16*>(out), n, scsh));
+    return conv_halo2_launch(&hp, S(stream));
 }
 
 int snrse_fir_nhwc(const void* x, void* out, int B, int H, int W, int C, int up, void* stream) {

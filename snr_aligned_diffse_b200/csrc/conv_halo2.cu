@@ -33,7 +33,8 @@
 
 namespace {
 
-constexpr int HALO_THREADS = 384;
+constexpr int HALO_THREADS = 384;        // + 256 (warps 12..19) when GroupNorm+SiLU is applied to the operand in flight
+constexpr int NORM_WARP0 = 12, NORM_THREADS = 256;
 constexpr int EPI_WARPS = 8;
 // The warp scheduler favours the highest warp id of a sub-partition: the single-lane issue warps sit above the
 // epilogue warps so that their (few) instructions never queue behind epilogue arithmetic.
@@ -52,6 +53,8 @@ struct Halo2Args {
     int acc_bufs;                  // 1 or 2 TMEM accumulator sets
     int stg_bufs;                  // 1 or 2 staging tiles per epilogue warp
     int has_res;
+    const float* scsh;             // null, or GroupNorm scale/shift [B][2][norm_c] applied (+SiLU) to operand 0 in shared memory
+    int norm_c;
     const float* bias;
     const float* tbias;
     int tb_stride;
@@ -77,12 +80,12 @@ __device__ __forceinline__ uint64_t umma_desc_rows(uint32_t smem_addr, uint32_t 
     return d;
 }
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(HALO_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(HALO_THREADS + NORM_THREADS, 1)
 conv_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                   const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapOut,
                   const __grid_constant__ CUtensorMap mapRes, const Halo2Args g) {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t a_full[MAX_A], a_empty[MAX_A], b_full[MAX_B], b_empty[MAX_B];
+    __shared__ __align__(8) uint64_t a_full[MAX_A], a_empty[MAX_A], a_land[MAX_A], b_full[MAX_B], b_empty[MAX_B];
     __shared__ __align__(8) uint64_t acc_full[2], acc_empty[2], res_bar[EPI_WARPS];
     __shared__ __align__(16) float bsum[EPI_WARPS][128];   // per epilogue warp: (bias + time-embedding bias) * scale
     __shared__ uint32_t tmem_base_smem;
@@ -103,7 +106,8 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
     if (warp == W_MMA1) {
         if (lane == 0) {
             for (int i = 0; i < g.na; ++i) {
-                ptx::mbar_init(ptx::smem_u32(&a_full[i]), 1);
+                ptx::mbar_init(ptx::smem_u32(&a_full[i]), 2);   // one arrival per CTA (producer, or normalising warps)
+                ptx::mbar_init(ptx::smem_u32(&a_land[i]), 1);   // local: raw tile landed, to be normalised
                 ptx::mbar_init(ptx::smem_u32(&a_empty[i]), (uint32_t)g.sub);   // one commit per issuing warp
             }
             for (int i = 0; i < g.nb; ++i) {
@@ -156,15 +160,23 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
                 const uint32_t dst = a_base + s * a_bytes;
                 const bool seg0 = j < g.c0_chunks;
                 if (elected) {
-                    if (rank == 0) ptx::mbar_arrive_expect_tx(ptx::smem_u32(&a_full[s]), 2 * a_tx);
                     // halo origin (w0-1, h0-1); rows / columns outside the image are zero-filled == conv padding
-                    if (seg0) ptx::tma_load_4d_2sm(dst, &mapA0, fb0 + 8u * s, j * 64, w0 - 1, h0 - 1, b);
-                    else ptx::tma_load_4d_2sm(dst, &mapA1, fb0 + 8u * s, (j - g.c0_chunks) * 64, w0 - 1, h0 - 1, b);
+                    if (g.scsh) {
+                        // tile -> this CTA's own barrier; the normalising warps publish it to the leader afterwards
+                        // (shortcut tiles take the same route untouched, so every ring slot follows one protocol)
+                        ptx::mbar_arrive_expect_tx(ptx::smem_u32(&a_land[s]), a_tx);
+                        if (seg0) ptx::tma_load_4d(dst, &mapA0, ptx::smem_u32(&a_land[s]), j * 64, w0 - 1, h0 - 1, b);
+                        else ptx::tma_load_4d(dst, &mapA1, ptx::smem_u32(&a_land[s]), (j - g.c0_chunks) * 64, w0 - 1, h0 - 1, b);
+                    } else {
+                        ptx::mbar_arrive_expect_tx_remote(fb0 + 8u * s, a_tx);
+                        if (seg0) ptx::tma_load_4d_2sm(dst, &mapA0, fb0 + 8u * s, j * 64, w0 - 1, h0 - 1, b);
+                        else ptx::tma_load_4d_2sm(dst, &mapA1, fb0 + 8u * s, (j - g.c0_chunks) * 64, w0 - 1, h0 - 1, b);
+                    }
                 }
                 __syncwarp();
             }
         }
-        if (g.dbg && elected) g.dbg[blockIdx.x * 8 + 6] = w_a;
+        if (g.dbg && elected && !g.scsh) g.dbg[blockIdx.x * 8 + 6] = w_a;
     } else if (warp == W_PROD_B) {
         // =========================== B producer: weight tiles ===========================
         const bool elected = ptx::elect_one();
@@ -191,8 +203,8 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
                 }
             }
         }
-        if (g.dbg && elected) g.dbg[blockIdx.x * 8 + 7] = w_b;
-    } else if (warp >= W_MMA0) {
+        if (g.dbg && elected && !g.scsh) g.dbg[blockIdx.x * 8 + 7] = w_b;
+    } else if (warp == W_MMA0 || warp == W_MMA1) {
         // =========================== MMA issuers (leader CTA only) ===========================
         // One issuing warp per sub-tile (accumulator): measured (profiles/r01_mma_probe.md), the issuing thread's
         // barrier waits do not overlap its own MMAs -- tcgen05.mma issue blocks while the pipe is busy -- so with
@@ -252,8 +264,96 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
             if (g.dbg && elected && u == 0) {
                 g.dbg[blockIdx.x * 8 + 0] = w_a;
                 g.dbg[blockIdx.x * 8 + 1] = w_b;
-                g.dbg[blockIdx.x * 8 + 2] = w_acc;
+                if (!g.scsh) g.dbg[blockIdx.x * 8 + 2] = w_acc;
                 g.dbg[blockIdx.x * 8 + 3] = clock64() - t_start;
+            }
+        }
+    } else if (warp >= NORM_WARP0) {
+        // =========================== GroupNorm + SiLU on the operand in flight ===========================
+        // y = silu(x * scale[b,c] + shift[b,c]) (ncsnpp_utils/layerspp.py:245,266) applied in place to every raw halo
+        // tile: 256 threads, thread = (16-byte chunk q of 8 channels, row group), rows strided by 32.  Pixels outside
+        // the image stay zero (the convolution pads the NORMALISED activation).  Same arithmetic as gn_apply_kernel.
+        if (g.scsh) {
+            const int tid = (warp - NORM_WARP0) * 32 + lane;
+            const uint32_t q = (uint32_t)(tid & 7);
+            const int rg = tid >> 3;
+            const int rows_total = (SUB_ROWS * g.sub + 2) * HALO_W;
+            const uint32_t fb0 = ptx::mapa_rank0(ptx::smem_u32(&a_full[0]));
+            uint32_t it = 0;
+            long long w_land = 0, t_xf = 0, t_sync = 0;
+            DBG_T0();
+            for (int ct = cluster_id; ct < n_ctiles; ct += n_clusters) {
+                const int tile = 2 * ct + (int)rank;
+                const int b = tile / tiles_per_img, rem = tile % tiles_per_img;
+                const int h0 = (rem / g.tiles_w) * SUB_ROWS * g.sub, w0 = (rem % g.tiles_w) * TW;
+                for (int j = 0; j < n_astage; ++j, ++it) {
+                    const uint32_t s = it % (uint32_t)g.na, ph = (it / (uint32_t)g.na) & 1u;
+                    const bool live = (b < g.B) && (j < g.c0_chunks);   // the 1x1 shortcut operand is used raw
+                    // h = x * (scale/2) + shift/2  ==  (x*scale + shift)/2 exactly;  silu(t) = h + h*tanh(h)  (silu_f)
+                    float sc[8], sh[8];
+                    if (live) {
+                        const float4* pa = reinterpret_cast<const float4*>(g.scsh + ((int64_t)b * 2) * g.norm_c + j * 64 + q * 8);
+                        const float4* pc = reinterpret_cast<const float4*>(g.scsh + ((int64_t)b * 2 + 1) * g.norm_c + j * 64 + q * 8);
+                        const float4 a0 = __ldg(pa), a1 = __ldg(pa + 1), c0 = __ldg(pc), c1 = __ldg(pc + 1);
+                        sc[0] = a0.x; sc[1] = a0.y; sc[2] = a0.z; sc[3] = a0.w; sc[4] = a1.x; sc[5] = a1.y; sc[6] = a1.z; sc[7] = a1.w;
+                        sh[0] = c0.x; sh[1] = c0.y; sh[2] = c0.z; sh[3] = c0.w; sh[4] = c1.x; sh[5] = c1.y; sh[6] = c1.z; sh[7] = c1.w;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) { sc[i] *= 0.5f; sh[i] *= 0.5f; }
+                    }
+                    if (g.dbg) t0__ = clock64();
+                    ptx::mbar_wait(ptx::smem_u32(&a_land[s]), ph);
+                    DBG_ADD(w_land);
+                    // rows advance by 32 (a multiple of 8): the swizzle term of this thread's chunk never changes
+                    const uint32_t addr0 = a_base + s * a_bytes + (uint32_t)rg * ROW_B + ((q ^ ((uint32_t)rg & 7u)) << 4);
+                    if (live) {
+                        const bool interior = h0 >= 1 && h0 + SUB_ROWS * g.sub + 1 <= g.H && w0 >= 1 && w0 + TW + 1 <= g.W;
+                        // two rows per trip (independent dependency chains hide the LDS / MUFU latency)
+                        for (int r = rg; r < rows_total; r += 64) {
+                            bool ok[2];
+                            uint4 raw[2];
+#pragma unroll
+                            for (int k = 0; k < 2; ++k) {
+                                const int rr = r + 32 * k;
+                                ok[k] = rr < rows_total;
+                                if (!interior) {   // border tile: padding pixels stay zero
+                                    const int hh = rr / HALO_W, ww = rr - hh * HALO_W;
+                                    const int ih = h0 - 1 + hh, iw = w0 - 1 + ww;
+                                    ok[k] = ok[k] && ih >= 0 && ih < g.H && iw >= 0 && iw < g.W;
+                                }
+                                if (ok[k]) raw[k] = ptx::lds128(addr0 + (uint32_t)(rr - rg) * ROW_B);
+                            }
+#pragma unroll
+                            for (int k = 0; k < 2; ++k) {
+                                if (ok[k]) {
+                                    const uint32_t w[4] = {raw[k].x, raw[k].y, raw[k].z, raw[k].w};
+                                    uint4 o;
+                                    uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+                                    for (int i = 0; i < 4; ++i) {
+                                        const float h0f = fmaf(__uint_as_float(w[i] << 16), sc[2 * i], sh[2 * i]);
+                                        const float h1f = fmaf(__uint_as_float(w[i] & 0xffff0000u), sc[2 * i + 1], sh[2 * i + 1]);
+                                        float t0, t1;
+                                        asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(h0f));
+                                        asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(h1f));
+                                        const __nv_bfloat162 pk = __floats2bfloat162_rn(fmaf(h0f, t0, h0f), fmaf(h1f, t1, h1f));
+                                        ow[i] = *reinterpret_cast<const uint32_t*>(&pk);
+                                    }
+                                    ptx::sts128(addr0 + (uint32_t)(r + 32 * k - rg) * ROW_B, o);
+                                }
+                            }
+                        }
+                    }
+                    DBG_ADD(t_xf);
+                    ptx::fence_proxy_async();                       // generic-proxy writes -> visible to the tensor core
+                    asm volatile("bar.sync 1, 256;" ::: "memory");   // all eight normalising warps are done with the tile
+                    if (tid == 0) ptx::mbar_arrive_remote(fb0 + 8u * s);
+                    DBG_ADD(t_sync);
+                }
+            }
+            if (g.dbg && tid == 0) {   // measurement builds: replaces the producers' counters
+                g.dbg[blockIdx.x * 8 + 6] = w_land;
+                g.dbg[blockIdx.x * 8 + 7] = t_xf;
+                g.dbg[blockIdx.x * 8 + 2] = t_sync;
             }
         }
     } else if (warp < EPI_WARPS) {
@@ -306,36 +406,39 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
                         ptx::mbar_arrive_expect_tx(my_rbar, 4096u);
                         ptx::tma_load_4d(stg, &mapRes, my_rbar, cbase, w0, hrow, b);
                     }
-                    uint32_t v[64];
                     const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * acc_cols + (uint32_t)(u * g.N + cbase);
-                    ptx::tmem_ld_32x32(taddr, v);
-                    ptx::tmem_ld_32x32(taddr + 32u, v + 32);
-                    ptx::tmem_ld_wait();
-                    if (g.has_res) {
-                        ptx::mbar_wait(my_rbar, rphase);
-                        rphase ^= 1u;
-                    }
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const float4 b0 = *reinterpret_cast<const float4*>(bs + cl + 8 * q);
-                        const float4 b1 = *reinterpret_cast<const float4*>(bs + cl + 8 * q + 4);
-                        float f[8];
-                        f[0] = fmaf(__uint_as_float(v[8 * q + 0]), g.scale, b0.x);
-                        f[1] = fmaf(__uint_as_float(v[8 * q + 1]), g.scale, b0.y);
-                        f[2] = fmaf(__uint_as_float(v[8 * q + 2]), g.scale, b0.z);
-                        f[3] = fmaf(__uint_as_float(v[8 * q + 3]), g.scale, b0.w);
-                        f[4] = fmaf(__uint_as_float(v[8 * q + 4]), g.scale, b1.x);
-                        f[5] = fmaf(__uint_as_float(v[8 * q + 5]), g.scale, b1.y);
-                        f[6] = fmaf(__uint_as_float(v[8 * q + 6]), g.scale, b1.z);
-                        f[7] = fmaf(__uint_as_float(v[8 * q + 7]), g.scale, b1.w);
-                        const uint32_t addr = stg + row_off + (((uint32_t)q ^ sw) << 4);   // 128-byte swizzle
-                        if (g.has_res) {
-                            float rr[8];
-                            unpack8(ptx::lds128(addr), rr);
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) f[i] = fmaf(rr[i], g.scale, f[i]);
+                    for (int hq = 0; hq < 2; ++hq) {   // 32 accumulator columns at a time (register budget: 640 threads)
+                        uint32_t v[32];
+                        ptx::tmem_ld_32x32(taddr + 32u * hq, v);
+                        ptx::tmem_ld_wait();
+                        if (hq == 0 && g.has_res) {
+                            ptx::mbar_wait(my_rbar, rphase);
+                            rphase ^= 1u;
                         }
-                        ptx::sts128(addr, pack8(f));
+#pragma unroll
+                        for (int qq = 0; qq < 4; ++qq) {
+                            const int q = 4 * hq + qq;
+                            const float4 b0 = *reinterpret_cast<const float4*>(bs + cl + 8 * q);
+                            const float4 b1 = *reinterpret_cast<const float4*>(bs + cl + 8 * q + 4);
+                            float f[8];
+                            f[0] = fmaf(__uint_as_float(v[8 * qq + 0]), g.scale, b0.x);
+                            f[1] = fmaf(__uint_as_float(v[8 * qq + 1]), g.scale, b0.y);
+                            f[2] = fmaf(__uint_as_float(v[8 * qq + 2]), g.scale, b0.z);
+                            f[3] = fmaf(__uint_as_float(v[8 * qq + 3]), g.scale, b0.w);
+                            f[4] = fmaf(__uint_as_float(v[8 * qq + 4]), g.scale, b1.x);
+                            f[5] = fmaf(__uint_as_float(v[8 * qq + 5]), g.scale, b1.y);
+                            f[6] = fmaf(__uint_as_float(v[8 * qq + 6]), g.scale, b1.z);
+                            f[7] = fmaf(__uint_as_float(v[8 * qq + 7]), g.scale, b1.w);
+                            const uint32_t addr = stg + row_off + (((uint32_t)q ^ sw) << 4);   // 128-byte swizzle
+                            if (g.has_res) {
+                                float rr[8];
+                                unpack8(ptx::lds128(addr), rr);
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) f[i] = fmaf(rr[i], g.scale, f[i]);
+                            }
+                            ptx::sts128(addr, pack8(f));
+                        }
                     }
                     ptx::fence_proxy_async();
                     __syncwarp();
@@ -376,7 +479,7 @@ bool conv_halo2_eligible(const ActView* a0, int taps0, int n_rows) {
 
 int conv_halo2_make_plan(ConvHaloPlan* p, const ActView* a0, const ActView* a1, const bf16* wt, int n_rows,
                          const float* bias, const float* tbias, int tb_stride, const ActView* res, float scale, bf16* out,
-                         int out_ld) {
+                         int out_ld, const float* scsh) {
     SNRSE_CHECK_ARG(conv_halo2_eligible(a0, 9, n_rows), "conv_halo2: shape not eligible");
     SNRSE_CHECK_ARG(a0->C % 64 == 0 && a0->ld % 8 == 0, "conv_halo2: Cin must be a multiple of 64");
     SNRSE_CHECK_ARG(!a1 || (a1->C % 64 == 0 && a1->ld % 8 == 0 && a1->H == a0->H && a1->W == a0->W && a1->B == a0->B),
@@ -402,10 +505,13 @@ int conv_halo2_make_plan(ConvHaloPlan* p, const ActView* a0, const ActView* a1, 
     p->acc_bufs = (sub * n_rows <= 256) ? 2 : 1;
     const int a_bytes = (int)halo_stage_bytes(sub), b_bytes = (n_rows / 2) * 128;
     const int budget = 220 * 1024;   // dynamic shared memory (static: barriers + per-warp bias slices, ~4.3 KB)
-    // one A slot feeds 9 taps x SUB x 4 MMAs (>= 2300 clk): two slots already hide the next tile's load
+    // One A slot feeds 9 taps x SUB x 4 MMAs (>= 2300 clk): two slots hide the next tile's load.  With in-flight
+    // normalisation the slot also waits for the normalising warps (load + ~2500 clk); at N=128 (64-clock MMAs) that
+    // needs a third slot, paid for with single-buffered epilogue staging.
     int na = 2, stg = 2;
+    if (scsh && n_rows == 128 && sub == 2) { na = 3; stg = 1; }
     int nb = (budget - na * a_bytes - stg * EPI_WARPS * 4096) / b_bytes;
-    if (nb < 6) {
+    if (nb < 6 && stg == 2) {
         stg = 1;
         nb = (budget - na * a_bytes - stg * EPI_WARPS * 4096) / b_bytes;
     }
@@ -419,6 +525,7 @@ int conv_halo2_make_plan(ConvHaloPlan* p, const ActView* a0, const ActView* a1, 
     p->bias = bias; p->tbias = tbias; p->tb_stride = tb_stride;
     p->res = res ? res->ptr : nullptr; p->res_ld = res ? res->ld : 0;
     p->scale = scale; p->out = out; p->out_ld = out_ld;
+    p->scsh = scsh;
     const int box_h = SUB_ROWS * sub + 2;
     SNRSE_TRY(tma_make_act_map(&p->mapA0, a0->ptr, a0->C, a0->W, a0->H, a0->B, a0->ld, 64, HALO_W, box_h));
     if (a1) SNRSE_TRY(tma_make_act_map(&p->mapA1, a1->ptr, a1->C, a1->W, a1->H, a1->B, a1->ld, 64, HALO_W, box_h));
@@ -446,8 +553,9 @@ int conv_halo2_launch(const ConvHaloPlan* p, cudaStream_t s) {
     g.has_res = p->res != nullptr;
     g.bias = p->bias; g.tbias = p->tbias; g.tb_stride = p->tb_stride;
     g.scale = p->scale;
+    g.scsh = p->scsh; g.norm_c = p->c0_chunks * 64;
     g.dbg = g_halo_dbg_shared;
-    conv_halo2_kernel<<<p->grid, HALO_THREADS, p->smem_bytes, s>>>(p->mapA0, p->mapA1, p->mapB, p->mapOut, p->mapRes, g);
+    conv_halo2_kernel<<<p->grid, HALO_THREADS + (p->scsh ? NORM_THREADS : 0), p->smem_bytes, s>>>(p->mapA0, p->mapA1, p->mapB, p->mapOut, p->mapRes, g);
     SNRSE_LAUNCH_CHECK();
     return SNRSE_OK;
 }

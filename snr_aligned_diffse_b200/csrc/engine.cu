@@ -314,8 +314,9 @@ const float INV_SQRT2 = 0.70710678118654752440f;
 enum { LK_OTHER = 0, LK_GEMM = 1, LK_GN = 2, LK_FIR = 3, LK_ATTN = 4, LK_THIN = 5, LK_HEAD = 6 };
 
 int rec_gemm(Plan& P, int a0, int taps0, int a1, int64_t w_off, int n_rows, int64_t bias_off, int tb_row, int res,
-             float scale, int out) {
+             float scale, int out, int norm = 0) {
     P.use(a0);
+    if (norm) P.use(P.t_scsh);
     if (a1 >= 0) P.use(a1);
     if (res >= 0) P.use(res);
     P.use(out);
@@ -359,9 +360,14 @@ int rec_gemm(Plan& P, int a0, int taps0, int a1, int64_t w_off, int n_rows, int6
         if (!(p.flags & 12) && conv_halo2_eligible(&va0, taps0, n_rows)) {   // 2-CTA (cta_group::2) halo kernel
             ConvHaloPlan hp;
             SNRSE_TRY(conv_halo2_make_plan(&hp, &va0, a1 >= 0 ? &va1 : nullptr, e.wb(w_off), n_rows, bias, tb, tb_stride,
-                                           res >= 0 ? &vres : nullptr, scale, vout.ptr, vout.ld));
+                                           res >= 0 ? &vres : nullptr, scale, vout.ptr, vout.ld,
+                                           norm ? p.fptr(p.t_scsh) : nullptr));
             p.add(LK_GEMM, 2.0 * px * n_rows * kt, by, [hp](cudaStream_t s) { return conv_halo2_launch(&hp, s); });
             return SNRSE_OK;
+        }
+        if (norm) {
+            snrse_set_error("internal: fused GroupNorm requested for a convolution the 2-CTA kernel cannot run");
+            return SNRSE_ERR_STATE;
         }
         ConvGemmPlan g;
         SNRSE_TRY(conv_gemm_make_plan(&g, &va0, taps0, a1 >= 0 ? &va1 : nullptr, e.wb(w_off), n_rows, 0, 0, bias, tb,
@@ -400,6 +406,39 @@ int rec_gn(Plan& P, int x, int64_t g_off, int64_t b_off, int silu) {
     return out;
 }
 
+// GroupNorm statistics only: leaves scale/shift in t_scsh for a convolution that normalises its operand in flight
+void rec_gn_stats(Plan& P, int x, int64_t g_off, int64_t b_off) {
+    P.use(x); P.use(P.t_partial); P.use(P.t_scsh);
+    P.step++;
+    P.builders.push_back([=](Plan& p) -> int {
+        Engine& e = *p.eng;
+        const ActView vx = p.view(x);
+        const int64_t hw = (int64_t)vx.H * vx.W;
+        int chunks = (int)std::min<int64_t>(gn_max_chunks(), std::max<int64_t>(1, hw / 256));
+        while ((int64_t)chunks * vx.B > 1184 && chunks > 1) chunks = (chunks + 1) / 2;
+        float* partial = p.fptr(p.t_partial);
+        float* scsh = p.fptr(p.t_scsh);
+        const float* gamma = e.wf(g_off);
+        const float* beta = e.wf(b_off);
+        const int64_t cnt = hw * (vx.C / 32);
+        const double el = (double)vx.B * hw * vx.C;
+        p.add(LK_GN, 0.0, 2.0 * el, [=](cudaStream_t s) {   // one read of x
+            SNRSE_TRY(gn_stats_launch(&vx, partial, chunks, s));
+            return gn_finalize_launch(partial, chunks, vx.B, vx.C, cnt, gamma, beta, 1e-6f, scsh, s);
+        });
+        return SNRSE_OK;
+    });
+}
+
+// can the 2-CTA kernel run (and therefore normalise in flight) a 3x3 convolution on this tensor?
+bool fusable(const Plan& P, int x, int n_rows) {
+    if (P.flags & (2 | 4 | 8 | 16)) return false;   // cross-check kernels / fusion disabled
+    const LT& t = P.tens[x];
+    ActView v;
+    v.ptr = nullptr; v.B = t.B; v.H = t.H; v.W = t.W; v.C = t.C; v.ld = t.C;
+    return conv_halo2_eligible(&v, 9, n_rows);
+}
+
 int rec_fir(Plan& P, int x, int up) {
     const LT tx = P.tens[x];
     const int out = up ? P.new_t(tx.B, tx.H * 2, tx.W * 2, tx.C, 2) : P.new_t(tx.B, tx.H / 2, tx.W / 2, tx.C, 2);
@@ -415,17 +454,31 @@ int rec_fir(Plan& P, int x, int up) {
 }
 
 int rec_resblock(Plan& P, const Mod& m, int x) {
-    int a = rec_gn(P, x, m.o[0], m.o[1], 1);
-    int xs = x;
-    if (m.up) { a = rec_fir(P, a, 1); xs = rec_fir(P, x, 1); }
-    if (m.down) { a = rec_fir(P, a, 0); xs = rec_fir(P, x, 0); }
+    // GroupNorm_0 + SiLU (+ FIR resampling of both branches) + Conv_0 + Dense_0(temb)
+    int a, xs = x, fuse0 = 0;
+    if (!m.up && !m.down && fusable(P, x, m.cout)) {
+        rec_gn_stats(P, x, m.o[0], m.o[1]);     // normalisation itself happens inside Conv_0
+        a = x;
+        fuse0 = 1;
+    } else {
+        a = rec_gn(P, x, m.o[0], m.o[1], 1);
+        if (m.up) { a = rec_fir(P, a, 1); xs = rec_fir(P, x, 1); }
+        if (m.down) { a = rec_fir(P, a, 0); xs = rec_fir(P, x, 0); }
+    }
     const LT ta = P.tens[a];
     const int h = P.new_t(ta.B, ta.H, ta.W, m.cout, 2);
-    rec_gemm(P, a, 9, -1, m.o[2], m.cout, m.o[3], m.tb_row, -1, 1.0f, h);
-    const int a2 = rec_gn(P, h, m.o[4], m.o[5], 1);
+    rec_gemm(P, a, 9, -1, m.o[2], m.cout, m.o[3], m.tb_row, -1, 1.0f, h, fuse0);
+    // GroupNorm_1 + SiLU + Conv_1 (+ Conv_2 shortcut or identity residual), / sqrt(2)
+    int a2 = h, fuse1 = 0;
+    if (fusable(P, h, m.cout)) {
+        rec_gn_stats(P, h, m.o[4], m.o[5]);
+        fuse1 = 1;
+    } else {
+        a2 = rec_gn(P, h, m.o[4], m.o[5], 1);
+    }
     const int out = P.new_t(ta.B, ta.H, ta.W, m.cout, 2);
-    if (m.has_c2) rec_gemm(P, a2, 9, xs, m.o[6], m.cout, m.o[7], -1, -1, INV_SQRT2, out);
-    else rec_gemm(P, a2, 9, -1, m.o[6], m.cout, m.o[7], -1, xs, INV_SQRT2, out);
+    if (m.has_c2) rec_gemm(P, a2, 9, xs, m.o[6], m.cout, m.o[7], -1, -1, INV_SQRT2, out, fuse1);
+    else rec_gemm(P, a2, 9, -1, m.o[6], m.cout, m.o[7], -1, xs, INV_SQRT2, out, fuse1);
     return out;
 }
 
@@ -745,7 +798,8 @@ int snrse_ncsnpp_set_weights(void* handle, const void* device_blob) {
 }
 
 // flags: bit0 = keep every activation alive (debug taps), bit1 = CUDA-core cross-check convolutions,
-//        bit2 = first-generation (non-halo) tcgen05 kernel for every convolution, bit3 = single-CTA halo kernel
+//        bit2 = first-generation (non-halo) tcgen05 kernel for every convolution, bit3 = single-CTA halo kernel,
+//        bit4 = GroupNorm applied by its own kernel instead of inside the following convolution
 int64_t snrse_ncsnpp_plan_bytes(void* handle, int B, int F, int T, int flags) {
     Engine* e = static_cast<Engine*>(handle);
     if (!e || B < 1 || F < 1 || T < 1 || (F % (1 << (e->n_levels - 1))) || (T % (1 << (e->n_levels - 1)))) {

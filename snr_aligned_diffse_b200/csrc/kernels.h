@@ -58,6 +58,7 @@ struct ConvHaloPlan {
     float scale;
     bf16* out;
     int out_ld;
+    const float* scsh;   // 2-CTA kernel only
 };
 bool conv_halo_eligible(const ActView* a0, int taps0, int n_rows);
 int conv_halo_make_plan(ConvHaloPlan* p, const ActView* a0, const ActView* a1, const bf16* wt, int n_rows,
@@ -66,9 +67,11 @@ int conv_halo_make_plan(ConvHaloPlan* p, const ActView* a0, const ActView* a1, c
 int conv_halo_launch(const ConvHaloPlan* p, cudaStream_t s);
 // 2-CTA (cta_group::2) single-halo-tile version, same plan structure (conv_halo2.cu): W >= 8, H >= 8
 bool conv_halo2_eligible(const ActView* a0, int taps0, int n_rows);
+// scsh (nullable): GroupNorm scale/shift [B][2][C0] (gn_finalize_launch); when given, operand 0 is replaced by
+// silu(x*scale + shift) inside the kernel (GroupNorm+SiLU+conv3x3 of ResnetBlockBigGANpp without the HBM round trip).
 int conv_halo2_make_plan(ConvHaloPlan* p, const ActView* a0, const ActView* a1, const bf16* wt, int n_rows,
                          const float* bias, const float* tbias, int tb_stride, const ActView* res, float scale, bf16* out,
-                         int out_ld);
+                         int out_ld, const float* scsh);
 int conv_halo2_launch(const ConvHaloPlan* p, cudaStream_t s);
 
 // ----------------------------------------------------------------------------- conv_simt.cu

@@ -37,7 +37,7 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
 // Bounded wait: a protocol bug must fault the launch (trap -> cudaErrorLaunchFailure), never hang the GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins) {
-        if (spins > (1u << 24)) {
+        if (spins > (1u << 22)) {
             asm volatile("trap;");
         }
     }
@@ -158,6 +158,11 @@ __device__ __forceinline__ uint32_t mapa_rank0(uint32_t smem_addr) {
 }
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_bar) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+}
+// arrive + expect-tx on a barrier addressed in cluster space (may live in the peer CTA)
+__device__ __forceinline__ void mbar_arrive_expect_tx_remote(uint32_t cluster_bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.release.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(cluster_bar), "r"(bytes)
+                 : "memory");
 }
 __device__ __forceinline__ void tma_load_4d_2sm(uint32_t smem_dst, const CUtensorMap* map, uint32_t cluster_bar, int c0,
                                                 int c1, int c2, int c3) {

@@ -131,6 +131,21 @@ def groupnorm_nhwc(x, gamma, beta, silu=True, eps=1e-6):
     return out
 
 
+def gn_silu_conv3x3_nhwc(x0, gamma, beta, wt, x1=None, bias=None, tbias=None, res=None, scale=1.0, eps=1e-6):
+    """conv3x3(silu(GroupNorm32(x0))) (+ 1x1 shortcut on x1, bias, tbias, residual, * scale) in one pass."""
+    lib = _lib_dev()
+    B, H, W, C0 = x0.shape
+    N = wt.shape[0]
+    out = torch.empty(B, H, W, N, dtype=torch.bfloat16, device=x0.device)
+    ws = torch.empty(int(lib.snrse_groupnorm_workspace_bytes(B)), dtype=torch.uint8, device=x0.device)
+    _lib.check(lib.snrse_gn_silu_conv3x3_nhwc(_lib.ptr(x0), C0, _lib.ptr(gamma), _lib.ptr(beta), eps, _lib.ptr(x1),
+                                              0 if x1 is None else x1.shape[-1], _lib.ptr(wt), N, _lib.ptr(bias),
+                                              _lib.ptr(tbias), 0 if tbias is None else tbias.shape[-1], _lib.ptr(res),
+                                              scale, _lib.ptr(out), B, H, W, _lib.ptr(ws), _lib.stream_ptr()),
+               "gn_silu_conv3x3")
+    return out
+
+
 def fir_nhwc(x, up):
     lib = _lib_dev()
     B, H, W, C = x.shape

@@ -225,6 +225,40 @@ def test_conv_fused_shortcut_residual_tbias(ops, impl):
     assert ((got2 - ref2).abs() <= 2 ** -7 * ref2.abs() + 2e-2 * ref2.abs().mean()).all()
 
 
+@pytest.mark.parametrize("case", [(2, 32, 64, 128, 128, 0), (2, 40, 20, 256, 256, 0), (1, 16, 24, 384, 128, 384),
+                                  (3, 72, 12, 128, 256, 0), (16, 64, 64, 256, 256, 0), (2, 8, 8, 512, 256, 512)])
+def test_gn_silu_conv3x3_fused_equals_unfused(ops, case):
+    """GroupNorm+SiLU applied inside the convolution (2-CTA kernel) == separate GroupNorm pass + convolution, bit for
+    bit, and both match the fp32 PyTorch chain (layerspp.py:245-271)."""
+    B, H, W, Ci, Co, Cs = case
+    g = torch.Generator().manual_seed(sum(case))
+    x = (torch.randn(B, Ci, H, W, generator=g) * 1.3 + 0.2).to(torch.bfloat16)
+    xs = torch.randn(B, Cs, H, W, generator=g).to(torch.bfloat16) if Cs else None
+    w = (torch.randn(Co, Ci, 3, 3, generator=g) / math.sqrt(9 * Ci)).to(torch.bfloat16)
+    w2 = (torch.randn(Co, Cs, 1, 1, generator=g) / math.sqrt(Cs)).to(torch.bfloat16) if Cs else None
+    gamma, beta = torch.rand(Ci, generator=g) + 0.5, torch.randn(Ci, generator=g) * 0.2
+    bias, tb = torch.randn(Co, generator=g) * 0.1, torch.randn(B, Co, generator=g) * 0.2
+    res = None if Cs else torch.randn(B, Co, H, W, generator=g).to(torch.bfloat16)
+    wt = _pack_w3(w) if not Cs else torch.cat([_pack_w3(w), w2.reshape(Co, Cs)], dim=1).contiguous()
+    dev = lambda t: None if t is None else t.to(DEV)
+    kw = dict(x1=dev(None if xs is None else _nhwc(xs)), bias=dev(bias), tbias=dev(tb),
+              res=dev(None if res is None else _nhwc(res)), scale=0.7)
+    fused = ops.gn_silu_conv3x3_nhwc(dev(_nhwc(x)), dev(gamma), dev(beta), dev(wt), **kw)
+    a = ops.groupnorm_nhwc(dev(_nhwc(x)), dev(gamma), dev(beta), silu=True)
+    unfused = ops.conv_nhwc(a, dev(wt), 9, impl=0, **kw)
+    assert torch.equal(fused, unfused)
+    ref = torch.nn.functional.conv2d(torch.nn.functional.silu(torch.nn.functional.group_norm(x.float(), 32, gamma, beta, 1e-6)),
+                                     w.float(), bias, padding=1) + tb[:, :, None, None]
+    if Cs:
+        ref = ref + torch.nn.functional.conv2d(xs.float(), w2.float())
+    else:
+        ref = ref + res.float()
+    ref = ref * 0.7
+    got = fused.float().cpu().permute(0, 3, 1, 2)
+    err = (got - ref).abs()
+    assert (err <= 2 ** -6 * ref.abs() + 3e-2 * ref.abs().mean()).all(), float(err.max())
+
+
 @pytest.mark.parametrize("C,H,W", [(128, 32, 64), (256, 16, 16), (384, 8, 12), (512, 4, 1), (128, 256, 64)])
 @pytest.mark.parametrize("silu", [True, False])
 def test_groupnorm(ops, C, H, W, silu):
@@ -281,7 +315,8 @@ def _network_report(engine, sd, x, t, flags):
     return ref[:, 0], out.cpu(), rep
 
 
-@pytest.mark.parametrize("flags", [2, 4, 8, 0], ids=["cuda-core-conv", "tcgen05gen1-conv", "tcgen05halo1-conv", "tcgen05-conv"])
+@pytest.mark.parametrize("flags", [2, 4, 8, 16, 0], ids=["cuda-core-conv", "tcgen05gen1-conv", "tcgen05halo1-conv",
+                                                       "tcgen05-unfused-gn", "tcgen05-conv"])
 def test_ncsnpp_forward_vs_golden(engine, sd, golden_dir, flags):
     z = np.load(os.path.join(golden_dir, "ncsnpp_forward.npz"))
     x, t = _c(z["x"]), _c(z["t"])

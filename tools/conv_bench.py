@@ -45,22 +45,30 @@ def main():
         flops = 2.0 * B * H * W * Co * (9 * Ci + Cs)
         row = dict(shape=(B, H, W, Ci, Co, Cs), gflop=flops / 1e9)
         outs = {}
+        gamma = (torch.rand(Ci, generator=g) + 0.5).cuda()
+        beta = (torch.randn(Ci, generator=g) * 0.2).cuda()
+
+        def run(impl):
+            if impl == 5:   # GroupNorm statistics + convolution normalising its operand in flight (timed together)
+                return ops.gn_silu_conv3x3_nhwc(x, gamma, beta, wt, x1=x1, bias=bias)
+            return ops.conv_nhwc(x, wt, 9, x1=x1, bias=bias, impl=impl)
+
         for impl in impls:
             for _ in range(3):
-                out = ops.conv_nhwc(x, wt, 9, x1=x1, bias=bias, impl=impl)
+                out = run(impl)
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             for _ in range(args.iters):
-                out = ops.conv_nhwc(x, wt, 9, x1=x1, bias=bias, impl=impl)
+                out = run(impl)
             e1.record()
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / args.iters
-            if impl in (0, 3) and args.debug:
+            if impl in (0, 3, 5) and args.debug:
                 from snr_aligned_diffse_b200 import _lib
                 dbg = torch.zeros(148 * 8, dtype=torch.int64, device="cuda")
                 _lib.load().snrse_conv_halo_set_debug(_lib.ptr(dbg))
-                ops.conv_nhwc(x, wt, 9, x1=x1, bias=bias, impl=impl)
+                run(impl)
                 torch.cuda.synchronize()
                 _lib.load().snrse_conv_halo_set_debug(None)
                 d = dbg.view(148, 8).double()

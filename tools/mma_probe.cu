@@ -153,6 +153,23 @@ __device__ __forceinline__ void probe_body(const ProbeArgs g) {
             if (CG == 2) ptx::mma_commit_2sm(ptx::smem_u32(&done_bar2)); else ptx::mma_commit(ptx::smem_u32(&done_bar2));
         }
         ptx::mbar_wait(ptx::smem_u32(&done_bar2), 0);
+    } else if ((warp == 2 || warp == 3) && g.traffic == 3) {
+        // SIMT shared-memory traffic: each lane reads 16 B, modifies, writes back (conflict-free rows), until stopped
+        const int w = warp - 2;
+        long long bytes = 0;
+        uint32_t addr = t_base + (uint32_t)w * 16384 + (uint32_t)lane * 16;
+        uint32_t k = 0;
+        while (!stop_flag) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                uint4 v = ptx::lds128(addr + ((k + u) & 31u) * 512u);
+                v.x += 1u;
+                ptx::sts128(addr + ((k + u) & 31u) * 512u, v);
+            }
+            k += 8;
+            bytes += 8 * 32 * 32;   // 8 x (16 B read + 16 B write) x 32 lanes
+        }
+        if (lane == 0) g.out[blockIdx.x * 4 + 2 + w] = bytes;
     } else if ((warp == 2 || warp == 3) && lane == 0 && g.traffic >= warp - 1 && !(warp == 3 && g.issuers == 2)) {
         // side traffic: bulk copies global -> shared, 4 in flight
         const int w = warp - 2;
@@ -228,12 +245,11 @@ int main() {
     CK(cudaMalloc(&gsrc, 148 * 2 * 65536));
     CK(cudaMemset(gsrc, 0, 148 * 2 * 65536));
     CK(cudaMalloc(&dout, sizeof(long long) * 4 * 148));
-    // data dependence (power): zero vs random operands, short and long runs
-    for (int rnd : {0, 1}) {
-        for (int n_iter : {2048, 65536}) {
-            run(2, 256, 128, 0, 0, 0, 8192, 148, gsrc, dout, 1, 4, rnd, n_iter);
-            run(2, 256, 256, 0, 0, 0, 8192, 148, gsrc, dout, 1, 4, rnd, n_iter);
-        }
-    }
+    // SIMT LDS/STS traffic (2 warps) next to the MMAs
+    run(2, 256, 128, 0, 0, 0, 8192, 148, gsrc, dout, 1, 4, 1, 8192);
+    run(2, 256, 128, 0, 3, 0, 8192, 148, gsrc, dout, 1, 4, 1, 8192);
+    run(2, 256, 256, 0, 3, 0, 8192, 148, gsrc, dout, 1, 4, 1, 8192);
+    run(1, 128, 256, 0, 3, 0, 8192, 148, gsrc, dout, 1, 4, 1, 8192);
+    run(2, 256, 32, 0, 3, 0, 8192, 148, gsrc, dout, 1, 4, 1, 8192);
     return 0;
 }
