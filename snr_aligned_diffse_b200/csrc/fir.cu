@@ -5,7 +5,7 @@
 //   up  : zero-insert x2, pad (2,1), gain 4  ->  per axis  out[2i]   = (x[i-1] + 3 x[i]) / 4
 //                                                           out[2i+1] = (3 x[i] + x[i+1]) / 4
 //   down: pad (1,1), keep every 2nd sample   ->  per axis  out[j] = (x[2j-1] + 3 x[2j] + 3 x[2j+1] + x[2j+2]) / 8
-// with zeros outside the image.  One thread produces 8 channels (bf16) or one 4-channel pixel (fp32).
+// with zeros outside the image.
 #include "kernels.h"
 
 namespace {
@@ -19,75 +19,117 @@ __device__ __forceinline__ V8 ld8(const bf16* p) {
     return r;
 }
 
-__global__ void __launch_bounds__(256)
-fir_down2_kernel(const bf16* __restrict__ x, int ld, int C, int H, int W, bf16* __restrict__ out, int out_ld,
-                 int64_t total) {
-    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= total) return;
-    const int tpp = C >> 3;
-    const int c0 = (int)(idx % tpp) * 8;
-    int64_t pix = idx / tpp;
-    const int Ho = H >> 1, Wo = W >> 1;
-    const int wo = (int)(pix % Wo);
-    pix /= Wo;
-    const int ho = (int)(pix % Ho);
-    const int b = (int)(pix / Ho);
+// Both bf16 kernels are separable and walk a band of rows with a sliding window in registers: thread = (column,
+// 8-channel chunk); every input row is filtered horizontally once (3 or 4 loads, neighbours shared through L1)
+// and reused by the two output rows it contributes to, so the kernels move ~1x the tensor instead of issuing
+// 16 (down) / 4 (up) loads per output chunk.  grid = (column blocks, row bands, B).
+constexpr int FIR_BAND = 16;   // rows per block (output rows for down, input rows for up)
+
+__device__ __forceinline__ void zero8(float* a) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] = 0.f;
+}
+
+// horizontal [1,3,3,1]/8 around output column wo of input row hh (zero outside the image)
+__device__ __forceinline__ void hfilt_down(const bf16* __restrict__ img, int ld, int H, int W, int hh, int wo, int c0,
+                                           float* r) {
+    zero8(r);
+    if (hh < 0 || hh >= H) return;
     const float k[4] = {0.125f, 0.375f, 0.375f, 0.125f};
-    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const bf16* row = img + (int64_t)hh * W * ld + c0;
 #pragma unroll
-    for (int a = 0; a < 4; ++a) {
-        const int hh = 2 * ho - 1 + a;
-        if (hh < 0 || hh >= H) continue;
+    for (int t = 0; t < 4; ++t) {
+        const int ww = 2 * wo - 1 + t;
+        if (ww < 0 || ww >= W) continue;
+        const V8 v = ld8(row + (int64_t)ww * ld);
 #pragma unroll
-        for (int bb = 0; bb < 4; ++bb) {
-            const int ww = 2 * wo - 1 + bb;
-            if (ww < 0 || ww >= W) continue;
-            const V8 v = ld8(x + (((int64_t)b * H + hh) * W + ww) * ld + c0);
-            const float kw = k[a] * k[bb];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) acc[j] = fmaf(kw, v.f[j], acc[j]);
-        }
+        for (int j = 0; j < 8; ++j) r[j] = fmaf(k[t], v.f[j], r[j]);
     }
-    *reinterpret_cast<uint4*>(out + (((int64_t)b * Ho + ho) * Wo + wo) * out_ld + c0) = pack8(acc);
 }
 
 __global__ void __launch_bounds__(256)
-fir_up2_kernel(const bf16* __restrict__ x, int ld, int C, int H, int W, bf16* __restrict__ out, int out_ld,
-               int64_t total) {
-    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= total) return;
-    const int tpp = C >> 3;
-    const int c0 = (int)(idx % tpp) * 8;
-    int64_t pix = idx / tpp;
-    const int Ho = H * 2, Wo = W * 2;
-    const int wo = (int)(pix % Wo);
-    pix /= Wo;
-    const int ho = (int)(pix % Ho);
-    const int b = (int)(pix / Ho);
-    // two contributing source rows / columns with weights (1/4, 3/4) or (3/4, 1/4)
-    const int hi = ho >> 1, wi = wo >> 1;
-    const int ha = (ho & 1) ? hi : hi - 1, hb = ha + 1;
-    const int wa = (wo & 1) ? wi : wi - 1, wb = wa + 1;
-    const float kha = (ho & 1) ? 0.75f : 0.25f, khb = 1.0f - kha;
-    const float kwa = (wo & 1) ? 0.75f : 0.25f, kwb = 1.0f - kwa;
-    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    const int hs[2] = {ha, hb};
-    const int ws[2] = {wa, wb};
-    const float kh[2] = {kha, khb};
-    const float kw[2] = {kwa, kwb};
+fir_down2_kernel(const bf16* __restrict__ x, int ld, int C, int H, int W, bf16* __restrict__ out, int out_ld) {
+    const int tpp = C >> 3, cols = blockDim.x / tpp;
+    const int c0 = (threadIdx.x % tpp) * 8;
+    const int Ho = H >> 1, Wo = W >> 1;
+    const int wo = blockIdx.x * cols + threadIdx.x / tpp;
+    if (wo >= Wo) return;
+    const int b = blockIdx.z;
+    const bf16* img = x + (int64_t)b * H * W * ld;
+    const int ho0 = blockIdx.y * FIR_BAND;
+    const int ho1 = min(ho0 + FIR_BAND, Ho);
+    float r0[8], r1[8], r2[8], r3[8];   // horizontally filtered rows 2ho-1 .. 2ho+2
+    hfilt_down(img, ld, H, W, 2 * ho0 - 1, wo, c0, r0);
+    hfilt_down(img, ld, H, W, 2 * ho0, wo, c0, r1);
+    for (int ho = ho0; ho < ho1; ++ho) {
+        hfilt_down(img, ld, H, W, 2 * ho + 1, wo, c0, r2);
+        hfilt_down(img, ld, H, W, 2 * ho + 2, wo, c0, r3);
+        float o[8];
 #pragma unroll
-    for (int a = 0; a < 2; ++a) {
-        if (hs[a] < 0 || hs[a] >= H) continue;
+        for (int j = 0; j < 8; ++j) o[j] = 0.125f * (r0[j] + r3[j]) + 0.375f * (r1[j] + r2[j]);
+        *reinterpret_cast<uint4*>(out + (((int64_t)b * Ho + ho) * Wo + wo) * out_ld + c0) = pack8(o);
 #pragma unroll
-        for (int bb = 0; bb < 2; ++bb) {
-            if (ws[bb] < 0 || ws[bb] >= W) continue;
-            const V8 v = ld8(x + (((int64_t)b * H + hs[a]) * W + ws[bb]) * ld + c0);
-            const float kk = kh[a] * kw[bb];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) acc[j] = fmaf(kk, v.f[j], acc[j]);
-        }
+        for (int j = 0; j < 8; ++j) { r0[j] = r2[j]; r1[j] = r3[j]; }
     }
-    *reinterpret_cast<uint4*>(out + (((int64_t)b * Ho + ho) * Wo + wo) * out_ld + c0) = pack8(acc);
+}
+
+// horizontal interpolation of input row hh at input column wi: ea -> output column 2wi, eb -> 2wi+1
+__device__ __forceinline__ void hfilt_up(const bf16* __restrict__ img, int ld, int H, int W, int hh, int wi, int c0,
+                                         float* ea, float* eb) {
+    zero8(ea);
+    zero8(eb);
+    if (hh < 0 || hh >= H) return;
+    const bf16* row = img + (int64_t)hh * W * ld + c0;
+    const V8 m = ld8(row + (int64_t)wi * ld);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { ea[j] = 0.75f * m.f[j]; eb[j] = 0.75f * m.f[j]; }
+    if (wi > 0) {
+        const V8 l = ld8(row + (int64_t)(wi - 1) * ld);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ea[j] = fmaf(0.25f, l.f[j], ea[j]);
+    }
+    if (wi + 1 < W) {
+        const V8 rr = ld8(row + (int64_t)(wi + 1) * ld);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) eb[j] = fmaf(0.25f, rr.f[j], eb[j]);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+fir_up2_kernel(const bf16* __restrict__ x, int ld, int C, int H, int W, bf16* __restrict__ out, int out_ld) {
+    const int tpp = C >> 3, cols = blockDim.x / tpp;
+    const int c0 = (threadIdx.x % tpp) * 8;
+    const int wi = blockIdx.x * cols + threadIdx.x / tpp;
+    if (wi >= W) return;
+    const int b = blockIdx.z;
+    const int Wo = 2 * W;
+    const bf16* img = x + (int64_t)b * H * W * ld;
+    bf16* oimg = out + (int64_t)b * (2 * H) * Wo * out_ld + c0;
+    const int h0 = blockIdx.y * FIR_BAND;
+    const int h1 = min(h0 + FIR_BAND, H);
+    float pa[8], pb[8], ca[8], cb[8], na[8], nb[8];   // rows hi-1, hi, hi+1 (a: even output column, b: odd)
+    hfilt_up(img, ld, H, W, h0 - 1, wi, c0, pa, pb);
+    hfilt_up(img, ld, H, W, h0, wi, c0, ca, cb);
+    for (int hi = h0; hi < h1; ++hi) {
+        hfilt_up(img, ld, H, W, hi + 1, wi, c0, na, nb);
+        float o[8];
+        bf16* r_even = oimg + ((int64_t)(2 * hi) * Wo + 2 * wi) * out_ld;
+        bf16* r_odd = r_even + (int64_t)Wo * out_ld;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = fmaf(0.25f, pa[j], 0.75f * ca[j]);
+        *reinterpret_cast<uint4*>(r_even) = pack8(o);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = fmaf(0.25f, pb[j], 0.75f * cb[j]);
+        *reinterpret_cast<uint4*>(r_even + out_ld) = pack8(o);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = fmaf(0.25f, na[j], 0.75f * ca[j]);
+        *reinterpret_cast<uint4*>(r_odd) = pack8(o);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = fmaf(0.25f, nb[j], 0.75f * cb[j]);
+        *reinterpret_cast<uint4*>(r_odd + out_ld) = pack8(o);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { pa[j] = ca[j]; pb[j] = cb[j]; ca[j] = na[j]; cb[j] = nb[j]; }
+    }
 }
 
 __global__ void __launch_bounds__(256)
@@ -161,16 +203,20 @@ fir_up2_f4_kernel(const float4* __restrict__ x, int H, int W, float4* __restrict
 
 int fir_down2_launch(const ActView* x, const ActView* out, cudaStream_t s) {
     SNRSE_CHECK_ARG(x->H % 2 == 0 && x->W % 2 == 0 && x->C % 8 == 0, "fir_down2: H, W must be even, C %% 8 == 0");
-    const int64_t total = (int64_t)x->B * (x->H / 2) * (x->W / 2) * (x->C / 8);
-    fir_down2_kernel<<<(unsigned)cdiv64(total, 256), 256, 0, s>>>(x->ptr, x->ld, x->C, x->H, x->W, out->ptr, out->ld, total);
+    SNRSE_CHECK_ARG(x->C <= 2048 && x->B <= 65535, "fir_down2: C <= 2048, B <= 65535");
+    const int tpp = x->C / 8, nthr = tpp * (256 / tpp > 0 ? 256 / tpp : 1), cols = nthr / tpp;
+    dim3 grid((unsigned)cdiv(x->W / 2, cols), (unsigned)cdiv(x->H / 2, FIR_BAND), (unsigned)x->B);
+    fir_down2_kernel<<<grid, nthr, 0, s>>>(x->ptr, x->ld, x->C, x->H, x->W, out->ptr, out->ld);
     SNRSE_LAUNCH_CHECK();
     return SNRSE_OK;
 }
 
 int fir_up2_launch(const ActView* x, const ActView* out, cudaStream_t s) {
     SNRSE_CHECK_ARG(x->C % 8 == 0, "fir_up2: C %% 8 == 0");
-    const int64_t total = (int64_t)x->B * (x->H * 2) * (x->W * 2) * (x->C / 8);
-    fir_up2_kernel<<<(unsigned)cdiv64(total, 256), 256, 0, s>>>(x->ptr, x->ld, x->C, x->H, x->W, out->ptr, out->ld, total);
+    SNRSE_CHECK_ARG(x->C <= 2048 && x->B <= 65535, "fir_up2: C <= 2048, B <= 65535");
+    const int tpp = x->C / 8, nthr = tpp * (256 / tpp > 0 ? 256 / tpp : 1), cols = nthr / tpp;
+    dim3 grid((unsigned)cdiv(x->W, cols), (unsigned)cdiv(x->H, FIR_BAND), (unsigned)x->B);
+    fir_up2_kernel<<<grid, nthr, 0, s>>>(x->ptr, x->ld, x->C, x->H, x->W, out->ptr, out->ld);
     SNRSE_LAUNCH_CHECK();
     return SNRSE_OK;
 }

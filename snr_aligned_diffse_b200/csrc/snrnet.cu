@@ -162,9 +162,11 @@ snr_convt_kernel(const float* __restrict__ a2, ConvtW cw, float* __restrict__ fe
             const int64_t nc = nc0 + cl;
             sx[cl][rr][t] = nc < ncl ? a2[nc * 16384 + (int64_t)(r0 + rr) * 8 + t] : 0.f;
         }
+        // weights: lane = output channel, so the transposing shared-memory store is conflict-free; every channel's
+        // 32*k floats of this chunk are contiguous in global memory (sectors fully used across the loop)
         for (int i = threadIdx.x; i < 32 * 32 * k; i += 256) {
-            const int co = i / (32 * k), rem = i % (32 * k);   // rem = rr*k + dt, contiguous in global
-            sw[rem * 32 + co] = wg[((int64_t)co * 2048 + r0) * k + rem];
+            const int co = i & 31, rem = i >> 5;             // rem = rr*k + dt
+            sw[rem * 32 + co] = __ldg(wg + ((int64_t)co * 2048 + r0) * k + rem);
         }
         __syncthreads();
         for (int rr = 0; rr < 32; ++rr) {
@@ -176,7 +178,8 @@ snr_convt_kernel(const float* __restrict__ a2, ConvtW cw, float* __restrict__ fe
                 if (dt < k) {
                     const float wv = sw[(rr * k + dt) * 32 + lane];
 #pragma unroll
-                    for (int t = 0; t + dt < 8; ++t) acc[t] = fmaf(xf[t + dt], wv, acc[t]);
+                    for (int t = 0; t + dt < 8; ++t)
+                        if (t < nout) acc[t] = fmaf(xf[t + dt], wv, acc[t]);   // only the 9-k valid output frames
                 }
             }
         }
