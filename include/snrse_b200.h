@@ -123,6 +123,13 @@ int snrse_gn_silu_conv3x3_nhwc(const void* x0, int c0, const float* gamma, const
                                int c1, const void* wt, int n, const float* bias, const float* tbias, int tb_stride,
                                const void* res, float scale, void* out, int B, int H, int W, void* workspace,
                                void* stream);
+/* conv3x3 (as snrse_conv_nhwc, taps0 = 9) whose epilogue also accumulates the GroupNorm sums of the result:
+ * ustats [B][n/4][2] int64 fixed point = (sum * 2^30, sum of squares * 2^24) per 4-channel unit (zeroed by the
+ * call).  Integer accumulation: bit-identical from run to run and independent of the batch.
+ * Needs W >= 8, H >= 8, n in {128, 256}. */
+int snrse_conv3x3_nhwc_stats(const void* x0, int c0, const void* x1, int c1, const void* wt, int n, const float* bias,
+                             const float* tbias, int tb_stride, const void* res, float scale, void* out, int B, int H,
+                             int W, void* ustats, void* stream);
 int64_t snrse_groupnorm_workspace_bytes(int B);
 int snrse_groupnorm_nhwc(const void* x, const float* gamma, const float* beta, void* out, int B, int H, int W, int C,
                          int silu, float eps, void* workspace, void* stream);

@@ -109,7 +109,7 @@ int snrse_conv_nhwc(const void* x0, int c0, int taps0, const void* x1, int c1, c
     if (impl == 0 && conv_halo2_eligible(&a0, taps0, n)) {
         ConvHaloPlan hp;
         SNRSE_TRY(conv_halo2_make_plan(&hp, &a0, x1 ? &a1 : nullptr, static_cast<const bf16*>(wt), n, bias, tbias, tb_stride,
-                                       res ? &r : nullptr, scale, static_cast<bf16*>(out), n, nullptr));
+                                       res ? &r : nullptr, scale, static_cast<bf16*>(out), n, nullptr, nullptr));
         return conv_halo2_launch(&hp, S(stream));
     }
     ConvGemmPlan p;
@@ -118,18 +118,37 @@ int snrse_conv_nhwc(const void* x0, int c0, int taps0, const void* x1, int c1, c
     return conv_gemm_launch(&p, S(stream));
 }
 
-int64_t snrse_groupnorm_workspace_bytes(int B) { return (int64_t)B * (gn_max_chunks() * 64 + 1024) * 4; }
+// conv3x3 on the 2-CTA kernel that also accumulates the GroupNorm sums of its result (what the NCSN++ executor uses so
+// that GroupNorm needs no pass of its own): ustats [B][n/4][2] 64-bit fixed point (sum * 2^30, sum of squares * 2^24
+// per 4-channel unit), zeroed here first.
+int snrse_conv3x3_nhwc_stats(const void* x0, int c0, const void* x1, int c1, const void* wt, int n, const float* bias,
+                             const float* tbias, int tb_stride, const void* res, float scale, void* out, int B, int H,
+                             int W, void* ustats, void* stream) {
+    SNRSE_CHECK_ARG(x0 && wt && out && ustats, "conv3x3_stats: null pointer");
+    ActView a0 = mk_view(x0, B, H, W, c0, c0), a1, r;
+    if (x1) a1 = mk_view(x1, B, H, W, c1, c1);
+    if (res) r = mk_view(res, B, H, W, n, n);
+    SNRSE_CHECK_ARG(conv_halo2_eligible(&a0, 9, n), "conv3x3_stats: needs W >= 8, H >= 8, N in {128, 256}");
+    SNRSE_CUDA(cudaMemsetAsync(ustats, 0, (size_t)B * (n / 4) * 16, S(stream)));
+    ConvHaloPlan hp;
+    SNRSE_TRY(conv_halo2_make_plan(&hp, &a0, x1 ? &a1 : nullptr, static_cast<const bf16*>(wt), n, bias, tbias, tb_stride,
+                                   res ? &r : nullptr, scale, static_cast<bf16*>(out), n, nullptr,
+                                   static_cast<unsigned long long*>(ustats)));
+    return conv_halo2_launch(&hp, S(stream));
+}
+
+int64_t snrse_groupnorm_workspace_bytes(int B) { return (int64_t)B * (128 * 16 + 1024 * 4); }
 
 int snrse_groupnorm_nhwc(const void* x, const float* gamma, const float* beta, void* out, int B, int H, int W, int C,
                          int silu, float eps, void* workspace, void* stream) {
     SNRSE_CHECK_ARG(x && gamma && beta && out && workspace, "groupnorm: null pointer");
     const ActView vx = mk_view(x, B, H, W, C, C), vo = mk_view(out, B, H, W, C, C);
-    float* partial = static_cast<float*>(workspace);
-    float* scsh = partial + (int64_t)B * gn_max_chunks() * 64;
+    unsigned long long* ust = static_cast<unsigned long long*>(workspace);
+    float* scsh = reinterpret_cast<float*>(ust + (int64_t)B * 128 * 2);
     const int64_t hw = (int64_t)H * W;
-    int chunks = (int)(hw / 256 < 1 ? 1 : (hw / 256 > gn_max_chunks() ? gn_max_chunks() : hw / 256));
-    SNRSE_TRY(gn_stats_launch(&vx, partial, chunks, S(stream)));
-    SNRSE_TRY(gn_finalize_launch(partial, chunks, B, C, hw * (C / 32), gamma, beta, eps, scsh, S(stream)));
+    SNRSE_CUDA(cudaMemsetAsync(ust, 0, (size_t)B * (C / 4) * 16, S(stream)));
+    SNRSE_TRY(gn_stats_launch(&vx, ust, S(stream)));
+    SNRSE_TRY(gn_finalize_launch(ust, C / 4, nullptr, 0, B, hw * (C / 32), gamma, beta, eps, scsh, S(stream)));
     return gn_apply_launch(&vx, scsh, silu, &vo, S(stream));
 }
 
@@ -145,15 +164,15 @@ int snrse_gn_silu_conv3x3_nhwc(const void* x0, int c0, const float* gamma, const
     if (x1) a1 = mk_view(x1, B, H, W, c1, c1);
     if (res) r = mk_view(res, B, H, W, n, n);
     SNRSE_CHECK_ARG(conv_halo2_eligible(&a0, 9, n), "gn_silu_conv3x3: needs W >= 8, H >= 8, N in {128, 256}");
-    float* partial = static_cast<float*>(workspace);
-    float* scsh = partial + (int64_t)B * gn_max_chunks() * 64;
+    unsigned long long* ust = static_cast<unsigned long long*>(workspace);
+    float* scsh = reinterpret_cast<float*>(ust + (int64_t)B * 128 * 2);
     const int64_t hw = (int64_t)H * W;
-    int chunks = (int)(hw / 256 < 1 ? 1 : (hw / 256 > gn_max_chunks() ? gn_max_chunks() : hw / 256));
-    SNRSE_TRY(gn_stats_launch(&a0, partial, chunks, S(stream)));
-    SNRSE_TRY(gn_finalize_launch(partial, chunks, B, c0, hw * (c0 / 32), gamma, beta, eps, scsh, S(stream)));
+    SNRSE_CUDA(cudaMemsetAsync(ust, 0, (size_t)B * (c0 / 4) * 16, S(stream)));
+    SNRSE_TRY(gn_stats_launch(&a0, ust, S(stream)));
+    SNRSE_TRY(gn_finalize_launch(ust, c0 / 4, nullptr, 0, B, hw * (c0 / 32), gamma, beta, eps, scsh, S(stream)));
     ConvHaloPlan hp;
     SNRSE_TRY(conv_halo2_make_plan(&hp, &a0, x1 ? &a1 : nullptr, static_cast<const bf16*>(wt), n, bias, tbias, tb_stride,
-                                   res ? &r : nullptr, scale, static_cast<bf16*>(out), n, scsh));
+                                   res ? &r : nullptr, scale, static_cast<bf16*>(out), n, scsh, nullptr));
     return conv_halo2_launch(&hp, S(stream));
 }
 

@@ -27,6 +27,7 @@
 #include <cuda.h>
 #include <stdlib.h>
 
+#include "gn_fixed.cuh"
 #include "kernels.h"
 #include "ptx.cuh"
 #include "tma_host.h"
@@ -53,6 +54,7 @@ struct Halo2Args {
     int acc_bufs;                  // 1 or 2 TMEM accumulator sets
     int stg_bufs;                  // 1 or 2 staging tiles per epilogue warp
     int has_res;
+    unsigned long long* ustats;    // null, or GroupNorm sums of the result, accumulated: [B][N/4][2] fixed point (gn_fixed.cuh)
     const float* scsh;             // null, or GroupNorm scale/shift [B][2][norm_c] applied (+SiLU) to operand 0 in shared memory
     int norm_c;
     const float* bias;
@@ -78,6 +80,42 @@ __device__ __forceinline__ uint64_t umma_desc_rows(uint32_t smem_addr, uint32_t 
     d |= (uint64_t)1 << 46;
     d |= (uint64_t)2 << 61;
     return d;
+}
+
+// Sum v[0..15] over the 32 lanes of the warp with a transpose-reduce butterfly (16 shuffles instead of 80): after
+// it, lane l holds the warp total of element ((l>>1) & 15) [bit 4 of l = element bit 3, ... bit 1 = element bit 0;
+// lanes l and l^1 hold the same value].  Fixed order -> deterministic.
+__device__ __forceinline__ float warp_transpose_reduce16(float* v, int lane) {
+    {
+        const bool up = lane & 16;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float keep = up ? v[i + 8] : v[i], send = up ? v[i] : v[i + 8];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+        }
+    }
+    {
+        const bool up = lane & 8;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float keep = up ? v[i + 4] : v[i], send = up ? v[i] : v[i + 4];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+        }
+    }
+    {
+        const bool up = lane & 4;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const float keep = up ? v[i + 2] : v[i], send = up ? v[i] : v[i + 2];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+        }
+    }
+    {
+        const bool up = lane & 2;
+        const float keep = up ? v[1] : v[0], send = up ? v[0] : v[1];
+        v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    }
+    return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
 }
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(HALO_THREADS + NORM_THREADS, 1)
@@ -369,6 +407,7 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
         uint32_t itt = 0, cnt = 0, rphase = 0;
         int last_b = -1;
         long long w_full = 0, t_body = 0;
+        const int units = g.N >> 2;
         DBG_T0();
         for (int ct = cluster_id; ct < n_ctiles; ct += n_clusters, ++itt) {
             const int tile = 2 * ct + (int)rank;
@@ -392,6 +431,8 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
             ptx::mbar_wait(ptx::smem_u32(&acc_full[buf]), use & 1u);
             DBG_ADD(w_full);
             ptx::tc_fence_after();
+            // GroupNorm sums of this tile (pass 0 / 1), already in fixed point: integer adds keep them independent of SUB
+            unsigned long long tile_s0 = 0, tile_q0 = 0, tile_s1 = 0, tile_q1 = 0;
             for (int u = 0; u < g.sub; ++u) {
                 const int hrow = h0 + SUB_ROWS * u + 4 * quarter;   // this warp's four image rows (32 pixels)
                 for (int p = 0; p < n_pass; ++p, ++cnt) {
@@ -407,6 +448,8 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
                         ptx::tma_load_4d(stg, &mapRes, my_rbar, cbase, w0, hrow, b);
                     }
                     const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * acc_cols + (uint32_t)(u * g.N + cbase);
+                    float us[16], uq[16];   // this pixel's unit sums / sums of squares for the 64 channels of the pass
+                    const bool pix_ok = b < g.B && (hrow + (lane >> 3)) < g.H && (w0 + (lane & 7)) < g.W;
 #pragma unroll
                     for (int hq = 0; hq < 2; ++hq) {   // 32 accumulator columns at a time (register budget: 640 threads)
                         uint32_t v[32];
@@ -438,7 +481,24 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
                                 for (int i = 0; i < 8; ++i) f[i] = fmaf(rr[i], g.scale, f[i]);
                             }
                             ptx::sts128(addr, pack8(f));
+                            if (g.ustats) {
+                                us[2 * q] = (f[0] + f[1]) + (f[2] + f[3]);
+                                us[2 * q + 1] = (f[4] + f[5]) + (f[6] + f[7]);
+                                uq[2 * q] = fmaf(f[0], f[0], f[1] * f[1]) + fmaf(f[2], f[2], f[3] * f[3]);
+                                uq[2 * q + 1] = fmaf(f[4], f[4], f[5] * f[5]) + fmaf(f[6], f[6], f[7] * f[7]);
+                            }
                         }
+                    }
+                    if (g.ustats) {
+                        if (!pix_ok) {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) us[i] = uq[i] = 0.f;
+                        }
+                        // warp totals over its 32 pixels (fixed order), then exact integer accumulation: the statistics
+                        // do not depend on which CTA handled which tile
+                        const float ts = warp_transpose_reduce16(us, lane), tq = warp_transpose_reduce16(uq, lane);
+                        if (p == 0) { tile_s0 += gn_fix_sum(ts); tile_q0 += gn_fix_sq(tq); }
+                        else { tile_s1 += gn_fix_sum(ts); tile_q1 += gn_fix_sq(tq); }
                     }
                     ptx::fence_proxy_async();
                     __syncwarp();
@@ -452,6 +512,15 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive_remote(ptx::mapa_rank0(ptx::smem_u32(&acc_empty[buf])));
+            if (g.ustats && !(lane & 1) && b < g.B) {   // lane l holds unit ((l>>1)&15) of each 64-channel pass
+                unsigned long long* dst = g.ustats + ((int64_t)b * units + half * (units >> 1) + ((lane >> 1) & 15)) * 2;
+                atomicAdd(dst, tile_s0);
+                atomicAdd(dst + 1, tile_q0);
+                if (n_pass == 2) {
+                    atomicAdd(dst + 32, tile_s1);
+                    atomicAdd(dst + 33, tile_q1);
+                }
+            }
             DBG_ADD(t_body);
         }
         if (elected) ptx::bulk_wait_group_read<0>();   // staging tiles must outlive the last stores' reads
@@ -479,7 +548,7 @@ bool conv_halo2_eligible(const ActView* a0, int taps0, int n_rows) {
 
 int conv_halo2_make_plan(ConvHaloPlan* p, const ActView* a0, const ActView* a1, const bf16* wt, int n_rows,
                          const float* bias, const float* tbias, int tb_stride, const ActView* res, float scale, bf16* out,
-                         int out_ld, const float* scsh) {
+                         int out_ld, const float* scsh, unsigned long long* ustats) {
     SNRSE_CHECK_ARG(conv_halo2_eligible(a0, 9, n_rows), "conv_halo2: shape not eligible");
     SNRSE_CHECK_ARG(a0->C % 64 == 0 && a0->ld % 8 == 0, "conv_halo2: Cin must be a multiple of 64");
     SNRSE_CHECK_ARG(!a1 || (a1->C % 64 == 0 && a1->ld % 8 == 0 && a1->H == a0->H && a1->W == a0->W && a1->B == a0->B),
@@ -526,6 +595,7 @@ int conv_halo2_make_plan(ConvHaloPlan* p, const ActView* a0, const ActView* a1, 
     p->res = res ? res->ptr : nullptr; p->res_ld = res ? res->ld : 0;
     p->scale = scale; p->out = out; p->out_ld = out_ld;
     p->scsh = scsh;
+    p->ustats = ustats;
     const int box_h = SUB_ROWS * sub + 2;
     SNRSE_TRY(tma_make_act_map(&p->mapA0, a0->ptr, a0->C, a0->W, a0->H, a0->B, a0->ld, 64, HALO_W, box_h));
     if (a1) SNRSE_TRY(tma_make_act_map(&p->mapA1, a1->ptr, a1->C, a1->W, a1->H, a1->B, a1->ld, 64, HALO_W, box_h));
@@ -554,6 +624,7 @@ int conv_halo2_launch(const ConvHaloPlan* p, cudaStream_t s) {
     g.bias = p->bias; g.tbias = p->tbias; g.tb_stride = p->tb_stride;
     g.scale = p->scale;
     g.scsh = p->scsh; g.norm_c = p->c0_chunks * 64;
+    g.ustats = p->ustats;
     g.dbg = g_halo_dbg_shared;
     conv_halo2_kernel<<<p->grid, HALO_THREADS + (p->scsh ? NORM_THREADS : 0), p->smem_bytes, s>>>(p->mapA0, p->mapA1, p->mapB, p->mapOut, p->mapRes, g);
     SNRSE_LAUNCH_CHECK();

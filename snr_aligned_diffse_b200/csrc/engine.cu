@@ -69,11 +69,19 @@ struct Plan {
     std::vector<std::function<int(Plan&)>> builders;
     std::vector<std::function<int(cudaStream_t)>> launches;
     std::map<int, int> taps;  // module index -> tensor id
+    // GroupNorm statistics by tensor: entry index into the fixed-point statistics arena t_stats (zeroed at the start
+    // of every forward; an entry holds [B][128 units][2] 64-bit sums)
+    std::map<int, int> stats_of;
+    int n_stat_entries = 0;
+    unsigned long long* stat_ptr(int entry) const {
+        return reinterpret_cast<unsigned long long*>(ws + tens[t_stats].off) + (int64_t)entry * B * 256;
+    }
+    std::map<int, std::pair<int, int>> cat_children;
     int step = 0;
     int64_t ws_bytes = 0;
     uint8_t* ws = nullptr;
     // fixed slots
-    int t_x4, t_tb, t_tscr, t_partial, t_scsh, t_pyr_final;
+    int t_x4, t_tb, t_tscr, t_stats, t_scsh, t_pyr_final;
     // bound per call
     const float* t_ptr = nullptr;
     const float2 *x_ptr = nullptr, *y_ptr = nullptr;
@@ -111,6 +119,7 @@ struct Plan {
         tens[c].last = std::max(tens[a].last, tens[b].last);
         tens[a].parent = c; tens[a].coff = 0;
         tens[b].parent = c; tens[b].coff = tens[a].C;
+        cat_children[c] = {a, b};
         return c;
     }
     ActView view(int id) const {
@@ -311,12 +320,18 @@ int build_topology(Engine& e, int image_size) {
 // current step, (c) registers a builder that, once buffers are placed, appends the launch closures.
 // ------------------------------------------------------------------------------------------------
 const float INV_SQRT2 = 0.70710678118654752440f;
+constexpr int MAX_STAT_ENTRIES = 192;   // tensors with GroupNorm statistics per forward (NCSN++ default: ~110)
 enum { LK_OTHER = 0, LK_GEMM = 1, LK_GN = 2, LK_FIR = 3, LK_ATTN = 4, LK_THIN = 5, LK_HEAD = 6 };
 
 int rec_gemm(Plan& P, int a0, int taps0, int a1, int64_t w_off, int n_rows, int64_t bias_off, int tb_row, int res,
-             float scale, int out, int norm = 0) {
+             float scale, int out, int norm = 0, int want_stats = 0) {
     P.use(a0);
     if (norm) P.use(P.t_scsh);
+    int st = -1;
+    if (want_stats) {   // the epilogue also accumulates the GroupNorm sums of `out`
+        st = P.n_stat_entries++;
+        P.stats_of[out] = st;
+    }
     if (a1 >= 0) P.use(a1);
     if (res >= 0) P.use(res);
     P.use(out);
@@ -361,11 +376,11 @@ int rec_gemm(Plan& P, int a0, int taps0, int a1, int64_t w_off, int n_rows, int6
             ConvHaloPlan hp;
             SNRSE_TRY(conv_halo2_make_plan(&hp, &va0, a1 >= 0 ? &va1 : nullptr, e.wb(w_off), n_rows, bias, tb, tb_stride,
                                            res >= 0 ? &vres : nullptr, scale, vout.ptr, vout.ld,
-                                           norm ? p.fptr(p.t_scsh) : nullptr));
+                                           norm ? p.fptr(p.t_scsh) : nullptr, st >= 0 ? p.stat_ptr(st) : nullptr));
             p.add(LK_GEMM, 2.0 * px * n_rows * kt, by, [hp](cudaStream_t s) { return conv_halo2_launch(&hp, s); });
             return SNRSE_OK;
         }
-        if (norm) {
+        if (norm || st >= 0) {
             snrse_set_error("internal: fused GroupNorm requested for a convolution the 2-CTA kernel cannot run");
             return SNRSE_ERR_STATE;
         }
@@ -378,56 +393,72 @@ int rec_gemm(Plan& P, int a0, int taps0, int a1, int64_t w_off, int n_rows, int6
     return out;
 }
 
-// GroupNorm (+SiLU) -> new dense tensor
-int rec_gn(Plan& P, int x, int64_t g_off, int64_t b_off, int silu) {
+// Sums of tensor x for GroupNorm: accumulated by its writer when that was the 2-CTA convolution, otherwise by one
+// stand-alone pass (cached: skip tensors are normalised twice, in the down path and inside a concatenation).
+int get_stats(Plan& P, int x) {
+    auto it = P.stats_of.find(x);
+    if (it != P.stats_of.end()) return it->second;
+    const int st = P.n_stat_entries++;
+    P.stats_of[x] = st;
+    P.use(x);
+    P.step++;
+    P.builders.push_back([=](Plan& p) -> int {
+        const ActView vx = p.view(x);
+        unsigned long long* dst = p.stat_ptr(st);
+        const double el = (double)vx.B * vx.H * vx.W * vx.C;
+        p.add(LK_GN, 0.0, 2.0 * el, [=](cudaStream_t s) { return gn_stats_launch(&vx, dst, s); });
+        return SNRSE_OK;
+    });
+    return st;
+}
+
+// scale/shift of GroupNorm(x) into t_scsh; x may be a concatenation whose halves carry their own statistics
+void rec_gn_finalize(Plan& P, int x, int64_t g_off, int64_t b_off) {
+    int s0, s1 = -1, u0, u1 = 0;
+    auto cc = P.cat_children.find(x);
+    if (cc != P.cat_children.end()) {
+        s0 = get_stats(P, cc->second.first);
+        s1 = get_stats(P, cc->second.second);
+        u0 = P.tens[cc->second.first].C / 4;
+        u1 = P.tens[cc->second.second].C / 4;
+    } else {
+        s0 = get_stats(P, x);
+        u0 = P.tens[x].C / 4;
+    }
     const LT tx = P.tens[x];
-    const int out = P.new_t(tx.B, tx.H, tx.W, tx.C, 2);
-    P.use(x); P.use(out); P.use(P.t_partial); P.use(P.t_scsh);
+    P.use(P.t_scsh);
     P.step++;
     P.builders.push_back([=](Plan& p) -> int {
         Engine& e = *p.eng;
-        const ActView vx = p.view(x), vo = p.view(out);
-        const int64_t hw = (int64_t)vx.H * vx.W;
-        int chunks = (int)std::min<int64_t>(gn_max_chunks(), std::max<int64_t>(1, hw / 256));
-        while ((int64_t)chunks * vx.B > 1184 && chunks > 1) chunks = (chunks + 1) / 2;  // ~8 blocks per SM at most
-        float* partial = p.fptr(p.t_partial);
+        const unsigned long long* a0 = p.stat_ptr(s0);
+        const unsigned long long* a1 = s1 >= 0 ? p.stat_ptr(s1) : nullptr;
         float* scsh = p.fptr(p.t_scsh);
         const float* gamma = e.wf(g_off);
         const float* beta = e.wf(b_off);
-        const int64_t cnt = hw * (vx.C / 32);
-        const double el = (double)vx.B * hw * vx.C;
-        p.add(LK_GN, 0.0, 2.0 * el * 3, [=](cudaStream_t s) {   // read x twice (stats, apply) + write once, bf16
-            SNRSE_TRY(gn_stats_launch(&vx, partial, chunks, s));
-            SNRSE_TRY(gn_finalize_launch(partial, chunks, vx.B, vx.C, cnt, gamma, beta, 1e-6f, scsh, s));
-            return gn_apply_launch(&vx, scsh, silu, &vo, s);
+        const int64_t cnt = (int64_t)tx.H * tx.W * (tx.C / 32);
+        const int B = tx.B;
+        p.add(LK_GN, 0.0, 0.0, [=](cudaStream_t s) {
+            return gn_finalize_launch(a0, u0, a1, u1, B, cnt, gamma, beta, 1e-6f, scsh, s);
         });
+        return SNRSE_OK;
+    });
+}
+
+// GroupNorm (+SiLU) as its own pass -> new dense tensor
+int rec_gn(Plan& P, int x, int64_t g_off, int64_t b_off, int silu) {
+    rec_gn_finalize(P, x, g_off, b_off);
+    const LT tx = P.tens[x];
+    const int out = P.new_t(tx.B, tx.H, tx.W, tx.C, 2);
+    P.use(x); P.use(out); P.use(P.t_scsh);
+    P.step++;
+    P.builders.push_back([=](Plan& p) -> int {
+        const ActView vx = p.view(x), vo = p.view(out);
+        float* scsh = p.fptr(p.t_scsh);
+        const double el = (double)vx.B * vx.H * vx.W * vx.C;
+        p.add(LK_GN, 0.0, 2.0 * el * 2, [=](cudaStream_t s) { return gn_apply_launch(&vx, scsh, silu, &vo, s); });
         return SNRSE_OK;
     });
     return out;
-}
-
-// GroupNorm statistics only: leaves scale/shift in t_scsh for a convolution that normalises its operand in flight
-void rec_gn_stats(Plan& P, int x, int64_t g_off, int64_t b_off) {
-    P.use(x); P.use(P.t_partial); P.use(P.t_scsh);
-    P.step++;
-    P.builders.push_back([=](Plan& p) -> int {
-        Engine& e = *p.eng;
-        const ActView vx = p.view(x);
-        const int64_t hw = (int64_t)vx.H * vx.W;
-        int chunks = (int)std::min<int64_t>(gn_max_chunks(), std::max<int64_t>(1, hw / 256));
-        while ((int64_t)chunks * vx.B > 1184 && chunks > 1) chunks = (chunks + 1) / 2;
-        float* partial = p.fptr(p.t_partial);
-        float* scsh = p.fptr(p.t_scsh);
-        const float* gamma = e.wf(g_off);
-        const float* beta = e.wf(b_off);
-        const int64_t cnt = hw * (vx.C / 32);
-        const double el = (double)vx.B * hw * vx.C;
-        p.add(LK_GN, 0.0, 2.0 * el, [=](cudaStream_t s) {   // one read of x
-            SNRSE_TRY(gn_stats_launch(&vx, partial, chunks, s));
-            return gn_finalize_launch(partial, chunks, vx.B, vx.C, cnt, gamma, beta, 1e-6f, scsh, s);
-        });
-        return SNRSE_OK;
-    });
 }
 
 // can the 2-CTA kernel run (and therefore normalise in flight) a 3x3 convolution on this tensor?
@@ -457,7 +488,7 @@ int rec_resblock(Plan& P, const Mod& m, int x) {
     // GroupNorm_0 + SiLU (+ FIR resampling of both branches) + Conv_0 + Dense_0(temb)
     int a, xs = x, fuse0 = 0;
     if (!m.up && !m.down && fusable(P, x, m.cout)) {
-        rec_gn_stats(P, x, m.o[0], m.o[1]);     // normalisation itself happens inside Conv_0
+        rec_gn_finalize(P, x, m.o[0], m.o[1]);  // normalisation itself happens inside Conv_0
         a = x;
         fuse0 = 1;
     } else {
@@ -467,18 +498,21 @@ int rec_resblock(Plan& P, const Mod& m, int x) {
     }
     const LT ta = P.tens[a];
     const int h = P.new_t(ta.B, ta.H, ta.W, m.cout, 2);
-    rec_gemm(P, a, 9, -1, m.o[2], m.cout, m.o[3], m.tb_row, -1, 1.0f, h, fuse0);
+    // the 2-CTA kernel's epilogue also emits the GroupNorm partial sums of what it writes
+    const int stats0 = fusable(P, a, m.cout);
+    rec_gemm(P, a, 9, -1, m.o[2], m.cout, m.o[3], m.tb_row, -1, 1.0f, h, fuse0, stats0);
     // GroupNorm_1 + SiLU + Conv_1 (+ Conv_2 shortcut or identity residual), / sqrt(2)
     int a2 = h, fuse1 = 0;
     if (fusable(P, h, m.cout)) {
-        rec_gn_stats(P, h, m.o[4], m.o[5]);
+        rec_gn_finalize(P, h, m.o[4], m.o[5]);
         fuse1 = 1;
     } else {
         a2 = rec_gn(P, h, m.o[4], m.o[5], 1);
     }
     const int out = P.new_t(ta.B, ta.H, ta.W, m.cout, 2);
-    if (m.has_c2) rec_gemm(P, a2, 9, xs, m.o[6], m.cout, m.o[7], -1, -1, INV_SQRT2, out, fuse1);
-    else rec_gemm(P, a2, 9, -1, m.o[6], m.cout, m.o[7], -1, xs, INV_SQRT2, out, fuse1);
+    const int stats1 = fusable(P, a2, m.cout);
+    if (m.has_c2) rec_gemm(P, a2, 9, xs, m.o[6], m.cout, m.o[7], -1, -1, INV_SQRT2, out, fuse1, stats1);
+    else rec_gemm(P, a2, 9, -1, m.o[6], m.cout, m.o[7], -1, xs, INV_SQRT2, out, fuse1, stats1);
     return out;
 }
 
@@ -514,9 +548,9 @@ int record_plan(Plan& P) {
     P.t_x4 = P.new_t(B, F, T, 4, 4);
     P.t_tb = P.new_t(B, 1, 1, e.dense_rows, 4);
     P.t_tscr = P.new_t(B, 1, 1, 4 * nf, 4);
-    P.t_partial = P.new_t(B, 1, 1, gn_max_chunks() * 64, 4);
+    P.t_stats = P.new_t(B, 1, 1, MAX_STAT_ENTRIES * 512, 4);   // statistics arena: entries of [B][128 units][2] x 8 bytes
     P.t_scsh = P.new_t(B, 1, 1, 2 * 512, 4);
-    const int persistent[] = {P.t_x4, P.t_tb, P.t_tscr, P.t_partial, P.t_scsh};
+    const int persistent[] = {P.t_x4, P.t_tb, P.t_tscr, P.t_stats, P.t_scsh};
     size_t mi = 0;
     // --- input packing + time embedding
     P.use(P.t_x4); P.use(P.t_tb); P.use(P.t_tscr);
@@ -529,7 +563,10 @@ int record_plan(Plan& P) {
         float* scr = p.fptr(p.t_tscr);
         const int64_t n = (int64_t)p.F * p.T;
         const Mod mf = e.mods[0], m1 = e.mods[1], m2 = e.mods[2];
+        unsigned long long* stats0 = p.stat_ptr(0);
+        const size_t stats_bytes = (size_t)p.n_stat_entries * p.B * 256 * 8;
         p.add(LK_HEAD, 0.0, (double)p.B * n * 32, [=, &e](cudaStream_t s) {
+            SNRSE_CUDA(cudaMemsetAsync(stats0, 0, stats_bytes, s));   // GroupNorm sums are accumulated with atomics
             SNRSE_TRY(pack_input_launch(pp->x_ptr, pp->y_ptr, x4, pp->B, n, s));
             return temb_launch(pp->t_ptr, pp->B, e.nf, e.wf(mf.o[0]), e.wf(m1.o[0]), e.wf(m1.o[1]), e.wf(m2.o[0]),
                                e.wf(m2.o[1]), e.wf(e.dense_w_off), e.wf(e.dense_b_off), e.dense_rows, scr, tb, s);
@@ -643,6 +680,10 @@ int record_plan(Plan& P) {
             h = rec_resblock(P, e.mods[mi], h);
             P.taps[(int)mi] = h; ++mi;
         }
+    }
+    if (P.n_stat_entries > MAX_STAT_ENTRIES) {
+        snrse_set_error("internal: %d GroupNorm statistics entries exceed the arena (%d)", P.n_stat_entries, MAX_STAT_ENTRIES);
+        return SNRSE_ERR_STATE;
     }
     if (!hs.empty() || mi != e.mods.size()) {
         snrse_set_error("internal: plan/topology mismatch (mi=%d of %d)", (int)mi, (int)e.mods.size());

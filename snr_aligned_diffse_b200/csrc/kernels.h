@@ -59,6 +59,7 @@ struct ConvHaloPlan {
     bf16* out;
     int out_ld;
     const float* scsh;   // 2-CTA kernel only
+    unsigned long long* ustats;   // 2-CTA kernel only
 };
 bool conv_halo_eligible(const ActView* a0, int taps0, int n_rows);
 int conv_halo_make_plan(ConvHaloPlan* p, const ActView* a0, const ActView* a1, const bf16* wt, int n_rows,
@@ -71,7 +72,9 @@ bool conv_halo2_eligible(const ActView* a0, int taps0, int n_rows);
 // silu(x*scale + shift) inside the kernel (GroupNorm+SiLU+conv3x3 of ResnetBlockBigGANpp without the HBM round trip).
 int conv_halo2_make_plan(ConvHaloPlan* p, const ActView* a0, const ActView* a1, const bf16* wt, int n_rows,
                          const float* bias, const float* tbias, int tb_stride, const ActView* res, float scale, bf16* out,
-                         int out_ld, const float* scsh);
+                         int out_ld, const float* scsh, unsigned long long* ustats);
+// ustats (nullable): the epilogue also accumulates the GroupNorm sums of the result into [B][N/4][2] (zeroed by the
+// caller; gn_finalize_launch source format), so the following GroupNorm needs no pass over the tensor.
 int conv_halo2_launch(const ConvHaloPlan* p, cudaStream_t s);
 
 // ----------------------------------------------------------------------------- conv_simt.cu
@@ -89,11 +92,15 @@ int combine4_launch(const float* p4, const ActView* h, const float* w, const flo
                     cudaStream_t s);
 
 // ----------------------------------------------------------------------------- norm.cu
-int gn_max_chunks();
-// partial: [B][chunks][32][2] f32; scsh: [B][2][C] f32 (scale, shift)
-int gn_stats_launch(const ActView* x, float* partial, int chunks, cudaStream_t s);
-int gn_finalize_launch(const float* partial, int chunks, int B, int C, int64_t count_per_group, const float* gamma,
-                       const float* beta, float eps, float* scsh, cudaStream_t s);
+// Statistics per 4-channel unit: ustats [B][U][2] (U = C/4) 64-bit fixed-point (sum, sum of squares), ACCUMULATED
+// with integer atomics into a buffer the caller zeroed (gn_fixed.cuh):
+//   gn_stats_launch   : stand-alone pass over x
+//   gn_finalize_launch: one source (U1 = 0) or two (GroupNorm over the channel concatenation [src0 | src1]);
+//                       scsh: [B][2][C] f32 (scale, shift), C = 4*(U0+U1)
+int gn_stats_launch(const ActView* x, unsigned long long* ustats, cudaStream_t s);
+int gn_finalize_launch(const unsigned long long* src0, int U0, const unsigned long long* src1, int U1, int B,
+                       int64_t count_per_group, const float* gamma, const float* beta, float eps, float* scsh,
+                       cudaStream_t s);
 int gn_apply_launch(const ActView* x, const float* scsh, int silu, const ActView* out, cudaStream_t s);
 
 // ----------------------------------------------------------------------------- fir.cu

@@ -3,10 +3,16 @@
 // (sgmse-bbed/sgmse/backbones/ncsnpp_utils/layerspp.py:221,233,245,266; ncsnpp.py:210,348,362);
 // biased variance over (C/32)*H*W elements per (sample, group).
 //
-// Three kernels, all deterministic (no floating-point atomics):
-//   gn_stats    : per-(sample, pixel-chunk) partial sum / sum-of-squares per group   -> partial[B][chunks][32][2]
-//   gn_finalize : combine partials in double, fold gamma/beta into per-(sample,channel) scale/shift
+// Statistics are kept per 4-channel UNIT (the group size at C=128; 2 / 3 / 4 units per group at C = 256 / 384 / 512)
+// as [B][U][2] (sum, sum of squares; U = C/4) 64-bit FIXED-POINT integers (gn_fixed.cuh) accumulated with integer
+// atomics: a tensor's statistics can be produced by whoever writes it (the convolution epilogue, conv_halo2.cu) and
+// re-grouped later, e.g. for the GroupNorm over torch.cat([h, skip]) (ncsnpp.py:337) from the two producers' units.
+// Integer addition commutes, so the result is bit-identical from run to run and independent of how pixels are
+// distributed over CTAs (no floating-point atomics anywhere).
+//   gn_stats    : stand-alone pass over a tensor (fp32 partial per block of <= 1024 pixels -> integer atomics)
+//   gn_finalize : regroup the units of one or two sources, fold gamma/beta into per-(sample, channel) scale/shift
 //   gn_apply    : y = silu(x*scale + shift)   (vectorised 8 channels / thread, HBM-bound)
+#include "gn_fixed.cuh"
 #include "kernels.h"
 
 namespace {
@@ -16,8 +22,8 @@ constexpr int GN_MAX_CHUNKS = 128;
 
 // thread t handles channel vector (t % tpp) of pixels (t / tpp) + k*ppb
 __global__ void __launch_bounds__(256)
-gn_stats_kernel(const bf16* __restrict__ x, int ld, int C, int64_t hw, int pix_per_chunk, float* __restrict__ partial,
-                int chunks) {
+gn_stats_kernel(const bf16* __restrict__ x, int ld, int C, int64_t hw, int pix_per_chunk,
+                unsigned long long* __restrict__ ustats) {
     const int tpp = C >> 3;
     const int ppb = blockDim.x / tpp;
     const int vec = threadIdx.x % tpp, prow = threadIdx.x / tpp;
@@ -67,33 +73,32 @@ gn_stats_kernel(const bf16* __restrict__ x, int ld, int C, int64_t hw, int pix_p
         hv_q[threadIdx.x] = q;
     }
     __syncthreads();
-    if (threadIdx.x < GN_GROUPS) {
-        const int units = (C / GN_GROUPS) >> 2;  // 4-channel units per group (1..4)
-        float a = 0.f, q = 0.f;
-        for (int u = 0; u < units; ++u) {
-            a += hv_s[threadIdx.x * units + u];
-            q += hv_q[threadIdx.x * units + u];
-        }
-        float* dst = partial + (((int64_t)b * chunks + chunk) * GN_GROUPS + threadIdx.x) * 2;
-        dst[0] = a;
-        dst[1] = q;
+    if ((int)threadIdx.x < halves) {   // one (sum, sumsq) pair per 4-channel unit, accumulated in fixed point
+        unsigned long long* dst = ustats + ((int64_t)b * halves + threadIdx.x) * 2;
+        atomicAdd(dst, gn_fix_sum(hv_s[threadIdx.x]));
+        atomicAdd(dst + 1, gn_fix_sq(hv_q[threadIdx.x]));
     }
 }
 
-__global__ void gn_finalize_kernel(const float* __restrict__ partial, int chunks, int C, double inv_count,
-                                   const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
-                                   float* __restrict__ scsh) {
+// block = one sample.  src: [B][U][2] fixed-point sums; two sources = GroupNorm over the channel concatenation.
+__global__ void __launch_bounds__(256)
+gn_finalize_kernel(const unsigned long long* __restrict__ src0, int U0, const unsigned long long* __restrict__ src1, int U1,
+                   double inv_count, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                   float* __restrict__ scsh) {
     __shared__ float s_mean[GN_GROUPS], s_rstd[GN_GROUPS];
     const int b = blockIdx.x;
+    const int U = U0 + U1, C = 4 * U;
     if (threadIdx.x < GN_GROUPS) {
-        double s = 0.0, q = 0.0;
-        const float* src = partial + ((int64_t)b * chunks * GN_GROUPS + threadIdx.x) * 2;
-        for (int c = 0; c < chunks; ++c) {
-            s += (double)src[(int64_t)c * GN_GROUPS * 2];
-            q += (double)src[(int64_t)c * GN_GROUPS * 2 + 1];
+        const int upg = U / GN_GROUPS;   // units per group
+        long long sm = 0, q = 0;         // exact integer sums of the fixed-point unit values
+        for (int k = 0; k < upg; ++k) {
+            const int u = threadIdx.x * upg + k;
+            const unsigned long long* p = u < U0 ? src0 + ((int64_t)b * U0 + u) * 2 : src1 + ((int64_t)b * U1 + (u - U0)) * 2;
+            sm += (long long)p[0];
+            q += (long long)p[1];
         }
-        const double mean = s * inv_count;
-        double var = q * inv_count - mean * mean;
+        const double mean = gn_unfix_sum(sm) * inv_count;
+        double var = gn_unfix_sq(q) * inv_count - mean * mean;
         if (var < 0.0) var = 0.0;
         s_mean[threadIdx.x] = (float)mean;
         s_rstd[threadIdx.x] = (float)(1.0 / sqrt(var + (double)eps));
@@ -160,22 +165,25 @@ int gn_threads(int C) {
 
 }  // namespace
 
-int gn_max_chunks() { return GN_MAX_CHUNKS; }
 
-int gn_stats_launch(const ActView* x, float* partial, int chunks, cudaStream_t s) {
+int gn_stats_launch(const ActView* x, unsigned long long* ustats, cudaStream_t s) {
     SNRSE_CHECK_ARG(x->C % 128 == 0 && x->C <= 512, "GroupNorm: C must be 128/256/384/512 (got %d)", x->C);
-    SNRSE_CHECK_ARG(chunks >= 1 && chunks <= GN_MAX_CHUNKS, "GroupNorm: bad chunk count %d", chunks);
     const int64_t hw = (int64_t)x->H * x->W;
+    int chunks = (int)(hw / 256 < 1 ? 1 : (hw / 256 > GN_MAX_CHUNKS ? GN_MAX_CHUNKS : hw / 256));
+    // the chunking depends on the image size only: a sample's statistics do not depend on its batch
     const int ppc = (int)cdiv64(hw, chunks);
     dim3 grid(chunks, x->B);
-    gn_stats_kernel<<<grid, gn_threads(x->C), 0, s>>>(x->ptr, x->ld, x->C, hw, ppc, partial, chunks);
+    gn_stats_kernel<<<grid, gn_threads(x->C), 0, s>>>(x->ptr, x->ld, x->C, hw, ppc, ustats);
     SNRSE_LAUNCH_CHECK();
     return SNRSE_OK;
 }
 
-int gn_finalize_launch(const float* partial, int chunks, int B, int C, int64_t count_per_group, const float* gamma,
-                       const float* beta, float eps, float* scsh, cudaStream_t s) {
-    gn_finalize_kernel<<<B, 256, 0, s>>>(partial, chunks, C, 1.0 / (double)count_per_group, gamma, beta, eps, scsh);
+int gn_finalize_launch(const unsigned long long* src0, int U0, const unsigned long long* src1, int U1, int B,
+                       int64_t count_per_group, const float* gamma, const float* beta, float eps, float* scsh,
+                       cudaStream_t s) {
+    const int C = 4 * (U0 + U1);
+    SNRSE_CHECK_ARG(C % 128 == 0 && C <= 512 && src0 && (U1 == 0 || src1), "GroupNorm finalize: bad sources");
+    gn_finalize_kernel<<<B, 256, 0, s>>>(src0, U0, src1, U1, 1.0 / (double)count_per_group, gamma, beta, eps, scsh);
     SNRSE_LAUNCH_CHECK();
     return SNRSE_OK;
 }

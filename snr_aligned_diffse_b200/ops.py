@@ -146,6 +146,22 @@ def gn_silu_conv3x3_nhwc(x0, gamma, beta, wt, x1=None, bias=None, tbias=None, re
     return out
 
 
+def conv3x3_nhwc_stats(x0, wt, x1=None, bias=None, tbias=None, res=None, scale=1.0):
+    """conv3x3 on the 2-CTA kernel; also returns the per-unit (4 channels) sums / sums of squares of the result as
+    [B, N/4, 2] float64 (decoded from the kernel's 64-bit fixed-point accumulators) and the raw int64 tensor."""
+    lib = _lib_dev()
+    B, H, W, C0 = x0.shape
+    N = wt.shape[0]
+    out = torch.empty(B, H, W, N, dtype=torch.bfloat16, device=x0.device)
+    ust = torch.empty(B, N // 4, 2, dtype=torch.int64, device=x0.device)
+    _lib.check(lib.snrse_conv3x3_nhwc_stats(_lib.ptr(x0), C0, _lib.ptr(x1), 0 if x1 is None else x1.shape[-1],
+                                            _lib.ptr(wt), N, _lib.ptr(bias), _lib.ptr(tbias),
+                                            0 if tbias is None else tbias.shape[-1], _lib.ptr(res), scale, _lib.ptr(out),
+                                            B, H, W, _lib.ptr(ust), _lib.stream_ptr()), "conv3x3_stats")
+    dec = ust.double() * torch.tensor([2.0 ** -30, 2.0 ** -24], dtype=torch.float64, device=x0.device)
+    return out, dec, ust
+
+
 def fir_nhwc(x, up):
     lib = _lib_dev()
     B, H, W, C = x.shape

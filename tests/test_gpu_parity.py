@@ -259,6 +259,37 @@ def test_gn_silu_conv3x3_fused_equals_unfused(ops, case):
     assert (err <= 2 ** -6 * ref.abs() + 3e-2 * ref.abs().mean()).all(), float(err.max())
 
 
+@pytest.mark.parametrize("case", [(2, 32, 64, 128, 128), (3, 40, 20, 128, 256), (16, 64, 64, 256, 256), (1, 24, 12, 256, 128),
+                                  (5, 72, 20, 128, 128)])
+def test_conv_epilogue_groupnorm_partials(ops, case):
+    """The 2-CTA kernel's epilogue accumulates per-unit sums / sums of squares of its (pre-rounding fp32) result in
+    64-bit fixed point; they must match the sums over the stored bf16 tensor up to the bf16 rounding of the elements,
+    with ragged tiles, an odd tile count (all-padding peer tile) and several images per CTA."""
+    B, H, W, Ci, Co = case
+    g = torch.Generator().manual_seed(sum(case))
+    x = torch.randn(B, Ci, H, W, generator=g).to(torch.bfloat16)
+    w = (torch.randn(Co, Ci, 3, 3, generator=g) / math.sqrt(9 * Ci)).to(torch.bfloat16)
+    bias = torch.randn(Co, generator=g) * 0.3
+    res = torch.randn(B, Co, H, W, generator=g).to(torch.bfloat16)
+    out, st, raw = ops.conv3x3_nhwc_stats(_nhwc(x).to(DEV), _pack_w3(w).to(DEV), bias=bias.to(DEV),
+                                          res=_nhwc(res).to(DEV), scale=0.7)
+    # integer accumulation: identical bits on a second run, and for a sample processed alone
+    _, _, raw2 = ops.conv3x3_nhwc_stats(_nhwc(x).to(DEV), _pack_w3(w).to(DEV), bias=bias.to(DEV), res=_nhwc(res).to(DEV),
+                                        scale=0.7)
+    _, _, raw1 = ops.conv3x3_nhwc_stats(_nhwc(x[-1:]).to(DEV), _pack_w3(w).to(DEV), bias=bias.to(DEV),
+                                        res=_nhwc(res[-1:]).to(DEV), scale=0.7)
+    assert torch.equal(raw, raw2) and torch.equal(raw[-1:], raw1)
+    plain = ops.conv_nhwc(_nhwc(x).to(DEV), _pack_w3(w).to(DEV), 9, bias=bias.to(DEV), res=_nhwc(res).to(DEV), scale=0.7)
+    assert torch.equal(out, plain)
+    o = out.double().cpu().reshape(B, H * W, Co // 4, 4)
+    want_s, want_q = o.sum((1, 3)), (o * o).sum((1, 3))
+    st = st.cpu()
+    n = H * W * 4
+    assert st.shape == (B, Co // 4, 2) and torch.isfinite(st).all()
+    assert ((st[..., 0] - want_s).abs() <= 2 ** -8 * math.sqrt(n) * 2.0 + 2 ** -9 * want_s.abs()).all()
+    assert ((st[..., 1] - want_q).abs() <= 2 ** -7 * want_q).all()
+
+
 @pytest.mark.parametrize("C,H,W", [(128, 32, 64), (256, 16, 16), (384, 8, 12), (512, 4, 1), (128, 256, 64)])
 @pytest.mark.parametrize("silu", [True, False])
 def test_groupnorm(ops, C, H, W, silu):

@@ -51,6 +51,8 @@ def main():
         def run(impl):
             if impl == 5:   # GroupNorm statistics + convolution normalising its operand in flight (timed together)
                 return ops.gn_silu_conv3x3_nhwc(x, gamma, beta, wt, x1=x1, bias=bias)
+            if impl == 6:   # 2-CTA kernel with GroupNorm partial sums in the epilogue (includes the host-side reduction)
+                return ops.conv3x3_nhwc_stats(x, wt, x1=x1, bias=bias)[0]
             return ops.conv_nhwc(x, wt, 9, x1=x1, bias=bias, impl=impl)
 
         for impl in impls:
@@ -64,7 +66,7 @@ def main():
             e1.record()
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / args.iters
-            if impl in (0, 3, 5) and args.debug:
+            if impl in (0, 3, 5, 6) and args.debug:
                 from snr_aligned_diffse_b200 import _lib
                 dbg = torch.zeros(148 * 8, dtype=torch.int64, device="cuda")
                 _lib.load().snrse_conv_halo_set_debug(_lib.ptr(dbg))
