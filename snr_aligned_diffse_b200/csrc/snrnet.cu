@@ -147,11 +147,11 @@ struct ConvtW {
 __global__ void __launch_bounds__(256)
 snr_convt_kernel(const float* __restrict__ a2, ConvtW cw, float* __restrict__ feats, int64_t ncl) {
     __shared__ __align__(16) float sx[8][32][8];     // [cluster][r][frame]      8 KB
-    __shared__ float sw[32 * 8 * 32];                // [r][dt][co]           <= 32 KB
+    __shared__ __align__(16) float sw[32 * 8 * 32];  // [r][dt][co]           <= 32 KB
     const int ki = blockIdx.y, k = 1 << ki, nout = 9 - k;
     const int64_t nc0 = (int64_t)blockIdx.x * 8;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const float* wg = cw.w[ki];                      // [co][r (2048)][dt (k)]
+    const float* wg = cw.w[ki];                      // packed [r (2048)][dt (k)][co (32)]
     float acc[8];
 #pragma unroll
     for (int t = 0; t < 8; ++t) acc[t] = 0.f;
@@ -162,11 +162,11 @@ snr_convt_kernel(const float* __restrict__ a2, ConvtW cw, float* __restrict__ fe
             const int64_t nc = nc0 + cl;
             sx[cl][rr][t] = nc < ncl ? a2[nc * 16384 + (int64_t)(r0 + rr) * 8 + t] : 0.f;
         }
-        // weights: lane = output channel, so the transposing shared-memory store is conflict-free; every channel's
-        // 32*k floats of this chunk are contiguous in global memory (sectors fully used across the loop)
-        for (int i = threadIdx.x; i < 32 * 32 * k; i += 256) {
-            const int co = i & 31, rem = i >> 5;             // rem = rr*k + dt
-            sw[rem * 32 + co] = __ldg(wg + ((int64_t)co * 2048 + r0) * k + rem);
+        // weights are pre-packed [r][dt][co]: the 32*k*32 floats of this chunk are one contiguous block
+        {
+            const float4* src = reinterpret_cast<const float4*>(wg + (int64_t)r0 * k * 32);
+            float4* dst = reinterpret_cast<float4*>(sw);
+            for (int i = threadIdx.x; i < 8 * 32 * k; i += 256) dst[i] = __ldg(src + i);
         }
         __syncthreads();
         for (int rr = 0; rr < 32; ++rr) {
@@ -313,7 +313,8 @@ int snrse_snrnet_param_info(int i, char* name, int name_cap, int64_t* offset, in
     memcpy(name, kParams[i].name, n + 1);
     *offset = param_offset(i);
     *numel = kParams[i].numel;
-    *transform = 0;
+    // transform 1: [co][ci][f][dt] is stored as [r = ci*64 + f][dt][co] (co fastest): the layout snr_convt_kernel stages
+    *transform = (i >= 4 && i <= 10 && (i % 2) == 0) ? 1 : 0;
     return SNRSE_OK;
 }
 

@@ -202,7 +202,7 @@ class SNRNetEngine:
             _lib.check(self.lib.snrse_snrnet_param_info(i, name, 256, byref(off), byref(numel), byref(tr)), "snrnet_param_info")
             dims, nd = (c_int64 * 4)(), c_int()
             _lib.check(self.lib.snrse_snrnet_param_shape(i, dims, byref(nd)), "snrnet_param_shape")
-            out.append(dict(name=name.value.decode(), offset=off.value, numel=numel.value,
+            out.append(dict(name=name.value.decode(), offset=off.value, numel=numel.value, transform=tr.value,
                             shape=tuple(int(dims[j]) for j in range(nd.value))))
         return out
 
@@ -214,7 +214,11 @@ class SNRNetEngine:
         blob = torch.zeros(int(self.lib.snrse_snrnet_weight_bytes()), dtype=torch.uint8)
         f32 = blob.view(torch.float32)
         for p in self.param_table():
-            w = sd[p["name"]].detach().to("cpu", torch.float32).reshape(-1)
+            w = sd[p["name"]].detach().to("cpu", torch.float32)
+            if p["transform"] == 1:   # (64 x k) convolutions: [co][ci][f][dt] -> [ci*64 + f][dt][co]
+                co, ci, f, k = w.shape
+                w = w.reshape(co, ci * f, k).permute(1, 2, 0).contiguous()
+            w = w.reshape(-1)
             assert w.numel() == p["numel"], p["name"]
             f32[p["offset"] // 4: p["offset"] // 4 + w.numel()].copy_(w)
         self.blob = blob.to(device)
