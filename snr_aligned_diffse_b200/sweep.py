@@ -1,0 +1,88 @@
+"""Multi-utterance / multi-GPU enhancement driver (BASELINE configs 3-5).
+
+The reference enhances one utterance per `ScoreModel.enhance` call (B/eval.py:119-132).  Utterances are
+independent (per-utterance normalisation, per-sample GroupNorm / attention), so a list is
+  1. partitioned over ranks by LPT on padded frames (`shard.lpt_shards`),
+  2. grouped into equal-Tpad batches on every rank (`shard.bucket_batches`),
+  3. enhanced batch by batch with `ScoreModel.enhance_batch` (ragged lengths inside a batch),
+with NO collective on the data path.  Only the per-utterance metrics (id, samples, checksum) and the
+rank timings are gathered at the end (`torch.distributed`: NCCL on GPUs, gloo in the CPU tests).
+"""
+import time
+
+import torch
+
+from .shard import HOP, bucket_batches, lpt_shards
+
+
+def pack_batch(waves, idx, tpad):
+    """Zero-padded batch [len(idx), 128*tpad - 1] + int32 lengths for utterances `idx` of one Tpad bucket.
+    The buffer length is the longest waveform with `tpad` padded frames (1 + L//128 <= tpad), so it depends on the
+    bucket only and every batch of a bucket has the same shape."""
+    lbuf = HOP * tpad - 1
+    y = torch.zeros(len(idx), lbuf, dtype=torch.float32)
+    lens = torch.empty(len(idx), dtype=torch.int32)
+    for r, i in enumerate(idx):
+        w = waves[i].reshape(-1)
+        y[r, :w.numel()] = w
+        lens[r] = w.numel()
+    return y, lens
+
+
+def enhance_sweep(enhance_fn, waves, rank=0, world=1, max_batch=16, device=None, keep_audio=False):
+    """Enhance the utterances `waves` (list of 1-D float tensors) this rank owns.
+
+    enhance_fn(y [B, L] , lengths [B] int32) -> enhanced [B, L] (e.g. `lambda y, n: model.enhance_batch(y, lengths=n)`).
+    Returns dict(ids, samples, checksum, seconds, batches, audio) for this rank's shard."""
+    lengths = [int(w.numel()) for w in waves]
+    mine = lpt_shards(lengths, world)[rank]
+    batches = bucket_batches(lengths, mine, max_batch)
+    ids, samples, checks, audio = [], [], [], {}
+    t0 = time.perf_counter()
+    for tpad, idx in batches:
+        y, lens = pack_batch(waves, idx, tpad)
+        if device is not None:
+            y, lens = y.to(device, non_blocking=True), lens.to(device, non_blocking=True)
+        out = enhance_fn(y, lens)
+        pos = torch.arange(out.shape[1], device=out.device)[None, :]
+        valid = pos < lens.to(out.device)[:, None].to(pos.dtype)
+        cs = (out.double() * valid).sum(1)            # per-utterance checksum over the valid samples only
+        for r, i in enumerate(idx):
+            ids.append(i)
+            samples.append(lengths[i])
+        checks.append(cs)
+        if keep_audio:
+            for r, i in enumerate(idx):
+                audio[i] = out[r, :lengths[i]].detach().cpu()
+    if checks and checks[0].is_cuda:
+        torch.cuda.synchronize(checks[0].device)
+    seconds = time.perf_counter() - t0
+    checksum = torch.cat(checks).cpu().tolist() if checks else []
+    return dict(ids=ids, samples=samples, checksum=checksum, seconds=seconds, batches=len(batches), audio=audio)
+
+
+def gather_metrics(local, world=1):
+    """All ranks' (id, samples, checksum) rows sorted by id + the slowest rank's wall time (the job time).
+    The only communication of the sweep (a few KB)."""
+    rows = torch.tensor([[float(i), float(n), float(c)] for i, n, c in zip(local["ids"], local["samples"], local["checksum"])],
+                        dtype=torch.float64).reshape(-1, 3)
+    sec = torch.tensor([local["seconds"]], dtype=torch.float64)
+    if world > 1:
+        import torch.distributed as dist
+        dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+        n = torch.tensor([rows.shape[0]], dtype=torch.int64, device=dev)
+        counts = [torch.zeros_like(n) for _ in range(world)]
+        dist.all_gather(counts, n)
+        cap = int(max(int(c.item()) for c in counts))
+        pad = torch.zeros(cap, 3, dtype=torch.float64, device=dev)
+        pad[:rows.shape[0]] = rows.to(dev)
+        parts = [torch.zeros_like(pad) for _ in range(world)]
+        dist.all_gather(parts, pad)
+        rows = torch.cat([p[:int(c.item())].cpu() for p, c in zip(parts, counts)])
+        sec = sec.to(dev)
+        dist.all_reduce(sec, op=dist.ReduceOp.MAX)
+        sec = sec.cpu()
+    order = torch.argsort(rows[:, 0])
+    rows = rows[order]
+    return dict(ids=rows[:, 0].long().tolist(), samples=rows[:, 1].long().tolist(), checksum=rows[:, 2].tolist(),
+                job_seconds=float(sec.item()))

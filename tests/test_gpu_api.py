@@ -156,3 +156,35 @@ def test_cuda_graph_replay_is_bit_identical(v3):
         s.synchronize()
     assert torch.equal(first, eager)
     assert not torch.equal(out, first) and torch.isfinite(out).all()
+
+
+def test_sweep_matches_single_utterance_calls(v3, sd):
+    """sweep.enhance_sweep (LPT shard + equal-Tpad batches + ragged lengths) returns, for every utterance, exactly
+    what a call with that utterance alone returns: results do not depend on batching or on the rank count."""
+    from snr_aligned_diffse_b200.sweep import enhance_sweep
+    g = torch.Generator().manual_seed(11)
+    lens = [5000, 9000, 8100, 16500, 8000, 5100, 23000]
+    waves = [torch.randn(n, generator=g) * 0.05 + 0.1 * torch.sin(torch.arange(n) * 0.03) for n in lens]
+
+    def fn(y, n):
+        # explicit, per-utterance noise so that batches and single calls see the same draw
+        tpad = (y.shape[1] + 1) // 128
+        Z = torch.stack([torch.view_as_complex(torch.randn(1, 256, tpad, 2, generator=torch.Generator().manual_seed(int(k)))
+                                               * 0.5 ** 0.5) for k in n.tolist()])
+        return v3.enhance_batch(y, lengths=n, oracle=True, noise_over_clean=[0.3] * y.shape[0], noise=Z)
+
+    merged = {}
+    for world in (1, 2):
+        for rank in range(world):
+            r = enhance_sweep(fn, waves, rank=rank, world=world, max_batch=3, device="cuda", keep_audio=True)
+            for i, a in r["audio"].items():
+                if i in merged:
+                    assert torch.equal(merged[i], a), i          # same bits whatever the sharding
+                merged[i] = a
+    assert sorted(merged) == list(range(len(lens)))
+    for i, w in enumerate(waves):
+        tpad = 64 * (-(-(1 + lens[i] // 128) // 64))
+        y = torch.zeros(1, 128 * tpad - 1)
+        y[0, :lens[i]] = w
+        alone = fn(y.cuda(), torch.tensor([lens[i]], dtype=torch.int32, device="cuda"))[0, :lens[i]].cpu()
+        assert torch.equal(alone, merged[i]), i

@@ -1,0 +1,86 @@
+#!/usr/bin/env python
+"""BASELINE.json configs 3-5 on 1..8 GPUs (one process per GPU under torchrun, or a single process):
+
+  --workload vbd    824 synthetic VoiceBank-DEMAND-test-shaped utterances (1.5-10 s), sharded by
+                    LPT over the ranks, equal-Tpad batches of <= 16, SNR estimator in the loop (config 4 with
+                    --fixed-snr 0.17783 / 0.31623 / 0.56234)
+  --workload long   60 s utterances (config 5): --count per rank, batch 1
+
+Prints one JSON line on rank 0: whole-job enhanced audio-seconds per wall-second (slowest rank).  No data-path
+collective; torch.distributed only gathers the per-utterance table and the timings.
+    python tools/sweep_bench.py --workload vbd
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/sweep_bench.py --workload vbd
+"""
+import argparse
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+from snr_aligned_diffse_b200.shard import synthetic_lengths  # noqa: E402
+from snr_aligned_diffse_b200.sweep import enhance_sweep, gather_metrics  # noqa: E402
+
+
+def synth_wave(length, seed):
+    g = torch.Generator().manual_seed(seed)
+    t = torch.arange(length) / bench.SR
+    f0 = 100.0 + (seed % 37) * 5.0
+    speech = sum(torch.sin(2 * torch.pi * f0 * (k + 1) * t + k) / (k + 1) for k in range(5))
+    env = 0.5 + 0.5 * torch.sin(2 * torch.pi * (1.5 + 0.01 * (seed % 50)) * t)
+    return (0.1 * speech * env + (0.01 + 0.0005 * (seed % 40)) * torch.randn(length, generator=g)).float()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--workload", default="vbd", choices=["vbd", "long"])
+    ap.add_argument("--count", type=int, default=0, help="utterances (vbd: total, default 824; long: per rank, default 2)")
+    ap.add_argument("--fixed-snr", type=float, default=bench.FIXED_SNR)
+    ap.add_argument("--max-batch", type=int, default=16)
+    ap.add_argument("--repeat", type=int, default=2, help="passes over the list; the last one is timed")
+    args = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    bench.FIXED_SNR = args.fixed_snr
+    model, est = bench.build_models(dev)
+    if args.workload == "vbd":
+        n = args.count or 824
+        lengths = synthetic_lengths(n, seed=0)
+        max_batch = args.max_batch
+    else:
+        n = (args.count or 2) * world
+        lengths = [60 * bench.SR] * n
+        max_batch = 1
+    waves = [synth_wave(int(l), seed=i) for i, l in enumerate(lengths)]
+    fn = lambda y, lens: model.enhance_batch(y, lengths=lens, oracle=False)  # noqa: E731
+    res = None
+    for _ in range(max(1, args.repeat)):       # first pass: plans, workspaces, func attributes for every bucket shape
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        res = enhance_sweep(fn, waves, rank=rank, world=world, max_batch=max_batch, device=dev)
+    allm = gather_metrics(res, world)
+    if rank == 0:
+        audio_s = sum(allm["samples"]) / bench.SR
+        ok = all(c == c for c in allm["checksum"])            # no NaN anywhere
+        print(json.dumps(dict(metric=bench.METRIC, workload=args.workload, value=audio_s / allm["job_seconds"], unit=bench.UNIT,
+                              n_gpus=world, utterances=len(allm["ids"]), audio_seconds=round(audio_s, 1),
+                              job_seconds=round(allm["job_seconds"], 4), batches_rank0=res["batches"],
+                              fixed_snr=args.fixed_snr, max_batch=max_batch, finite=ok, mode="eager launches, no CUDA graph",
+                              scaling="strong" if args.workload == "vbd" else "weak")), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
