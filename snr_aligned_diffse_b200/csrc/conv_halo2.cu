@@ -54,6 +54,8 @@ struct Halo2Args {
     int acc_bufs;                  // 1 or 2 TMEM accumulator sets
     int stg_bufs;                  // 1 or 2 staging tiles per epilogue warp
     int has_res;
+    float4* out4;                  // N == 16 only: fp32 4-channel output [B,H,W,4] = acc[:, 0:4] + bias (+ addend4)
+    const float4* addend4;
     unsigned long long* ustats;    // null, or GroupNorm sums of the result, accumulated: [B][N/4][2] fixed point (gn_fixed.cuh)
     const float* scsh;             // null, or GroupNorm scale/shift [B][2][norm_c] applied (+SiLU) to operand 0 in shared memory
     int norm_c;
@@ -415,6 +417,33 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
             const int h0 = (rem / g.tiles_w) * SUB_ROWS * g.sub, w0 = (rem % g.tiles_w) * TW;
             const uint32_t buf = g.acc_bufs == 2 ? (itt & 1u) : 0u;
             const uint32_t use = g.acc_bufs == 2 ? (itt >> 1) : itt;
+            if (g.out4) {
+                // Thin output convolution (C -> 4, the pyramid heads of ncsnpp.py:350-366): N = 16 accumulator columns
+                // of which 4 are real; fp32 result + bias (+ the up-sampled pyramid) written straight from registers.
+                // Column half h of the warp grid takes sub-tile h.
+                ptx::mbar_wait(ptx::smem_u32(&acc_full[buf]), use & 1u);
+                ptx::tc_fence_after();
+                if (half < g.sub) {
+                    const int hh = h0 + SUB_ROWS * half + 4 * quarter + (lane >> 3), ww = w0 + (lane & 7);
+                    uint32_t v[4];
+                    ptx::tmem_ld_32x32_x4(tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * acc_cols + (uint32_t)(half * g.N), v);
+                    ptx::tmem_ld_wait();
+                    if (b < g.B && hh < g.H && ww < g.W) {
+                        const int64_t pix = ((int64_t)b * g.H + hh) * g.W + ww;
+                        float4 r = make_float4(__uint_as_float(v[0]) + __ldg(g.bias), __uint_as_float(v[1]) + __ldg(g.bias + 1),
+                                               __uint_as_float(v[2]) + __ldg(g.bias + 2), __uint_as_float(v[3]) + __ldg(g.bias + 3));
+                        if (g.addend4) {
+                            const float4 ad = __ldg(g.addend4 + pix);
+                            r.x += ad.x; r.y += ad.y; r.z += ad.z; r.w += ad.w;
+                        }
+                        g.out4[pix] = r;
+                    }
+                }
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive_remote(ptx::mapa_rank0(ptx::smem_u32(&acc_empty[buf])));
+                continue;
+            }
             if (b != last_b) {   // new image: refresh this warp's slice of the per-channel additive term
                 last_b = b;
                 const int bb = b < g.B ? b : g.B - 1;
@@ -609,6 +638,45 @@ int conv_halo2_make_plan(ConvHaloPlan* p, const ActView* a0, const ActView* a1, 
     return SNRSE_OK;
 }
 
+// Thin output convolution on the same kernel: 3x3, C -> 4 (weights packed as 16 rows, rows 4..15 zero), optional
+// GroupNorm+SiLU of the operand in flight, fp32 output [B,H,W,4] = conv + bias (+ addend4).
+int conv_halo2_make_plan_out4(ConvHaloPlan* p, const ActView* a0, const bf16* wt16, const float* bias4, const float* addend4,
+                              float* out4, const float* scsh) {
+    SNRSE_CHECK_ARG(a0->W >= TW && a0->H >= 8 && a0->C % 64 == 0 && a0->ld % 8 == 0, "conv_halo2 out4: shape not eligible");
+    SNRSE_CHECK_ARG(bias4 && out4, "conv_halo2 out4: null pointer");
+    if (g_num_sms2 == 0) {
+        int dev = 0;
+        SNRSE_CUDA(cudaGetDevice(&dev));
+        SNRSE_CUDA(cudaDeviceGetAttribute(&g_num_sms2, cudaDevAttrMultiProcessorCount, dev));
+    }
+    memset(p, 0, sizeof(*p));
+    const int tiles_w = cdiv(a0->W, TW);
+    int sub = 2;
+    if (a0->H < 2 * SUB_ROWS || (int64_t)a0->B * cdiv(a0->H, 2 * SUB_ROWS) * tiles_w < g_num_sms2) sub = 1;
+    p->sub = sub;
+    p->c0_chunks = a0->C / 64;
+    p->c1_chunks = 0;
+    p->B = a0->B; p->H = a0->H; p->W = a0->W;
+    p->tiles_h = cdiv(a0->H, SUB_ROWS * sub);
+    p->tiles_w = tiles_w;
+    p->n_tiles = a0->B * p->tiles_h * p->tiles_w;
+    p->N = 16;
+    p->acc_bufs = 2;
+    const int a_bytes = (int)halo_stage_bytes(sub);
+    p->na = 3; p->nb = MAX_B; p->stg_bufs = 1;
+    p->smem_bytes = p->na * a_bytes + p->nb * 1024 + 1024;
+    const int n_ctiles = (p->n_tiles + 1) / 2, max_clusters = g_num_sms2 / 2;
+    p->grid = 2 * (n_ctiles < max_clusters ? n_ctiles : max_clusters);
+    p->bias = bias4; p->scale = 1.0f;
+    p->scsh = scsh;
+    p->out4 = out4; p->addend4 = addend4;
+    SNRSE_TRY(tma_make_act_map(&p->mapA0, a0->ptr, a0->C, a0->W, a0->H, a0->B, a0->ld, 64, HALO_W, SUB_ROWS * sub + 2));
+    p->mapA1 = p->mapA0; p->mapOut = p->mapA0; p->mapRes = p->mapA0;
+    const int64_t ktot = 64 * (int64_t)(9 * p->c0_chunks);
+    SNRSE_TRY(tma_make_wt_map(&p->mapB, wt16, ktot, 16, 1, ktot * 16, 64, 8));
+    return SNRSE_OK;
+}
+
 int conv_halo2_launch(const ConvHaloPlan* p, cudaStream_t s) {
     static bool attr_set = false;
     if (!attr_set) {
@@ -625,6 +693,7 @@ int conv_halo2_launch(const ConvHaloPlan* p, cudaStream_t s) {
     g.scale = p->scale;
     g.scsh = p->scsh; g.norm_c = p->c0_chunks * 64;
     g.ustats = p->ustats;
+    g.out4 = reinterpret_cast<float4*>(p->out4); g.addend4 = reinterpret_cast<const float4*>(p->addend4);
     g.dbg = g_halo_dbg_shared;
     conv_halo2_kernel<<<p->grid, HALO_THREADS + (p->scsh ? NORM_THREADS : 0), p->smem_bytes, s>>>(p->mapA0, p->mapA1, p->mapB, p->mapOut, p->mapRes, g);
     SNRSE_LAUNCH_CHECK();

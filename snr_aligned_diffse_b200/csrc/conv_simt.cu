@@ -150,25 +150,34 @@ conv_out4_kernel(const bf16* __restrict__ a, int ld, int C, const float* __restr
 }
 
 // ------------------------------------------------------------------------------------------------
-// combine4: out = h + W(Cx4) p4 + bias, thread = (pixel, 8 channels)
+// combine4: out = h + W(Cx4) p4 + bias.  Thread = (8-channel chunk, pixel slot); its 32 weights + 8 biases stay in
+// registers while it walks pixels, so the pass is bound by reading h / writing out (HBM), not by weight loads.
 // ------------------------------------------------------------------------------------------------
+constexpr int CB_PIX = 32;   // pixels per thread
 __global__ void __launch_bounds__(256)
 combine4_kernel(const float4* __restrict__ p4, const bf16* __restrict__ h, int h_ld, const float4* __restrict__ w,
                 const float* __restrict__ bias, bf16* out, int out_ld, int C, int64_t npix) {
-    const int tpp = C / 8;
-    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= npix * tpp) return;
-    const int64_t pix = idx / tpp;
-    const int c0 = (int)(idx % tpp) * 8;
-    const float4 p = p4[pix];
-    float f[8];
-    unpack8(__ldg(reinterpret_cast<const uint4*>(h + pix * h_ld + c0)), f);
+    const int tpp = C / 8, slots = blockDim.x / tpp;
+    const int c0 = (threadIdx.x % tpp) * 8, slot = threadIdx.x / tpp;
+    float wr[8][4], bs[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         const float4 wv = __ldg(w + c0 + j);
-        f[j] += bias[c0 + j] + wv.x * p.x + wv.y * p.y + wv.z * p.z + wv.w * p.w;
+        wr[j][0] = wv.x; wr[j][1] = wv.y; wr[j][2] = wv.z; wr[j][3] = wv.w;
+        bs[j] = __ldg(bias + c0 + j);
     }
-    *reinterpret_cast<uint4*>(out + pix * out_ld + c0) = pack8(f);
+    const int64_t p0 = (int64_t)blockIdx.x * slots * CB_PIX + slot;
+#pragma unroll 4
+    for (int k = 0; k < CB_PIX; ++k) {
+        const int64_t pix = p0 + (int64_t)k * slots;
+        if (pix >= npix) break;
+        const float4 p = __ldg(p4 + pix);
+        float f[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(h + pix * h_ld + c0)), f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] += bs[j] + wr[j][0] * p.x + wr[j][1] * p.y + wr[j][2] * p.z + wr[j][3] * p.w;
+        *reinterpret_cast<uint4*>(out + pix * out_ld + c0) = pack8(f);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -261,8 +270,8 @@ int conv_out4_launch(const ActView* a, const float* w, const float* bias, const 
 int combine4_launch(const float* p4, const ActView* h, const float* w, const float* bias, const ActView* out,
                     cudaStream_t s) {
     const int64_t npix = (int64_t)h->B * h->H * h->W;
-    const int64_t total = npix * (h->C / 8);
-    combine4_kernel<<<(unsigned)cdiv64(total, 256), 256, 0, s>>>(reinterpret_cast<const float4*>(p4), h->ptr, h->ld,
+    const int tpp = h->C / 8, nthr = tpp * (256 / tpp), slots = nthr / tpp;
+    combine4_kernel<<<(unsigned)cdiv64(npix, (int64_t)slots * CB_PIX), nthr, 0, s>>>(reinterpret_cast<const float4*>(p4), h->ptr, h->ld,
                                                                  reinterpret_cast<const float4*>(w), bias, out->ptr,
                                                                  out->ld, h->C, npix);
     SNRSE_LAUNCH_CHECK();

@@ -252,6 +252,10 @@ int build_topology(Engine& e, int image_size) {
                 r.o[1] = e.alloc(r.cout * 4);
                 e.add_param(p + "weight", {r.cout, r.cin, 3, 3}, PK_CONV3_TAP_F32, r.o[0]);
                 e.add_param(p + "bias", {r.cout}, PK_RAW_F32, r.o[1]);
+                if (r.kind == M_CONV_OUT) {   // tensor-core copy: bf16 K-major, 16 rows of which the first 4 are real
+                    r.o[2] = e.alloc((int64_t)16 * 9 * r.cin * 2);
+                    e.add_param(p + "weight", {r.cout, r.cin, 3, 3}, PK_CONV3_K_BF16, r.o[2], 9 * (int64_t)r.cin, 0);
+                }
                 break;
             case M_GN:
                 r.o[0] = e.alloc(r.cin * 4);
@@ -650,13 +654,19 @@ int record_plan(Plan& P) {
         }
         {
             const Mod mg = e.mods[mi], mc = e.mods[mi + 1];
-            const int a = rec_gn(P, h, mg.o[0], mg.o[1], 1);
+            // GroupNorm + SiLU + conv3x3 C -> 4, added to the FIR-upsampled pyramid (ncsnpp.py:348-366): on the 2-CTA
+            // tensor-core kernel with the normalisation in flight when the map is large enough, CUDA cores otherwise
+            const bool tc = fusable(P, h, 128);
+            int a = h;
+            if (tc) rec_gn_finalize(P, h, mg.o[0], mg.o[1]);
+            else a = rec_gn(P, h, mg.o[0], mg.o[1], 1);
             const LT th = P.tens[h];
             const int np = P.new_t(th.B, th.H, th.W, 4, 4);
             int up = -1;
             if (pyr >= 0) up = P.new_t(th.B, th.H, th.W, 4, 4);
             const int prev = pyr;
             P.use(a); P.use(np);
+            if (tc) P.use(P.t_scsh);
             if (prev >= 0) { P.use(prev); P.use(up); }
             P.step++;
             P.builders.push_back([=](Plan& p) -> int {
@@ -666,6 +676,15 @@ int record_plan(Plan& P) {
                 float* upp = up >= 0 ? p.fptr(up) : nullptr;
                 const float* pv = prev >= 0 ? p.fptr(prev) : nullptr;
                 const double px = (double)va.B * va.H * va.W;
+                if (tc) {
+                    ConvHaloPlan hp;
+                    SNRSE_TRY(conv_halo2_make_plan_out4(&hp, &va, e.wb(mc.o[2]), e.wf(mc.o[1]), upp, dst, p.fptr(p.t_scsh)));
+                    p.add(LK_THIN, 2.0 * px * 36 * va.C, px * (2.0 * va.C + 16 + (pv ? 20 : 0)), [=](cudaStream_t s) {
+                        if (pv) SNRSE_TRY(fir_up2_f4_launch(pv, upp, va.B, va.H / 2, va.W / 2, s));
+                        return conv_halo2_launch(&hp, s);
+                    });
+                    return SNRSE_OK;
+                }
                 p.add(LK_THIN, 2.0 * px * 36 * va.C, px * (2.0 * va.C + 16 + (pv ? 20 : 0)), [=, &e](cudaStream_t s) {
                     if (pv) SNRSE_TRY(fir_up2_f4_launch(pv, upp, va.B, va.H / 2, va.W / 2, s));
                     return conv_out4_launch(&va, e.wf(mc.o[0]), e.wf(mc.o[1]), upp, dst, s);

@@ -60,6 +60,8 @@ struct ConvHaloPlan {
     int out_ld;
     const float* scsh;   // 2-CTA kernel only
     unsigned long long* ustats;   // 2-CTA kernel only
+    float* out4;                  // 2-CTA kernel, thin C -> 4 output convolution only
+    const float* addend4;
 };
 bool conv_halo_eligible(const ActView* a0, int taps0, int n_rows);
 int conv_halo_make_plan(ConvHaloPlan* p, const ActView* a0, const ActView* a1, const bf16* wt, int n_rows,
@@ -76,6 +78,11 @@ int conv_halo2_make_plan(ConvHaloPlan* p, const ActView* a0, const ActView* a1, 
 // ustats (nullable): the epilogue also accumulates the GroupNorm sums of the result into [B][N/4][2] (zeroed by the
 // caller; gn_finalize_launch source format), so the following GroupNorm needs no pass over the tensor.
 int conv_halo2_launch(const ConvHaloPlan* p, cudaStream_t s);
+
+// Thin 3x3 output convolution C -> 4 on the 2-CTA kernel (N = 16, weights [16][9*C] bf16 with rows 4..15 zero), fp32
+// result [B,H,W,4] = conv + bias4 (+ addend4); scsh as above.  Needs W >= 8, H >= 8.
+int conv_halo2_make_plan_out4(ConvHaloPlan* p, const ActView* a0, const bf16* wt16, const float* bias4, const float* addend4,
+                              float* out4, const float* scsh);
 
 // ----------------------------------------------------------------------------- conv_simt.cu
 // Reference-grade direct convolution on CUDA cores (debug / cross-check path, fp32 accumulate).
