@@ -27,7 +27,8 @@ enum PackKind {       // how the host packs a reference state-dict tensor into t
     PK_CONV3_K_BF16 = 1,  // [Cout,Cin,3,3] -> bf16 rows [cout][k_off + (r*3+s)*Cin + cin], row pitch row_stride
     PK_CONV1_K_BF16 = 2,  // [Cout,Cin,1,1] -> bf16 rows [cout][k_off + cin]
     PK_NIN_K_BF16 = 3,    // W[in,out]      -> bf16 rows [out][k_off + in]
-    PK_CONV3_TAP_F32 = 4  // [Cout,Cin,3,3] -> fp32 [cout][r][s][cin]
+    PK_CONV3_TAP_F32 = 4, // [Cout,Cin,3,3] -> fp32 [cout][r][s][cin]
+    PK_CONV3_K_BF16_HILO64 = 5  // [Cout,Cin<=4,3,3] -> bf16 rows [cout][(r*3+s)*64 + c], c < 2*Cin: w[cout][c % Cin][r][s]
 };
 
 struct Param {
@@ -252,6 +253,10 @@ int build_topology(Engine& e, int image_size) {
                 r.o[1] = e.alloc(r.cout * 4);
                 e.add_param(p + "weight", {r.cout, r.cin, 3, 3}, PK_CONV3_TAP_F32, r.o[0]);
                 e.add_param(p + "bias", {r.cout}, PK_RAW_F32, r.o[1]);
+                if (r.kind == M_CONV_IN) {    // tensor-core copy for the 64-channel hi/lo operand (pack_input64)
+                    r.o[2] = e.alloc((int64_t)r.cout * 9 * 64 * 2);
+                    e.add_param(p + "weight", {r.cout, r.cin, 3, 3}, PK_CONV3_K_BF16_HILO64, r.o[2], 9 * 64, 0);
+                }
                 if (r.kind == M_CONV_OUT) {   // tensor-core copy: bf16 K-major, 16 rows of which the first 4 are real
                     r.o[2] = e.alloc((int64_t)16 * 9 * r.cin * 2);
                     e.add_param(p + "weight", {r.cout, r.cin, 3, 3}, PK_CONV3_K_BF16, r.o[2], 9 * (int64_t)r.cin, 0);
@@ -556,8 +561,10 @@ int record_plan(Plan& P) {
     P.t_scsh = P.new_t(B, 1, 1, 2 * 512, 4);
     const int persistent[] = {P.t_x4, P.t_tb, P.t_tscr, P.t_stats, P.t_scsh};
     size_t mi = 0;
-    // --- input packing + time embedding
+    // --- input packing + time embedding (+ the bf16 hi/lo operand of the tensor-core input convolution)
+    const int x64 = (P.flags & 2) ? -1 : P.new_t(B, F, T, 64, 2);
     P.use(P.t_x4); P.use(P.t_tb); P.use(P.t_tscr);
+    if (x64 >= 0) P.use(x64);
     P.step++;
     P.builders.push_back([=](Plan& p) -> int {
         Engine& e = *p.eng;
@@ -565,22 +572,29 @@ int record_plan(Plan& P) {
         float* x4 = p.fptr(p.t_x4);
         float* tb = p.fptr(p.t_tb);
         float* scr = p.fptr(p.t_tscr);
+        bf16* x64p = x64 >= 0 ? p.view(x64).ptr : nullptr;
         const int64_t n = (int64_t)p.F * p.T;
         const Mod mf = e.mods[0], m1 = e.mods[1], m2 = e.mods[2];
         unsigned long long* stats0 = p.stat_ptr(0);
         const size_t stats_bytes = (size_t)p.n_stat_entries * p.B * 256 * 8;
-        p.add(LK_HEAD, 0.0, (double)p.B * n * 32, [=, &e](cudaStream_t s) {
+        p.add(LK_HEAD, 0.0, (double)p.B * n * (32 + (x64p ? 128 : 0)), [=, &e](cudaStream_t s) {
             SNRSE_CUDA(cudaMemsetAsync(stats0, 0, stats_bytes, s));   // GroupNorm sums are accumulated with atomics
-            SNRSE_TRY(pack_input_launch(pp->x_ptr, pp->y_ptr, x4, pp->B, n, s));
+            if (x64p) SNRSE_TRY(pack_input64_launch(pp->x_ptr, pp->y_ptr, x4, x64p, pp->B, n, s));
+            else SNRSE_TRY(pack_input_launch(pp->x_ptr, pp->y_ptr, x4, pp->B, n, s));
             return temb_launch(pp->t_ptr, pp->B, e.nf, e.wf(mf.o[0]), e.wf(m1.o[0]), e.wf(m1.o[1]), e.wf(m2.o[0]),
                                e.wf(m2.o[1]), e.wf(e.dense_w_off), e.wf(e.dense_b_off), e.dense_rows, scr, tb, s);
         });
         return SNRSE_OK;
     });
     mi = 3;
-    // --- input conv
+    // --- input conv 4 -> nf (ncsnpp.py:285): tensor cores on the 64-channel hi/lo operand, or fp32 CUDA cores (flag bit1)
     int h = P.new_t(B, F, T, nf, 2);
-    {
+    if (x64 >= 0) {
+        const Mod m = e.mods[mi];
+        rec_gemm(P, x64, 9, -1, m.o[2], nf, m.o[1], -1, -1, 1.0f, h, 0, fusable(P, x64, nf) ? 1 : 0);
+        P.taps[(int)mi] = h;
+        ++mi;
+    } else {
         const Mod m = e.mods[mi];
         const int out = h;
         P.use(P.t_x4); P.use(out);

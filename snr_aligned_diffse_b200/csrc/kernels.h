@@ -131,6 +131,8 @@ int temb_launch(const float* t, int B, int nf, const float* fourier_w, const flo
 // ----------------------------------------------------------------------------- sampler.cu
 // x, y, out: complex64 [B, F*T]; x4: [B,F,T,4] f32 = (re x, im x, re y, im y)
 int pack_input_launch(const float2* x, const float2* y, float* x4, int B, int64_t n, cudaStream_t s);
+// same + x64: [B,F,T,64] bf16 (hi/lo split of the 4 channels in 0..7, zeros above) for the tensor-core input convolution
+int pack_input64_launch(const float2* x, const float2* y, float* x4, bf16* x64, int B, int64_t n, cudaStream_t s);
 // out = alpha_b * xres + beta_b * (Wout * (p4 / t_b) + bout); mode 0: alpha=0,beta=1; 1: sebridge precond; 2: alpha=0,beta=-1
 int final_launch(const float* p4, const float* t, const float* w, const float* bias, const float2* xres, float2* out,
                  int B, int64_t n, int mode, cudaStream_t s);

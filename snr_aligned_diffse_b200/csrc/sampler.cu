@@ -19,6 +19,33 @@ pack_input_kernel(const float2* __restrict__ x, const float2* __restrict__ y, fl
     x4[i] = make_float4(a.x, a.y, b.x, b.y);
 }
 
+// Same, plus the tensor-core operand of the input convolution: NHWC bf16 with 64 channels per pixel, channels 0..3 =
+// bf16(v), 4..7 = bf16(v - bf16(v)) (hi/lo split: the first convolution sees ~16 mantissa bits of the spectrogram,
+// its weights are duplicated over both halves), 8..63 = 0.  Thread = (pixel, 16-byte chunk).
+__global__ void __launch_bounds__(256)
+pack_input64_kernel(const float2* __restrict__ x, const float2* __restrict__ y, float4* __restrict__ x4,
+                    uint4* __restrict__ x64, int64_t total) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t i = idx >> 3;
+    if (i >= total) return;
+    const int chunk = (int)(idx & 7);
+    uint4 o = make_uint4(0, 0, 0, 0);
+    if (chunk == 0) {
+        const float2 a = x[i], b = y[i];
+        x4[i] = make_float4(a.x, a.y, b.x, b.y);
+        const float v[4] = {a.x, a.y, b.x, b.y};
+        float hi[4], lo[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            hi[k] = __bfloat162float(__float2bfloat16(v[k]));
+            lo[k] = v[k] - hi[k];
+        }
+        const float f[8] = {hi[0], hi[1], hi[2], hi[3], lo[0], lo[1], lo[2], lo[3]};
+        o = pack8(f);
+    }
+    x64[idx] = o;
+}
+
 __global__ void __launch_bounds__(256)
 final_kernel(const float4* __restrict__ p4, const float* __restrict__ t, const float* __restrict__ w,
              const float* __restrict__ bias, const float2* __restrict__ xres, float2* __restrict__ out, int64_t n,
@@ -111,6 +138,14 @@ int snr_ratio_launch(const float* g, float* ratio, int B, cudaStream_t s) {
 int pack_input_launch(const float2* x, const float2* y, float* x4, int B, int64_t n, cudaStream_t s) {
     const int64_t total = (int64_t)B * n;
     pack_input_kernel<<<(unsigned)cdiv64(total, 256), 256, 0, s>>>(x, y, reinterpret_cast<float4*>(x4), total);
+    SNRSE_LAUNCH_CHECK();
+    return SNRSE_OK;
+}
+
+int pack_input64_launch(const float2* x, const float2* y, float* x4, bf16* x64, int B, int64_t n, cudaStream_t s) {
+    const int64_t total = (int64_t)B * n;
+    pack_input64_kernel<<<(unsigned)cdiv64(total * 8, 256), 256, 0, s>>>(x, y, reinterpret_cast<float4*>(x4),
+                                                                        reinterpret_cast<uint4*>(x64), total);
     SNRSE_LAUNCH_CHECK();
     return SNRSE_OK;
 }

@@ -11,7 +11,7 @@ import torch
 
 from . import _lib
 
-PK_RAW_F32, PK_CONV3_K_BF16, PK_CONV1_K_BF16, PK_NIN_K_BF16, PK_CONV3_TAP_F32 = range(5)
+PK_RAW_F32, PK_CONV3_K_BF16, PK_CONV1_K_BF16, PK_NIN_K_BF16, PK_CONV3_TAP_F32, PK_CONV3_K_BF16_HILO64 = range(6)
 
 DEFAULT_CONFIG = dict(nf=128, ch_mult=(1, 1, 2, 2, 2, 2, 2), num_res_blocks=2, attn_resolutions=(16,), image_size=256)
 
@@ -97,7 +97,16 @@ class NCSNppEngine:
                 flat = w.permute(0, 2, 3, 1).reshape(-1)
                 f32[off // 4: off // 4 + flat.numel()].copy_(flat)
                 continue
-            if k == PK_CONV3_K_BF16:
+            if k == PK_CONV3_K_BF16_HILO64:
+                # input convolution on the 64-channel hi/lo operand (pack_input64): [cout][tap*64 + c], the Cin
+                # weights repeated for the hi (c < Cin) and lo (Cin <= c < 2 Cin) halves, zero above
+                co, ci = w.shape[0], w.shape[1]
+                rows = torch.zeros(co, 9, 64)
+                taps = w.permute(0, 2, 3, 1).reshape(co, 9, ci)
+                rows[:, :, :ci] = taps
+                rows[:, :, ci:2 * ci] = taps
+                rows = rows.reshape(co, 9 * 64)
+            elif k == PK_CONV3_K_BF16:
                 rows = w.permute(0, 2, 3, 1).reshape(w.shape[0], -1)       # [cout][(r,s,cin)]
             elif k == PK_CONV1_K_BF16:
                 rows = w.reshape(w.shape[0], w.shape[1])                    # [cout][cin]
