@@ -137,8 +137,10 @@ int snrse_groupnorm_nhwc(const void* x, const float* gamma, const float* beta, v
  * op/upfirdn2d.cpp:12-23, op/upfirdn2d_kernel.cu modes 3 and 5) */
 int snrse_fir_nhwc(const void* x, void* out, int B, int H, int W, int C, int up, void* stream);
 int snrse_fir_f4(const float* x, float* out, int B, int H, int W, int up, void* stream);
-/* softmax(q k^T / sqrt(C)) v over n positions (ncsnpp_utils/layerspp.py:84-88); scores: f32 [B][n][n] scratch */
-int snrse_attention_nhwc(const void* q, const void* k, const void* v, float* scores, void* out, int B, int n, int C,
+/* softmax(q k^T / sqrt(C)) v over n positions (ncsnpp_utils/layerspp.py:84-88); workspace:
+ * snrse_attention_workspace_bytes(B, n, C) (fp32 scores, bf16 probabilities, V^T).  Tensor cores when n % 64 == 0. */
+int64_t snrse_attention_workspace_bytes(int B, int n, int C);
+int snrse_attention_nhwc(const void* q, const void* k, const void* v, void* workspace, void* out, int B, int n, int C,
                          void* stream);
 
 /* ---------------------------------------------------------------- SNR estimator ----------------

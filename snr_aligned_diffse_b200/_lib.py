@@ -51,6 +51,7 @@ PROTOTYPES = {
     "snrse_groupnorm_nhwc": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, vp, vp]),
     "snrse_fir_nhwc": (i32, [vp, vp, i32, i32, i32, i32, i32, vp]),
     "snrse_fir_f4": (i32, [vp, vp, i32, i32, i32, i32, vp]),
+    "snrse_attention_workspace_bytes": (i64, [i32, i32, i32]),
     "snrse_attention_nhwc": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, vp]),
     "snrse_snrnet_num_params": (i32, []),
     "snrse_snrnet_param_info": (i32, [i32, c_char_p, i32, POINTER(i64), POINTER(i64), POINTER(i32)]),

@@ -188,7 +188,9 @@ int snrse_fir_f4(const float* x, float* out, int B, int H, int W, int up, void* 
     return up ? fir_up2_f4_launch(x, out, B, H, W, S(stream)) : fir_down2_f4_launch(x, out, B, H, W, S(stream));
 }
 
-int snrse_attention_nhwc(const void* q, const void* k, const void* v, float* scores, void* out, int B, int n, int C,
+int64_t snrse_attention_workspace_bytes(int B, int n, int C) { return attention_workspace_bytes(B, n, C); }
+
+int snrse_attention_nhwc(const void* q, const void* k, const void* v, void* scores, void* out, int B, int n, int C,
                          void* stream) {
     SNRSE_CHECK_ARG(q && k && v && scores && out, "attention: null pointer");
     const ActView vq = mk_view(q, B, 1, n, C, C), vk = mk_view(k, B, 1, n, C, C), vv = mk_view(v, B, 1, n, C, C),

@@ -1,10 +1,13 @@
 // Single-head self-attention core of `AttnBlockpp` (sgmse-bbed/sgmse/backbones/ncsnpp_utils/layerspp.py:84-88):
 //   w = softmax_j( q_i . k_j / sqrt(C) ),  o_i = sum_j w_ij v_j     over all n = H*W positions of one image.
-// q, k, v come from the NIN projections (tcgen05 GEMMs); this file holds the score / softmax / mix
-// kernels.  0.1 % of the network FLOPs, so they run on CUDA cores in fp32:
-//   scores  S = scale * Q K^T        (64x64 tiles, fp32 accumulate)  -> f32 [B, n, n] workspace
-//   softmax rows in place            (one warp per row)
-//   mix     O = S V                  (64x64 tiles)                    -> bf16 view
+// q, k, v come from the NIN projections (tcgen05 GEMMs).  Two paths:
+//  * tensor cores (n % 64 == 0): S = scale * Q K^T and O = P V are batched GEMMs on conv_gemm.cu (operand B = K
+//    resp. V^T of the same image), fp32 scores, fp32 softmax, probabilities rounded to bf16 for the second GEMM.
+//    3076*T^2 FLOP per NFE: 0.1 % of the network at 4 s, 1.1 % at 60 s.
+//  * CUDA cores in fp32 (any n; the 4 x T/64 bottleneck of short inputs, and the cross-check):
+//      scores  S = scale * Q K^T        (64x64 tiles, fp32 accumulate)  -> f32 [B, n, n] workspace
+//      softmax rows in place            (one warp per row)
+//      mix     O = S V                  (64x64 tiles)                    -> bf16 view
 #include "kernels.h"
 
 namespace {
@@ -120,12 +123,74 @@ attn_mix_kernel(const float* __restrict__ S, const bf16* __restrict__ v, int v_l
     }
 }
 
+// row softmax of fp32 scores -> bf16 probabilities (one warp per row)
+__global__ void __launch_bounds__(256)
+attn_softmax_bf16_kernel(const float* __restrict__ S, bf16* __restrict__ P, int n, int64_t rows) {
+    const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float* p = S + row * n;
+    bf16* o = P + row * n;
+    float m = -INFINITY;
+    for (int j = lane; j < n; j += 32) m = fmaxf(m, p[j]);
+    m = warp_max(m);
+    float sum = 0.f;
+    for (int j = lane; j < n; j += 32) sum += __expf(p[j] - m);
+    sum = warp_sum(sum);
+    const float inv = 1.0f / sum;
+    for (int j = lane; j < n; j += 32) o[j] = __float2bfloat16(__expf(p[j] - m) * inv);
+}
+
+// V [B][n][ld] (C channels) -> V^T [B][C][n], 32x32 tiles through shared memory
+__global__ void __launch_bounds__(256)
+attn_transpose_kernel(const bf16* __restrict__ v, int v_ld, int n, int C, bf16* __restrict__ vt) {
+    __shared__ bf16 t[32][33];
+    const int b = blockIdx.z, j0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int r = ty; r < 32; r += 8)
+        if (j0 + r < n && c0 + tx < C) t[r][tx] = v[((int64_t)b * n + j0 + r) * v_ld + c0 + tx];
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8)
+        if (c0 + r < C && j0 + tx < n) vt[((int64_t)b * C + c0 + r) * n + j0 + tx] = t[tx][r];
+}
+
 }  // namespace
 
-int attention_launch(const ActView* q, const ActView* k, const ActView* v, float* scores, const ActView* o,
-                     cudaStream_t s) {
+int64_t attention_workspace_bytes(int B, int n, int C) {
+    const int64_t nn = (int64_t)B * n * n;
+    return nn * 4 + ((nn * 2 + 255) / 256) * 256 + (int64_t)B * C * n * 2 + 512;
+}
+
+int attention_launch(const ActView* q, const ActView* k, const ActView* v, void* workspace, const ActView* o,
+                     cudaStream_t s, int allow_tensor_cores) {
     const int n = q->H * q->W, C = q->C, B = q->B;
     SNRSE_CHECK_ARG(C % TK == 0, "attention: C must be a multiple of %d", TK);
+    float* scores = static_cast<float*>(workspace);
+    if (allow_tensor_cores && n % 64 == 0 && C % 64 == 0 && q->ld % 8 == 0 && k->ld % 8 == 0) {
+        const int64_t nn = (int64_t)B * n * n;
+        bf16* probs = reinterpret_cast<bf16*>(static_cast<uint8_t*>(workspace) + nn * 4);
+        bf16* vt = reinterpret_cast<bf16*>(reinterpret_cast<uint8_t*>(probs) + ((nn * 2 + 255) / 256) * 256);
+        // S[b] = scale * Q[b] K[b]^T : A = Q (tokens x C), B = K (keys x C, row pitch k->ld)
+        ActView qa = *q;
+        qa.H = 1; qa.W = n;
+        ConvGemmPlan g1;
+        SNRSE_TRY(conv_gemm_make_plan_ex(&g1, &qa, 1, nullptr, k->ptr, n, (int64_t)n * k->ld, 1, nullptr, nullptr, 0, nullptr,
+                                         rsqrtf((float)C), scores, n, 1, k->ld));
+        SNRSE_TRY(conv_gemm_launch(&g1, s));
+        const int64_t rows = (int64_t)B * n;
+        attn_softmax_bf16_kernel<<<(unsigned)cdiv64(rows, 8), 256, 0, s>>>(scores, probs, n, rows);
+        SNRSE_LAUNCH_CHECK();
+        dim3 gt(cdiv(C, 32), cdiv(n, 32), B);
+        attn_transpose_kernel<<<gt, 256, 0, s>>>(v->ptr, v->ld, n, C, vt);
+        SNRSE_LAUNCH_CHECK();
+        // O[b] = P[b] V[b] : A = P (tokens x keys), B = V^T (C x keys)
+        ActView pa;
+        pa.ptr = probs; pa.B = B; pa.H = 1; pa.W = n; pa.C = n; pa.ld = n;
+        ConvGemmPlan g2;
+        SNRSE_TRY(conv_gemm_make_plan_ex(&g2, &pa, 1, nullptr, vt, C, (int64_t)C * n, 1, nullptr, nullptr, 0, nullptr, 1.0f,
+                                         o->ptr, o->ld, 0, n));
+        return conv_gemm_launch(&g2, s);
+    }
     dim3 g1(cdiv(n, TS), cdiv(n, TS), B);
     attn_scores_kernel<<<g1, 256, 0, s>>>(q->ptr, q->ld, k->ptr, k->ld, n, C, rsqrtf((float)C), scores);
     SNRSE_LAUNCH_CHECK();

@@ -58,7 +58,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
     __shared__ __align__(8) uint64_t accum_bar;
     __shared__ uint32_t tmem_base_smem;
 
-    const int warp = threadIdx.x >> 5;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // provably warp-uniform (uniform-register descriptors)
     const int lane = threadIdx.x & 31;
 
     // ---- tile coordinates
@@ -98,55 +98,58 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
-    const uint32_t tmem_base = tmem_base_smem;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_base_smem, 0);
 
     if (warp == 0) {
         // =========================== TMA producer ===========================
-        if (lane == 0) {
-            for (int kb = 0; kb < nkb; ++kb) {
-                const int s = kb % g.stages;
-                const uint32_t ph = (uint32_t)(kb / g.stages) & 1u;
-                ptx::mbar_wait(ptx::smem_u32(&empty_bar[s]), ph ^ 1u);
-                const uint32_t fb = ptx::smem_u32(&full_bar[s]);
+        // the whole warp walks the loop (uniform control flow), one elected lane issues
+        const bool elected = ptx::elect_one();
+        for (int kb = 0; kb < nkb; ++kb) {
+            const int s = kb % g.stages;
+            const uint32_t ph = (uint32_t)(kb / g.stages) & 1u;
+            ptx::mbar_wait(ptx::smem_u32(&empty_bar[s]), ph ^ 1u);
+            const uint32_t fb = ptx::smem_u32(&full_bar[s]);
+            const uint32_t sa = smem_base + (uint32_t)s * stage_bytes;
+            const bool seg0 = kb < nkb0;
+            const int tap = seg0 ? kb / g.c0_chunks : 0;
+            const int chunk = seg0 ? kb - tap * g.c0_chunks : kb - nkb0;
+            int dh = 0, dw = 0;
+            if (seg0 && g.taps0 == 9) {
+                dh = tap / 3 - 1;
+                dw = tap % 3 - 1;
+            }
+            if (elected) {
                 ptx::mbar_arrive_expect_tx(fb, stage_bytes);
-                const uint32_t sa = smem_base + (uint32_t)s * stage_bytes;
-                if (kb < nkb0) {
-                    const int tap = kb / g.c0_chunks;
-                    const int chunk = kb - tap * g.c0_chunks;
-                    int dh = 0, dw = 0;
-                    if (g.taps0 == 9) {
-                        dh = tap / 3 - 1;
-                        dw = tap % 3 - 1;
-                    }
-                    ptx::tma_load_4d(sa, &mapA0, fb, chunk * BLOCK_K, w0 + dw, h0 + dh, b);
-                } else {
-                    ptx::tma_load_4d(sa, &mapA1, fb, (kb - nkb0) * BLOCK_K, w0, h0, b);
-                }
+                if (seg0) ptx::tma_load_4d(sa, &mapA0, fb, chunk * BLOCK_K, w0 + dw, h0 + dh, b);
+                else ptx::tma_load_4d(sa, &mapA1, fb, chunk * BLOCK_K, w0, h0, b);
                 ptx::tma_load_3d(sa + A_STAGE_BYTES, &mapB, fb, kb * BLOCK_K, n0, g.b_batched ? b : 0);
             }
+            __syncwarp();
         }
     } else if (warp == 1) {
         // =========================== MMA issuer ===========================
-        if (lane == 0) {
-            const uint32_t idesc = ptx::umma_idesc_bf16(BLOCK_M, (uint32_t)g.n_tile);
-            for (int kb = 0; kb < nkb; ++kb) {
-                const int s = kb % g.stages;
-                const uint32_t ph = (uint32_t)(kb / g.stages) & 1u;
-                ptx::mbar_wait(ptx::smem_u32(&full_bar[s]), ph);
-                ptx::tc_fence_after();
-                const uint32_t sa = smem_base + (uint32_t)s * stage_bytes;
-                const uint64_t da = ptx::umma_desc_k_sw128(sa);
-                const uint64_t db = ptx::umma_desc_k_sw128(sa + A_STAGE_BYTES);
-#pragma unroll
-                for (int k = 0; k < BLOCK_K / 16; ++k) {
-                    // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the (addr>>4) field
-                    ptx::mma_bf16_ss(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
-                                     (kb > 0 || k > 0) ? 1u : 0u);
-                }
+        const uint32_t idesc = ptx::umma_idesc_bf16(BLOCK_M, (uint32_t)g.n_tile);
+        const bool elected = ptx::elect_one();
+        for (int kb = 0; kb < nkb; ++kb) {
+            const int s = kb % g.stages;
+            const uint32_t ph = (uint32_t)(kb / g.stages) & 1u;
+            ptx::mbar_wait(ptx::smem_u32(&full_bar[s]), ph);
+            ptx::tc_fence_after();
+            const uint32_t sa = smem_base + (uint32_t)s * stage_bytes;
+            const uint64_t da = ptx::umma_desc_k_sw128(sa);
+            const uint64_t db = ptx::umma_desc_k_sw128(sa + A_STAGE_BYTES);
+            if (elected) {
+                // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the (addr>>4) field
+                ptx::mma_bf16_ss(tmem_base, da, db, idesc, kb > 0 ? 1u : 0u);
+                ptx::mma_bf16_ss(tmem_base, da + 2, db + 2, idesc, 1u);
+                ptx::mma_bf16_ss(tmem_base, da + 4, db + 4, idesc, 1u);
+                ptx::mma_bf16_ss(tmem_base, da + 6, db + 6, idesc, 1u);
                 ptx::mma_commit(ptx::smem_u32(&empty_bar[s]));  // frees the smem stage when these MMAs retire
             }
-            ptx::mma_commit(ptx::smem_u32(&accum_bar));  // accumulator complete
+            __syncwarp();
         }
+        if (elected) ptx::mma_commit(ptx::smem_u32(&accum_bar));  // accumulator complete
+        __syncwarp();
     } else {
         // =========================== epilogue (warps 2..5) ===========================
         const int quarter = warp & 3;  // TMEM lane quarter this warp may access
@@ -219,12 +222,19 @@ int ilog2(int v) {
 int conv_gemm_make_plan(ConvGemmPlan* p, const ActView* a0, int taps0, const ActView* a1, const bf16* wt, int n_rows,
                         int64_t wt_batch_stride, int b_batched, const float* bias, const float* tbias, int tb_stride,
                         const ActView* res, float scale, void* out, int out_ld, int out_f32) {
+    return conv_gemm_make_plan_ex(p, a0, taps0, a1, wt, n_rows, wt_batch_stride, b_batched, bias, tbias, tb_stride, res,
+                                  scale, out, out_ld, out_f32, 0);
+}
+
+int conv_gemm_make_plan_ex(ConvGemmPlan* p, const ActView* a0, int taps0, const ActView* a1, const bf16* wt, int n_rows,
+                           int64_t wt_batch_stride, int b_batched, const float* bias, const float* tbias, int tb_stride,
+                           const ActView* res, float scale, void* out, int out_ld, int out_f32, int64_t wt_row_pitch) {
     SNRSE_CHECK_ARG(taps0 == 1 || taps0 == 9, "conv_gemm: taps0 must be 1 or 9");
     SNRSE_CHECK_ARG(a0->C % 64 == 0 && a0->ld % 8 == 0, "conv_gemm: Cin must be a multiple of 64 (got %d)", a0->C);
     SNRSE_CHECK_ARG(!a1 || (a1->C % 64 == 0 && a1->ld % 8 == 0), "conv_gemm: Cin1 must be a multiple of 64");
     SNRSE_CHECK_ARG(!a1 || (a1->B == a0->B && a1->H == a0->H && a1->W == a0->W), "conv_gemm: segment shapes differ");
     SNRSE_CHECK_ARG(n_rows % 32 == 0, "conv_gemm: N must be a multiple of 32 (got %d)", n_rows);
-    SNRSE_CHECK_ARG(out_ld % 8 == 0, "conv_gemm: output pitch must be a multiple of 8");
+    SNRSE_CHECK_ARG(out_ld % (out_f32 ? 4 : 8) == 0, "conv_gemm: output pitch must be a multiple of 16 bytes");
     SNRSE_CHECK_ARG(!res || res->ld % 8 == 0, "conv_gemm: residual pitch must be a multiple of 8");
     memset(p, 0, sizeof(*p));
     p->taps0 = taps0;
@@ -252,6 +262,14 @@ int conv_gemm_make_plan(ConvGemmPlan* p, const ActView* a0, int taps0, const Act
     p->tiles_w = cdiv(a0->W, tw);
     p->N = n_rows;
     p->n_tile = n_rows >= 256 ? 256 : (n_rows >= 128 ? 128 : 64);
+    // Few pixel tiles (small feature maps): one CTA walks the whole K loop alone and is bound by the TMA latency per
+    // K block, not by the tensor pipe.  Split N into 64-column tiles (4x the CTAs, a quarter of the MMA time each) and
+    // give every CTA a whole SM's shared memory for a deep TMA ring.
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int64_t pixel_tiles = (int64_t)a0->B * p->tiles_h * p->tiles_w;
+    const bool small = pixel_tiles * cdiv(n_rows, p->n_tile) * 2 <= sms && n_rows % 64 == 0;
+    if (small) p->n_tile = 64;
     p->b_batched = b_batched;
     p->bias = bias;
     p->tbias = tbias;
@@ -264,7 +282,7 @@ int conv_gemm_make_plan(ConvGemmPlan* p, const ActView* a0, int taps0, const Act
     p->out_f32 = out_f32;
     const int stage_bytes = A_STAGE_BYTES + p->n_tile * BLOCK_K * 2;
     // two CTAs per SM when possible (overlaps one tile's epilogue with the other's main loop)
-    int stages = (110 * 1024) / stage_bytes;
+    int stages = ((small ? 196 : 110) * 1024) / stage_bytes;
     if (stages > MAX_STAGES) stages = MAX_STAGES;
     if (stages < 2) stages = 2;
     const int nkb = taps0 * p->c0_chunks + p->c1_chunks;
@@ -280,7 +298,8 @@ int conv_gemm_make_plan(ConvGemmPlan* p, const ActView* a0, int taps0, const Act
         p->mapA1 = p->mapA0;
     }
     const int nb = b_batched ? a0->B : 1;
-    SNRSE_TRY(tma_make_wt_map(&p->mapB, wt, ktot, n_rows, nb, b_batched ? wt_batch_stride : ktot * n_rows, 64, p->n_tile));
+    SNRSE_TRY(tma_make_wt_map(&p->mapB, wt, ktot, n_rows, nb, b_batched ? wt_batch_stride : ktot * n_rows, 64, p->n_tile,
+                              wt_row_pitch));
     return SNRSE_OK;
 }
 

@@ -531,7 +531,7 @@ int rec_attn(Plan& P, const Mod& m, int x) {
     const int a = rec_gn(P, x, m.o[0], m.o[1], 0);
     const int qkv = P.new_t(tx.B, tx.H, tx.W, 3 * c, 2);
     rec_gemm(P, a, 1, -1, m.o[2], 3 * c, m.o[3], -1, -1, 1.0f, qkv);
-    const int sc = P.new_t(tx.B, n, n, 1, 4);
+    const int sc = P.new_t(1, 1, 1, (int)((attention_workspace_bytes(tx.B, n, c) + 3) / 4), 4);   // scores | probabilities | V^T
     const int o = P.new_t(tx.B, tx.H, tx.W, c, 2);
     P.use(qkv); P.use(sc); P.use(o);
     P.step++;
@@ -543,7 +543,8 @@ int rec_attn(Plan& P, const Mod& m, int x) {
         v.ptr += 2 * c;
         float* scores = p.fptr(sc);
         const double nn = (double)q.H * q.W;
-        p.add(LK_ATTN, 4.0 * q.B * nn * nn * c, 2.0 * q.B * nn * c * 4, [=](cudaStream_t s) { return attention_launch(&q, &k, &v, scores, &vo, s); });
+        const int tc = (p.flags & 2) ? 0 : 1;   // cross-check mode keeps the fp32 CUDA-core kernels
+        p.add(LK_ATTN, 4.0 * q.B * nn * nn * c, 2.0 * q.B * nn * c * 4, [=](cudaStream_t s) { return attention_launch(&q, &k, &v, scores, &vo, s, tc); });
         return SNRSE_OK;
     });
     const int out = P.new_t(tx.B, tx.H, tx.W, c, 2);

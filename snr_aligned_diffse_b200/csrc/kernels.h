@@ -43,6 +43,10 @@ struct ConvGemmPlan {
 int conv_gemm_make_plan(ConvGemmPlan* p, const ActView* a0, int taps0, const ActView* a1, const bf16* wt, int n_rows,
                         int64_t wt_batch_stride, int b_batched, const float* bias, const float* tbias, int tb_stride,
                         const ActView* res, float scale, void* out, int out_ld, int out_f32);
+// same with an explicit pitch (elements) between the rows of wt (0: dense) -- attention operands inside a fused qkv buffer
+int conv_gemm_make_plan_ex(ConvGemmPlan* p, const ActView* a0, int taps0, const ActView* a1, const bf16* wt, int n_rows,
+                           int64_t wt_batch_stride, int b_batched, const float* bias, const float* tbias, int tb_stride,
+                           const ActView* res, float scale, void* out, int out_ld, int out_f32, int64_t wt_row_pitch);
 int conv_gemm_launch(const ConvGemmPlan* p, cudaStream_t s);
 
 // ----------------------------------------------------------------------------- conv_halo.cu
@@ -118,8 +122,12 @@ int fir_down2_f4_launch(const float* x, float* out, int B, int H, int W, cudaStr
 
 // ----------------------------------------------------------------------------- attention.cu
 // q,k,v: [B, n, C] bf16 views (tokens = H*W); scores: [B, n, n] f32 workspace; o: bf16 view.
-int attention_launch(const ActView* q, const ActView* k, const ActView* v, float* scores, const ActView* o,
-                     cudaStream_t s);
+// workspace: attention_workspace_bytes(B, n, C): scores f32 [B,n,n] | probabilities bf16 [B,n,n] | V^T bf16 [B,C,n].
+// n % 64 == 0 and C % 64 == 0: Q K^T and P V run on the tensor cores (conv_gemm.cu, batched operand B), softmax in
+// fp32 in between; otherwise (the 4 x T/64 bottleneck of short inputs) fp32 CUDA-core kernels.
+int64_t attention_workspace_bytes(int B, int n, int C);
+int attention_launch(const ActView* q, const ActView* k, const ActView* v, void* workspace, const ActView* o,
+                     cudaStream_t s, int allow_tensor_cores = 1);
 
 // ----------------------------------------------------------------------------- temb.cu
 // t: [B]; fourier_w [nf]; w1 [4nf][2nf], b1; w2 [4nf][4nf], b2; dense_w [rows][4nf], dense_b [rows]

@@ -50,13 +50,15 @@ int tma_make_act_map(CUtensorMap* map, const bf16* ptr, int C, int W, int H, int
 }
 
 int tma_make_wt_map(CUtensorMap* map, const bf16* ptr, int64_t K, int64_t rows, int64_t batch, int64_t batch_stride,
-                    int box_k, int box_rows) {
+                    int box_k, int box_rows, int64_t row_pitch) {
+    if (row_pitch <= 0) row_pitch = K;
     EncodeTiledFn enc;
     SNRSE_TRY(get_encode(&enc));
     SNRSE_CHECK_ARG((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "TMA: weight pointer must be 16-byte aligned");
-    SNRSE_CHECK_ARG(box_k * 2 == 128 && box_rows <= 256 && K % 8 == 0 && batch_stride % 8 == 0, "TMA: bad weight box");
+    SNRSE_CHECK_ARG(box_k * 2 == 128 && box_rows <= 256 && K % 8 == 0 && batch_stride % 8 == 0 && row_pitch % 8 == 0,
+                    "TMA: bad weight box");
     cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)batch};
-    cuuint64_t strides[2] = {(cuuint64_t)K * 2, (cuuint64_t)batch_stride * 2};
+    cuuint64_t strides[2] = {(cuuint64_t)row_pitch * 2, (cuuint64_t)batch_stride * 2};
     cuuint32_t box[3] = {(cuuint32_t)box_k, (cuuint32_t)box_rows, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<bf16*>(ptr), dims, strides, box, estr,

@@ -179,7 +179,7 @@ def attention_nhwc(q, k, v):
     """q,k,v [B, n, C] bf16 -> [B, n, C] bf16."""
     lib = _lib_dev()
     B, n, C = q.shape
-    scores = torch.empty(B, n, n, dtype=torch.float32, device=q.device)
+    scores = torch.empty(int(lib.snrse_attention_workspace_bytes(B, n, C)), dtype=torch.uint8, device=q.device)
     out = torch.empty_like(q)
     _lib.check(lib.snrse_attention_nhwc(_lib.ptr(q), _lib.ptr(k), _lib.ptr(v), _lib.ptr(scores), _lib.ptr(out), B, n, C,
                                         _lib.stream_ptr()), "attention")
