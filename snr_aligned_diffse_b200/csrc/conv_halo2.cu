@@ -46,6 +46,7 @@ constexpr uint32_t ROW_B = 128;                       // one pixel = 64 bf16 cha
 
 struct Halo2Args {
     int c0_chunks, c1_chunks;
+    unsigned char seq[16];         // order of the channel chunks in the K loop: chunk | 0x80 for the 1x1 shortcut operand
     int H, W, B;
     int sub;                       // sub-tiles per super-tile (1 or 2)
     int tiles_h, tiles_w, n_tiles;
@@ -135,7 +136,8 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
     const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
     const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t a_bytes = halo_stage_bytes(g.sub);                                   // ring slot
-    const uint32_t a_tx = (uint32_t)(SUB_ROWS * g.sub + 2) * HALO_W * ROW_B;            // bytes one TMA box delivers
+    const uint32_t a_tx = (uint32_t)(SUB_ROWS * g.sub + 2) * HALO_W * ROW_B;            // bytes one halo TMA box delivers
+    const uint32_t a1_tx = (uint32_t)(SUB_ROWS * g.sub) * TW * ROW_B;                   // shortcut operand: no halo
     const uint32_t b_bytes = (uint32_t)(g.N / 2) * ROW_B;   // this CTA's half of the weight tile
     const uint32_t a_base = smem_base, b_base = smem_base + (uint32_t)g.na * a_bytes;
     const uint32_t stg_base = b_base + (uint32_t)g.nb * b_bytes;
@@ -198,19 +200,21 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
                 ptx::mbar_wait(ptx::smem_u32(&a_empty[s]), ph ^ 1u);
                 DBG_ADD(w_a);
                 const uint32_t dst = a_base + s * a_bytes;
-                const bool seg0 = j < g.c0_chunks;
+                const bool seg0 = !(g.seq[j] & 0x80);
+                const int chunk = g.seq[j] & 0x7f;
                 if (elected) {
-                    // halo origin (w0-1, h0-1); rows / columns outside the image are zero-filled == conv padding
+                    // 3x3 operand: halo origin (w0-1, h0-1), rows / columns outside the image are zero-filled == conv padding;
+                    // 1x1 shortcut operand: the bare tile (8 x 16*SUB pixels)
                     if (g.scsh) {
                         // tile -> this CTA's own barrier; the normalising warps publish it to the leader afterwards
                         // (shortcut tiles take the same route untouched, so every ring slot follows one protocol)
-                        ptx::mbar_arrive_expect_tx(ptx::smem_u32(&a_land[s]), a_tx);
-                        if (seg0) ptx::tma_load_4d(dst, &mapA0, ptx::smem_u32(&a_land[s]), j * 64, w0 - 1, h0 - 1, b);
-                        else ptx::tma_load_4d(dst, &mapA1, ptx::smem_u32(&a_land[s]), (j - g.c0_chunks) * 64, w0 - 1, h0 - 1, b);
+                        ptx::mbar_arrive_expect_tx(ptx::smem_u32(&a_land[s]), seg0 ? a_tx : a1_tx);
+                        if (seg0) ptx::tma_load_4d(dst, &mapA0, ptx::smem_u32(&a_land[s]), chunk * 64, w0 - 1, h0 - 1, b);
+                        else ptx::tma_load_4d(dst, &mapA1, ptx::smem_u32(&a_land[s]), chunk * 64, w0, h0, b);
                     } else {
-                        ptx::mbar_arrive_expect_tx_remote(fb0 + 8u * s, a_tx);
-                        if (seg0) ptx::tma_load_4d_2sm(dst, &mapA0, fb0 + 8u * s, j * 64, w0 - 1, h0 - 1, b);
-                        else ptx::tma_load_4d_2sm(dst, &mapA1, fb0 + 8u * s, (j - g.c0_chunks) * 64, w0 - 1, h0 - 1, b);
+                        ptx::mbar_arrive_expect_tx_remote(fb0 + 8u * s, seg0 ? a_tx : a1_tx);
+                        if (seg0) ptx::tma_load_4d_2sm(dst, &mapA0, fb0 + 8u * s, chunk * 64, w0 - 1, h0 - 1, b);
+                        else ptx::tma_load_4d_2sm(dst, &mapA1, fb0 + 8u * s, chunk * 64, w0, h0, b);
                     }
                 }
                 __syncwarp();
@@ -226,7 +230,8 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
         const uint32_t fb0 = ptx::mapa_rank0(ptx::smem_u32(&b_full[0]));
         for (int ct = cluster_id; ct < n_ctiles; ct += n_clusters) {
             for (int j = 0; j < n_astage; ++j) {
-                const bool seg0 = j < g.c0_chunks;
+                const bool seg0 = !(g.seq[j] & 0x80);
+                const int chunk = g.seq[j] & 0x7f;
                 const int ntap = seg0 ? 9 : 1;
                 for (int tap = 0; tap < ntap; ++tap, ++it) {
                     const uint32_t s = it % (uint32_t)g.nb, ph = (it / (uint32_t)g.nb) & 1u;
@@ -234,7 +239,7 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
                     ptx::mbar_wait(ptx::smem_u32(&b_empty[s]), ph ^ 1u);
                     DBG_ADD(w_b);
                     // K layout of the packed weights: [tap = r*3 + s][cin], then the shortcut channels
-                    const int kb = seg0 ? (tap * g.c0_chunks + j) : (9 * g.c0_chunks + (j - g.c0_chunks));
+                    const int kb = seg0 ? (tap * g.c0_chunks + chunk) : (9 * g.c0_chunks + chunk);
                     if (elected) {
                         if (rank == 0) ptx::mbar_arrive_expect_tx(ptx::smem_u32(&b_full[s]), 2 * b_bytes);
                         ptx::tma_load_3d_2sm(b_base + s * b_bytes, &mapB, fb0 + 8u * s, kb * 64, (int)rank * (g.N / 2), 0);
@@ -272,17 +277,17 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
                     if (g.dbg) t0__ = clock64();
                     ptx::mbar_wait(ptx::smem_u32(&a_full[sa]), pha);
                     DBG_ADD(w_a);
-                    const bool seg0 = j < g.c0_chunks;
+                    const bool seg0 = !(g.seq[j] & 0x80);
                     const int ntap = seg0 ? 9 : 1;
                     for (int t = 0; t < ntap; ++t, ++itb) {
                         const uint32_t sb = itb % (uint32_t)g.nb, phb = (itb / (uint32_t)g.nb) & 1u;
-                        const uint32_t tap = seg0 ? (uint32_t)t : 4u;          // the 1x1 shortcut reads the centre tap
-                        const uint32_t r = tap / 3u, sft = tap - 3u * r;
+                        const uint32_t r = (uint32_t)t / 3u, sft = (uint32_t)t - 3u * r;
                         const uint64_t db = ptx::umma_desc_k_sw128(b_base + sb * b_bytes);
                         const uint32_t acc = (j > 0 || t > 0) ? 1u : 0u;
-                        // first pixel row of this sub-tile's tap window in the halo tile
-                        const uint32_t row0 = (r + (uint32_t)(SUB_ROWS * u)) * HALO_W + sft;
-                        const uint64_t da = umma_desc_rows(a_base + sa * a_bytes + row0 * ROW_B, HALO_W * ROW_B);
+                        // 3x3: first pixel row of this sub-tile's tap window in the halo tile, 8-row groups 10 rows apart;
+                        // 1x1 shortcut: the bare tile, sub-tile u starts at row 16*8*u, groups 8 rows apart
+                        const uint32_t row0 = seg0 ? (r + (uint32_t)(SUB_ROWS * u)) * HALO_W + sft : (uint32_t)(SUB_ROWS * TW * u);
+                        const uint64_t da = umma_desc_rows(a_base + sa * a_bytes + row0 * ROW_B, (seg0 ? HALO_W : TW) * ROW_B);
                         if (g.dbg) t0__ = clock64();
                         ptx::mbar_wait(ptx::smem_u32(&b_full[sb]), phb);
                         DBG_ADD(w_b);
@@ -328,12 +333,13 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
                 const int h0 = (rem / g.tiles_w) * SUB_ROWS * g.sub, w0 = (rem % g.tiles_w) * TW;
                 for (int j = 0; j < n_astage; ++j, ++it) {
                     const uint32_t s = it % (uint32_t)g.na, ph = (it / (uint32_t)g.na) & 1u;
-                    const bool live = (b < g.B) && (j < g.c0_chunks);   // the 1x1 shortcut operand is used raw
+                    const bool live = (b < g.B) && !(g.seq[j] & 0x80);   // the 1x1 shortcut operand is used raw
+                    const int chunk = g.seq[j] & 0x7f;
                     // h = x * (scale/2) + shift/2  ==  (x*scale + shift)/2 exactly;  silu(t) = h + h*tanh(h)  (silu_f)
                     float sc[8], sh[8];
                     if (live) {
-                        const float4* pa = reinterpret_cast<const float4*>(g.scsh + ((int64_t)b * 2) * g.norm_c + j * 64 + q * 8);
-                        const float4* pc = reinterpret_cast<const float4*>(g.scsh + ((int64_t)b * 2 + 1) * g.norm_c + j * 64 + q * 8);
+                        const float4* pa = reinterpret_cast<const float4*>(g.scsh + ((int64_t)b * 2) * g.norm_c + chunk * 64 + q * 8);
+                        const float4* pc = reinterpret_cast<const float4*>(g.scsh + ((int64_t)b * 2 + 1) * g.norm_c + chunk * 64 + q * 8);
                         const float4 a0 = __ldg(pa), a1 = __ldg(pa + 1), c0 = __ldg(pc), c1 = __ldg(pc + 1);
                         sc[0] = a0.x; sc[1] = a0.y; sc[2] = a0.z; sc[3] = a0.w; sc[4] = a1.x; sc[5] = a1.y; sc[6] = a1.z; sc[7] = a1.w;
                         sh[0] = c0.x; sh[1] = c0.y; sh[2] = c0.z; sh[3] = c0.w; sh[4] = c1.x; sh[5] = c1.y; sh[6] = c1.z; sh[7] = c1.w;
@@ -582,6 +588,7 @@ int conv_halo2_make_plan(ConvHaloPlan* p, const ActView* a0, const ActView* a1, 
     SNRSE_CHECK_ARG(a0->C % 64 == 0 && a0->ld % 8 == 0, "conv_halo2: Cin must be a multiple of 64");
     SNRSE_CHECK_ARG(!a1 || (a1->C % 64 == 0 && a1->ld % 8 == 0 && a1->H == a0->H && a1->W == a0->W && a1->B == a0->B),
                     "conv_halo2: bad shortcut operand");
+    SNRSE_CHECK_ARG(a0->C / 64 + (a1 ? a1->C / 64 : 0) <= 16, "conv_halo2: at most 16 channel chunks (1024 channels)");
     SNRSE_CHECK_ARG(out_ld % 8 == 0 && (!res || res->ld % 8 == 0), "conv_halo2: pitches must be multiples of 8");
     if (g_num_sms2 == 0) {
         int dev = 0;
@@ -627,7 +634,7 @@ int conv_halo2_make_plan(ConvHaloPlan* p, const ActView* a0, const ActView* a1, 
     p->ustats = ustats;
     const int box_h = SUB_ROWS * sub + 2;
     SNRSE_TRY(tma_make_act_map(&p->mapA0, a0->ptr, a0->C, a0->W, a0->H, a0->B, a0->ld, 64, HALO_W, box_h));
-    if (a1) SNRSE_TRY(tma_make_act_map(&p->mapA1, a1->ptr, a1->C, a1->W, a1->H, a1->B, a1->ld, 64, HALO_W, box_h));
+    if (a1) SNRSE_TRY(tma_make_act_map(&p->mapA1, a1->ptr, a1->C, a1->W, a1->H, a1->B, a1->ld, 64, TW, SUB_ROWS * sub));
     else p->mapA1 = p->mapA0;
     const int64_t ktot = 64 * (int64_t)(9 * p->c0_chunks + p->c1_chunks);
     SNRSE_TRY(tma_make_wt_map(&p->mapB, wt, ktot, n_rows, 1, ktot * n_rows, 64, n_rows / 2));
@@ -685,6 +692,14 @@ int conv_halo2_launch(const ConvHaloPlan* p, cudaStream_t s) {
     }
     Halo2Args g;
     g.c0_chunks = p->c0_chunks; g.c1_chunks = p->c1_chunks;
+    {   // K-loop order: 3x3 chunks, then the 1x1 shortcut chunks.  (Interleaving the short shortcut chunks between the
+        // long 3x3 chunks was measured and did not help: with two or three A slots the 3x3 tile that follows two
+        // shortcut tiles has only 1024 clk of MMA work to hide its load behind.)
+        int n = 0;
+        for (int i = 0; i < p->c0_chunks; ++i) g.seq[n++] = (unsigned char)i;
+        for (int i = 0; i < p->c1_chunks; ++i) g.seq[n++] = (unsigned char)(0x80 | i);
+        for (; n < 16; ++n) g.seq[n] = 0;
+    }
     g.H = p->H; g.W = p->W; g.B = p->B;
     g.sub = p->sub; g.tiles_h = p->tiles_h; g.tiles_w = p->tiles_w; g.n_tiles = p->n_tiles;
     g.N = p->N; g.na = p->na; g.nb = p->nb; g.acc_bufs = p->acc_bufs; g.stg_bufs = p->stg_bufs;
