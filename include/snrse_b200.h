@@ -146,7 +146,8 @@ int snrse_attention_nhwc(const void* q, const void* k, const void* v, void* work
 /* ---------------------------------------------------------------- SNR estimator ----------------
  * SNRNet.forward (backbones/snrnet.py:47-97).  feat: f32 [B][2][256][T16] (T16 % 16 == 0);
  * out: f32 [B] = noise/(speech+noise).  weights: packed blob, see snrse_snrnet_param_info (transform 0: flat copy of
- * the state-dict tensor; 1: the (64 x k) convolution weights [co][ci][f][dt] stored as [ci*64+f][dt][co]). */
+ * the state-dict tensor; 1: the (64 x k) convolution weights [co][ci][f][dt] stored as [ci*64+f][dt][co]; 2: the 3x3
+ * convolution [co][ci][3][3] stored as [ci][tap][co]). */
 int snrse_snrnet_num_params(void);
 int snrse_snrnet_param_info(int i, char* name, int name_cap, int64_t* offset, int64_t* numel, int* transform);
 int snrse_snrnet_param_shape(int i, int64_t* dims, int* ndim);

@@ -557,7 +557,7 @@ int record_plan(Plan& P) {
     const int B = P.B, F = P.F, T = P.T, L = e.n_levels, nf = e.nf;
     P.t_x4 = P.new_t(B, F, T, 4, 4);
     P.t_tb = P.new_t(B, 1, 1, e.dense_rows, 4);
-    P.t_tscr = P.new_t(B, 1, 1, 4 * nf, 4);
+    P.t_tscr = P.new_t(B, 1, 1, 10 * nf, 4);   // act(temb) [4nf] | Fourier features [2nf] | hidden [4nf] per sample
     P.t_stats = P.new_t(B, 1, 1, MAX_STAT_ENTRIES * 512, 4);   // statistics arena: entries of [B][128 units][2] x 8 bytes
     P.t_scsh = P.new_t(B, 1, 1, 2 * 512, 4);
     const int persistent[] = {P.t_x4, P.t_tb, P.t_tscr, P.t_stats, P.t_scsh};

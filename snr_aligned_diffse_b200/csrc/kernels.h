@@ -131,7 +131,7 @@ int attention_launch(const ActView* q, const ActView* k, const ActView* v, void*
 
 // ----------------------------------------------------------------------------- temb.cu
 // t: [B]; fourier_w [nf]; w1 [4nf][2nf], b1; w2 [4nf][4nf], b2; dense_w [rows][4nf], dense_b [rows]
-// act_temb: [B][4nf] scratch; tb_out: [B][rows]
+// scratch: B*10*nf floats (act(temb) [B][4nf], Fourier features [B][2nf], hidden [B][4nf]); tb_out: [B][rows]
 int temb_launch(const float* t, int B, int nf, const float* fourier_w, const float* w1, const float* b1,
                 const float* w2, const float* b2, const float* dense_w, const float* dense_b, int rows, float* scratch,
                 float* tb_out, cudaStream_t s);

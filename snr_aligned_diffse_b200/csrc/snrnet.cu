@@ -88,9 +88,10 @@ snr_conv3_pool_kernel(const float* __restrict__ a1, const float* __restrict__ w,
     float* sw = sm3;                       // [ci][k][co]   32*9*32 floats = 36 KB
     float* sx = sm3 + 32 * 9 * 32;         // [ci][18][10]  23 KB
     const int nc = blockIdx.y, f0 = blockIdx.x * C3_ROWS;
-    for (int i = threadIdx.x; i < 32 * 32 * 9; i += 256) {
-        const int co = i / 288, ci = (i / 9) % 32, k = i % 9;  // global [co][ci][3][3]
-        sw[(ci * 9 + k) * 32 + co] = w[i];
+    {   // weights pre-packed [ci][tap][co] (transform 2): a straight, conflict-free copy
+        const float4* src = reinterpret_cast<const float4*>(w);
+        float4* dst = reinterpret_cast<float4*>(sw);
+        for (int i = threadIdx.x; i < 32 * 32 * 9 / 4; i += 256) dst[i] = __ldg(src + i);
     }
     for (int i = threadIdx.x; i < 32 * 18 * 10; i += 256) {
         const int c = i / 180, r = (i / 10) % 18, t = i % 10;
@@ -144,17 +145,16 @@ struct ConvtW {
     const float* w[4];
     const float* b[4];
 };
-__global__ void __launch_bounds__(256)
-snr_convt_kernel(const float* __restrict__ a2, ConvtW cw, float* __restrict__ feats, int64_t ncl) {
-    __shared__ __align__(16) float sx[8][32][8];     // [cluster][r][frame]      8 KB
-    __shared__ __align__(16) float sw[32 * 8 * 32];  // [r][dt][co]           <= 32 KB
-    const int ki = blockIdx.y, k = 1 << ki, nout = 9 - k;
+template <int K>   // kernel width in frames (1, 2, 4, 8): compile-time so that only the K * (9-K) useful FMAs per row are issued
+__device__ __forceinline__ void snr_convt_body(const float* __restrict__ a2, const float* __restrict__ wg,
+                                               const float* __restrict__ bg, float* __restrict__ feats, int64_t ncl, int ki,
+                                               float (*sx)[32][8], float* sw) {
+    constexpr int NOUT = 9 - K;
     const int64_t nc0 = (int64_t)blockIdx.x * 8;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const float* wg = cw.w[ki];                      // packed [r (2048)][dt (k)][co (32)]
-    float acc[8];
+    float acc[NOUT];
 #pragma unroll
-    for (int t = 0; t < 8; ++t) acc[t] = 0.f;
+    for (int t = 0; t < NOUT; ++t) acc[t] = 0.f;
     for (int r0 = 0; r0 < 2048; r0 += 32) {
         __syncthreads();
         for (int i = threadIdx.x; i < 8 * 32 * 8; i += 256) {
@@ -162,34 +162,42 @@ snr_convt_kernel(const float* __restrict__ a2, ConvtW cw, float* __restrict__ fe
             const int64_t nc = nc0 + cl;
             sx[cl][rr][t] = nc < ncl ? a2[nc * 16384 + (int64_t)(r0 + rr) * 8 + t] : 0.f;
         }
-        // weights are pre-packed [r][dt][co]: the 32*k*32 floats of this chunk are one contiguous block
+        // weights are pre-packed [r][dt][co]: the 32*K*32 floats of this chunk are one contiguous block
         {
-            const float4* src = reinterpret_cast<const float4*>(wg + (int64_t)r0 * k * 32);
+            const float4* src = reinterpret_cast<const float4*>(wg + (int64_t)r0 * K * 32);
             float4* dst = reinterpret_cast<float4*>(sw);
-            for (int i = threadIdx.x; i < 8 * 32 * k; i += 256) dst[i] = __ldg(src + i);
+            for (int i = threadIdx.x; i < 8 * 32 * K; i += 256) dst[i] = __ldg(src + i);
         }
         __syncthreads();
+#pragma unroll 4
         for (int rr = 0; rr < 32; ++rr) {
             const float4 xa = *reinterpret_cast<const float4*>(&sx[warp][rr][0]);
             const float4 xb = *reinterpret_cast<const float4*>(&sx[warp][rr][4]);
             const float xf[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
 #pragma unroll
-            for (int dt = 0; dt < 8; ++dt) {
-                if (dt < k) {
-                    const float wv = sw[(rr * k + dt) * 32 + lane];
+            for (int dt = 0; dt < K; ++dt) {
+                const float wv = sw[(rr * K + dt) * 32 + lane];
 #pragma unroll
-                    for (int t = 0; t + dt < 8; ++t)
-                        if (t < nout) acc[t] = fmaf(xf[t + dt], wv, acc[t]);   // only the 9-k valid output frames
-                }
+                for (int t = 0; t < NOUT; ++t) acc[t] = fmaf(xf[t + dt], wv, acc[t]);
             }
         }
     }
     float best = -INFINITY;
 #pragma unroll
-    for (int t = 0; t < 8; ++t)
-        if (t < nout) best = fmaxf(best, acc[t]);
+    for (int t = 0; t < NOUT; ++t) best = fmaxf(best, acc[t]);
     const int64_t nc = nc0 + warp;
-    if (nc < ncl) feats[nc * 128 + ki * 32 + lane] = best + cw.b[ki][lane];
+    if (nc < ncl) feats[nc * 128 + ki * 32 + lane] = best + bg[lane];
+}
+
+__global__ void __launch_bounds__(256)
+snr_convt_kernel(const float* __restrict__ a2, ConvtW cw, float* __restrict__ feats, int64_t ncl) {
+    __shared__ __align__(16) float sx[8][32][8];     // [cluster][r][frame]      8 KB
+    __shared__ __align__(16) float sw[32 * 8 * 32];  // [r][dt][co]           <= 32 KB
+    const int ki = blockIdx.y;                       // weights packed [r (2048)][dt (k)][co (32)]
+    if (ki == 0) snr_convt_body<1>(a2, cw.w[0], cw.b[0], feats, ncl, 0, sx, sw);
+    else if (ki == 1) snr_convt_body<2>(a2, cw.w[1], cw.b[1], feats, ncl, 1, sx, sw);
+    else if (ki == 2) snr_convt_body<4>(a2, cw.w[2], cw.b[2], feats, ncl, 2, sx, sw);
+    else snr_convt_body<8>(a2, cw.w[3], cw.b[3], feats, ncl, 3, sx, sw);
 }
 
 // ---- LSTM input projections for both directions: pre[dir][B*S][512] = W_ih x + b_ih + b_hh
@@ -314,7 +322,8 @@ int snrse_snrnet_param_info(int i, char* name, int name_cap, int64_t* offset, in
     *offset = param_offset(i);
     *numel = kParams[i].numel;
     // transform 1: [co][ci][f][dt] is stored as [r = ci*64 + f][dt][co] (co fastest): the layout snr_convt_kernel stages
-    *transform = (i >= 4 && i <= 10 && (i % 2) == 0) ? 1 : 0;
+    // transform 2: conv3x3 [co][ci][3][3] stored as [ci][tap][co]
+    *transform = (i >= 4 && i <= 10 && (i % 2) == 0) ? 1 : (i == 2 ? 2 : 0);
     return SNRSE_OK;
 }
 

@@ -6,51 +6,40 @@
 
 namespace {
 
-// one block per batch item; blockDim = 4*nf (<= 512)
-__global__ void temb_mlp_kernel(const float* __restrict__ t, int nf, const float* __restrict__ fw,
-                                const float* __restrict__ w1, const float* __restrict__ b1,
-                                const float* __restrict__ w2, const float* __restrict__ b2, float* __restrict__ act_out) {
-    extern __shared__ float sm[];  // emb[2nf] | h1[4nf]
-    float* emb = sm;
-    float* h1 = sm + 2 * nf;
+// Gaussian Fourier features of log(t): emb[b] = [sin(p), cos(p)], p = log(t_b) * W * 2*pi  (layerspp.py:32-43),
+// evaluated in the reference's order.  grid = B, block = nf.
+__global__ void temb_fourier_kernel(const float* __restrict__ t, int nf, const float* __restrict__ fw, float* __restrict__ emb) {
     const int b = blockIdx.x, tid = threadIdx.x;
-    const float lt = logf(t[b]);
-    if (tid < nf) {
-        // x_proj = log(t) * W * 2 * pi  (layerspp.py:42), evaluated in the reference's order
-        const float proj = lt * fw[tid] * 2.0f * 3.14159265358979323846f;
-        emb[tid] = sinf(proj);
-        emb[nf + tid] = cosf(proj);
-    }
-    __syncthreads();
-    const int d = 4 * nf;
-    {
-        float a = b1[tid];
-        const float* wr = w1 + (int64_t)tid * 2 * nf;
-        for (int k = 0; k < 2 * nf; ++k) a = fmaf(wr[k], emb[k], a);
-        h1[tid] = a / (1.0f + expf(-a));  // act(temb) before the second Linear (ncsnpp.py:274)
-    }
-    __syncthreads();
-    {
-        float a = b2[tid];
-        const float* wr = w2 + (int64_t)tid * d;
-        for (int k = 0; k < d; ++k) a = fmaf(wr[k], h1[k], a);
-        act_out[(int64_t)b * d + tid] = a / (1.0f + expf(-a));  // act(temb) fed to every Dense_0
-    }
+    if (tid >= nf) return;
+    const float proj = logf(t[b]) * fw[tid] * 2.0f * 3.14159265358979323846f;
+    emb[(int64_t)b * 2 * nf + tid] = sinf(proj);
+    emb[(int64_t)b * 2 * nf + nf + tid] = cosf(proj);
 }
 
-// one warp per output row, all batch items (B <= 32 per pass handled by looping)
+// out[b, row] = f(W[row, :] . in[b, :] + bias[row]),  f = identity or SiLU.  One warp per output row: its weights are
+// read once (coalesced) into registers and reused for every batch item.  d <= 1024, d % 32 == 0.
+template <int SILU>
 __global__ void __launch_bounds__(256)
-temb_dense_kernel(const float* __restrict__ act, int B, int d, const float* __restrict__ dw,
-                  const float* __restrict__ db, int rows, float* __restrict__ out) {
+dense_rows_kernel(const float* __restrict__ in, int B, int d, const float* __restrict__ w, const float* __restrict__ bias,
+                  int rows, float* __restrict__ out) {
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= rows) return;
-    const float* wr = dw + (int64_t)row * d;
+    float wr[32];
+    const int per = d >> 5;
+    const float* wp = w + (int64_t)row * d;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) wr[i] = i < per ? __ldg(wp + i * 32 + lane) : 0.f;
+    const float bs = bias[row];
     for (int b = 0; b < B; ++b) {
+        const float* x = in + (int64_t)b * d;
         float a = 0.f;
-        for (int k = lane; k < d; k += 32) a = fmaf(wr[k], act[(int64_t)b * d + k], a);
-        a = warp_sum(a);
-        if (lane == 0) out[(int64_t)b * rows + row] = a + db[row];
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+            if (i < per) a = fmaf(wr[i], __ldg(x + i * 32 + lane), a);
+        a = warp_sum(a) + bs;
+        if (SILU) a = a / (1.0f + expf(-a));
+        if (lane == 0) out[(int64_t)b * rows + row] = a;
     }
 }
 
@@ -59,10 +48,20 @@ temb_dense_kernel(const float* __restrict__ act, int B, int d, const float* __re
 int temb_launch(const float* t, int B, int nf, const float* fourier_w, const float* w1, const float* b1,
                 const float* w2, const float* b2, const float* dense_w, const float* dense_b, int rows, float* scratch,
                 float* tb_out, cudaStream_t s) {
-    SNRSE_CHECK_ARG(4 * nf <= 1024, "temb: nf too large");
-    temb_mlp_kernel<<<B, 4 * nf, 6 * nf * sizeof(float), s>>>(t, nf, fourier_w, w1, b1, w2, b2, scratch);
+    SNRSE_CHECK_ARG(4 * nf <= 1024 && nf % 16 == 0, "temb: nf must be a multiple of 16, <= 256");
+    // scratch: act(temb) [B][4nf] | emb [B][2nf] | h1 [B][4nf]   (caller provides B*4nf floats + this tail: see engine)
+    const int d = 4 * nf;
+    float* act = scratch;
+    float* emb = scratch + (int64_t)B * d;
+    float* h1 = emb + (int64_t)B * 2 * nf;
+    temb_fourier_kernel<<<B, nf, 0, s>>>(t, nf, fourier_w, emb);
     SNRSE_LAUNCH_CHECK();
-    temb_dense_kernel<<<cdiv(rows, 8), 256, 0, s>>>(scratch, B, 4 * nf, dense_w, dense_b, rows, tb_out);
+    // Linear(2nf -> 4nf) -> SiLU -> Linear(4nf -> 4nf) -> SiLU (the activation every Dense_0 applies to temb, ncsnpp.py:256-275)
+    dense_rows_kernel<1><<<cdiv(d, 8), 256, 0, s>>>(emb, B, 2 * nf, w1, b1, d, h1);
+    SNRSE_LAUNCH_CHECK();
+    dense_rows_kernel<1><<<cdiv(d, 8), 256, 0, s>>>(h1, B, d, w2, b2, d, act);
+    SNRSE_LAUNCH_CHECK();
+    dense_rows_kernel<0><<<cdiv(rows, 8), 256, 0, s>>>(act, B, d, dense_w, dense_b, rows, tb_out);
     SNRSE_LAUNCH_CHECK();
     return SNRSE_OK;
 }

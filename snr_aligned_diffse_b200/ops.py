@@ -218,6 +218,9 @@ class SNRNetEngine:
             if p["transform"] == 1:   # (64 x k) convolutions: [co][ci][f][dt] -> [ci*64 + f][dt][co]
                 co, ci, f, k = w.shape
                 w = w.reshape(co, ci * f, k).permute(1, 2, 0).contiguous()
+            elif p["transform"] == 2:   # conv3x3: [co][ci][3][3] -> [ci][tap][co]
+                co, ci = w.shape[0], w.shape[1]
+                w = w.reshape(co, ci, 9).permute(1, 2, 0).contiguous()
             w = w.reshape(-1)
             assert w.numel() == p["numel"], p["name"]
             f32[p["offset"] // 4: p["offset"] // 4 + w.numel()].copy_(w)
