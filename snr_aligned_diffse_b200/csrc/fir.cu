@@ -30,25 +30,32 @@ __device__ __forceinline__ void zero8(float* a) {
     for (int j = 0; j < 8; ++j) a[j] = 0.f;
 }
 
-// horizontal [1,3,3,1]/8 around output column wo of input row hh (zero outside the image)
-__device__ __forceinline__ void hfilt_down(const bf16* __restrict__ img, int ld, int H, int W, int hh, int wo, int c0,
-                                           float* r) {
-    zero8(r);
-    if (hh < 0 || hh >= H) return;
-    const float k[4] = {0.125f, 0.375f, 0.375f, 0.125f};
-    const bf16* row = img + (int64_t)hh * W * ld + c0;
+// raw 16-byte loads of the 4 input columns around output column wo of input row hh (zero outside the image)
+__device__ __forceinline__ void load_row_down(const bf16* __restrict__ img, int ld, int H, int W, int hh, int wo, int c0,
+                                              uint4* raw) {
+    const bool row_ok = hh >= 0 && hh < H;
+    const bf16* row = img + (int64_t)(row_ok ? hh : 0) * W * ld + c0;
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
         const int ww = 2 * wo - 1 + t;
-        if (ww < 0 || ww >= W) continue;
-        const V8 v = ld8(row + (int64_t)ww * ld);
+        raw[t] = (row_ok && ww >= 0 && ww < W) ? __ldg(reinterpret_cast<const uint4*>(row + (int64_t)ww * ld)) : make_uint4(0, 0, 0, 0);
+    }
+}
+// horizontal [1,3,3,1]/8
+__device__ __forceinline__ void hfilt_down(const uint4* raw, float* r) {
+    const float k[4] = {0.125f, 0.375f, 0.375f, 0.125f};
+    zero8(r);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) r[j] = fmaf(k[t], v.f[j], r[j]);
+    for (int t = 0; t < 4; ++t) {
+        float f[8];
+        unpack8(raw[t], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = fmaf(k[t], f[j], r[j]);
     }
 }
 
 __global__ void __launch_bounds__(256)
-fir_down2_kernel(const bf16* __restrict__ x, int ld, int C, int H, int W, bf16* __restrict__ out, int out_ld) {
+fir_down2_kernel(const bf16* __restrict__ x, int ld, int C, int H, int W, bf16* __restrict__ out, int out_ld, int band) {
     const int tpp = C >> 3, cols = blockDim.x / tpp;
     const int c0 = (threadIdx.x % tpp) * 8;
     const int Ho = H >> 1, Wo = W >> 1;
@@ -56,14 +63,23 @@ fir_down2_kernel(const bf16* __restrict__ x, int ld, int C, int H, int W, bf16* 
     if (wo >= Wo) return;
     const int b = blockIdx.z;
     const bf16* img = x + (int64_t)b * H * W * ld;
-    const int ho0 = blockIdx.y * FIR_BAND;
-    const int ho1 = min(ho0 + FIR_BAND, Ho);
+    const int ho0 = blockIdx.y * band;
+    const int ho1 = min(ho0 + band, Ho);
     float r0[8], r1[8], r2[8], r3[8];   // horizontally filtered rows 2ho-1 .. 2ho+2
-    hfilt_down(img, ld, H, W, 2 * ho0 - 1, wo, c0, r0);
-    hfilt_down(img, ld, H, W, 2 * ho0, wo, c0, r1);
+    uint4 ra[4], rb[4];
+    load_row_down(img, ld, H, W, 2 * ho0 - 1, wo, c0, ra);
+    load_row_down(img, ld, H, W, 2 * ho0, wo, c0, rb);
+    hfilt_down(ra, r0);
+    hfilt_down(rb, r1);
+    load_row_down(img, ld, H, W, 2 * ho0 + 1, wo, c0, ra);   // the two new rows of the first output row
+    load_row_down(img, ld, H, W, 2 * ho0 + 2, wo, c0, rb);
     for (int ho = ho0; ho < ho1; ++ho) {
-        hfilt_down(img, ld, H, W, 2 * ho + 1, wo, c0, r2);
-        hfilt_down(img, ld, H, W, 2 * ho + 2, wo, c0, r3);
+        hfilt_down(ra, r2);
+        hfilt_down(rb, r3);
+        if (ho + 1 < ho1) {   // next output row's loads are in flight while this one is finished
+            load_row_down(img, ld, H, W, 2 * ho + 3, wo, c0, ra);
+            load_row_down(img, ld, H, W, 2 * ho + 4, wo, c0, rb);
+        }
         float o[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) o[j] = 0.125f * (r0[j] + r3[j]) + 0.375f * (r1[j] + r2[j]);
@@ -96,7 +112,7 @@ __device__ __forceinline__ void hfilt_up(const bf16* __restrict__ img, int ld, i
 }
 
 __global__ void __launch_bounds__(256)
-fir_up2_kernel(const bf16* __restrict__ x, int ld, int C, int H, int W, bf16* __restrict__ out, int out_ld) {
+fir_up2_kernel(const bf16* __restrict__ x, int ld, int C, int H, int W, bf16* __restrict__ out, int out_ld, int band) {
     const int tpp = C >> 3, cols = blockDim.x / tpp;
     const int c0 = (threadIdx.x % tpp) * 8;
     const int wi = blockIdx.x * cols + threadIdx.x / tpp;
@@ -105,8 +121,8 @@ fir_up2_kernel(const bf16* __restrict__ x, int ld, int C, int H, int W, bf16* __
     const int Wo = 2 * W;
     const bf16* img = x + (int64_t)b * H * W * ld;
     bf16* oimg = out + (int64_t)b * (2 * H) * Wo * out_ld + c0;
-    const int h0 = blockIdx.y * FIR_BAND;
-    const int h1 = min(h0 + FIR_BAND, H);
+    const int h0 = blockIdx.y * band;
+    const int h1 = min(h0 + band, H);
     float pa[8], pb[8], ca[8], cb[8], na[8], nb[8];   // rows hi-1, hi, hi+1 (a: even output column, b: odd)
     hfilt_up(img, ld, H, W, h0 - 1, wi, c0, pa, pb);
     hfilt_up(img, ld, H, W, h0, wi, c0, ca, cb);
@@ -205,8 +221,11 @@ int fir_down2_launch(const ActView* x, const ActView* out, cudaStream_t s) {
     SNRSE_CHECK_ARG(x->H % 2 == 0 && x->W % 2 == 0 && x->C % 8 == 0, "fir_down2: H, W must be even, C %% 8 == 0");
     SNRSE_CHECK_ARG(x->C <= 2048 && x->B <= 65535, "fir_down2: C <= 2048, B <= 65535");
     const int tpp = x->C / 8, nthr = tpp * (256 / tpp > 0 ? 256 / tpp : 1), cols = nthr / tpp;
-    dim3 grid((unsigned)cdiv(x->W / 2, cols), (unsigned)cdiv(x->H / 2, FIR_BAND), (unsigned)x->B);
-    fir_down2_kernel<<<grid, nthr, 0, s>>>(x->ptr, x->ld, x->C, x->H, x->W, out->ptr, out->ld);
+    // rows per block: as many as keep >= ~4 blocks per SM in flight (small maps would otherwise use a handful of SMs)
+    int band = FIR_BAND;
+    while (band > 1 && (int64_t)cdiv(x->W / 2, cols) * cdiv(x->H / 2, band) * x->B < 592) band >>= 1;
+    dim3 grid((unsigned)cdiv(x->W / 2, cols), (unsigned)cdiv(x->H / 2, band), (unsigned)x->B);
+    fir_down2_kernel<<<grid, nthr, 0, s>>>(x->ptr, x->ld, x->C, x->H, x->W, out->ptr, out->ld, band);
     SNRSE_LAUNCH_CHECK();
     return SNRSE_OK;
 }
@@ -215,8 +234,10 @@ int fir_up2_launch(const ActView* x, const ActView* out, cudaStream_t s) {
     SNRSE_CHECK_ARG(x->C % 8 == 0, "fir_up2: C %% 8 == 0");
     SNRSE_CHECK_ARG(x->C <= 2048 && x->B <= 65535, "fir_up2: C <= 2048, B <= 65535");
     const int tpp = x->C / 8, nthr = tpp * (256 / tpp > 0 ? 256 / tpp : 1), cols = nthr / tpp;
-    dim3 grid((unsigned)cdiv(x->W, cols), (unsigned)cdiv(x->H, FIR_BAND), (unsigned)x->B);
-    fir_up2_kernel<<<grid, nthr, 0, s>>>(x->ptr, x->ld, x->C, x->H, x->W, out->ptr, out->ld);
+    int band = FIR_BAND;
+    while (band > 1 && (int64_t)cdiv(x->W, cols) * cdiv(x->H, band) * x->B < 592) band >>= 1;
+    dim3 grid((unsigned)cdiv(x->W, cols), (unsigned)cdiv(x->H, band), (unsigned)x->B);
+    fir_up2_kernel<<<grid, nthr, 0, s>>>(x->ptr, x->ld, x->C, x->H, x->W, out->ptr, out->ld, band);
     SNRSE_LAUNCH_CHECK();
     return SNRSE_OK;
 }
