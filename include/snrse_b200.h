@@ -87,7 +87,8 @@ int snrse_ncsnpp_param_shape(void* handle, int i, int64_t* dims, int* ndim); /* 
 int snrse_ncsnpp_set_weights(void* handle, const void* device_blob);
 /* Plan for inputs [B][F][T]: returns the workspace size (or -1).  flags bit0: keep all activations
  * (debug taps); bit1: CUDA-core cross-check convolutions instead of tcgen05; bit2: first-generation tcgen05 kernel only;
- * bit3: single-CTA halo kernel instead of the 2-CTA one; bit4: GroupNorm+SiLU as a separate pass (no in-kernel fusion). */
+ * bit3: single-CTA halo kernel instead of the 2-CTA one; bit4: GroupNorm+SiLU as a separate pass (no in-kernel fusion);
+ * bit5: GroupNorm+SiLU of the up / down blocks inside the FIR kernels. */
 int64_t snrse_ncsnpp_plan_bytes(void* handle, int B, int F, int T, int flags);
 int snrse_ncsnpp_plan_bind(void* handle, int B, int F, int T, void* workspace, int64_t bytes);
 /* x (state), y (noisy), out: complex64 [B][F][T]; t [B] f32.  mode 0: dnn(cat[x,y], t);
@@ -137,6 +138,10 @@ int snrse_groupnorm_nhwc(const void* x, const float* gamma, const float* beta, v
  * op/upfirdn2d.cpp:12-23, op/upfirdn2d_kernel.cu modes 3 and 5) */
 int snrse_fir_nhwc(const void* x, void* out, int B, int H, int W, int C, int up, void* stream);
 int snrse_fir_f4(const float* x, float* out, int B, int H, int W, int up, void* stream);
+/* FIR resampling of silu(GroupNorm32(x)), normalisation applied on load (layerspp.py:245-257); workspace:
+ * snrse_groupnorm_workspace_bytes(B) */
+int snrse_gn_silu_fir_nhwc(const void* x, const float* gamma, const float* beta, float eps, void* out, int B, int H, int W,
+                           int C, int up, void* workspace, void* stream);
 /* softmax(q k^T / sqrt(C)) v over n positions (ncsnpp_utils/layerspp.py:84-88); workspace:
  * snrse_attention_workspace_bytes(B, n, C) (fp32 scores, bf16 probabilities, V^T).  Tensor cores when n % 64 == 0. */
 int64_t snrse_attention_workspace_bytes(int B, int n, int C);

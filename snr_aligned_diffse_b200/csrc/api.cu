@@ -183,6 +183,21 @@ int snrse_fir_nhwc(const void* x, void* out, int B, int H, int W, int C, int up,
     return up ? fir_up2_launch(&vx, &vo, S(stream)) : fir_down2_launch(&vx, &vo, S(stream));
 }
 
+// FIR resampling of silu(GroupNorm(x)) with the normalisation applied on load (ResnetBlockBigGANpp up / down blocks,
+// ncsnpp_utils/layerspp.py:245-257).  workspace: snrse_groupnorm_workspace_bytes(B).
+int snrse_gn_silu_fir_nhwc(const void* x, const float* gamma, const float* beta, float eps, void* out, int B, int H, int W,
+                           int C, int up, void* workspace, void* stream) {
+    SNRSE_CHECK_ARG(x && gamma && beta && out && workspace, "gn_silu_fir: null pointer");
+    const ActView vx = mk_view(x, B, H, W, C, C);
+    const ActView vo = up ? mk_view(out, B, 2 * H, 2 * W, C, C) : mk_view(out, B, H / 2, W / 2, C, C);
+    unsigned long long* ust = static_cast<unsigned long long*>(workspace);
+    float* scsh = reinterpret_cast<float*>(ust + (int64_t)B * 128 * 2);
+    SNRSE_CUDA(cudaMemsetAsync(ust, 0, (size_t)B * (C / 4) * 16, S(stream)));
+    SNRSE_TRY(gn_stats_launch(&vx, ust, S(stream)));
+    SNRSE_TRY(gn_finalize_launch(ust, C / 4, nullptr, 0, B, (int64_t)H * W * (C / 32), gamma, beta, eps, scsh, S(stream)));
+    return up ? fir_up2_launch(&vx, &vo, S(stream), scsh) : fir_down2_launch(&vx, &vo, S(stream), scsh);
+}
+
 int snrse_fir_f4(const float* x, float* out, int B, int H, int W, int up, void* stream) {
     SNRSE_CHECK_ARG(x && out, "fir_f4: null pointer");
     return up ? fir_up2_f4_launch(x, out, B, H, W, S(stream)) : fir_down2_f4_launch(x, out, B, H, W, S(stream));

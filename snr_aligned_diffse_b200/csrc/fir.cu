@@ -19,6 +19,35 @@ __device__ __forceinline__ V8 ld8(const bf16* p) {
     return r;
 }
 
+// Optional GroupNorm + SiLU on load (ResnetBlockBigGANpp up / down blocks: h = FIR(silu(GroupNorm(x))),
+// layerspp.py:245-257): the loaders apply y = silu(x*scale + shift) with the per-(sample, channel) scale/shift of
+// gn_finalize; positions outside the image contribute zero (the FIR pads the NORMALISED tensor).  Same arithmetic as
+// gn_apply_kernel followed by a bf16 round trip, so fusing does not change a bit.
+struct Norm8 {
+    float sc[8], sh[8];
+    bool on;
+};
+__device__ __forceinline__ Norm8 load_norm(const float* __restrict__ scsh, int b, int C, int c0) {
+    Norm8 n;
+    n.on = scsh != nullptr;
+    if (n.on) {
+        const float4* a = reinterpret_cast<const float4*>(scsh + ((int64_t)b * 2) * C + c0);
+        const float4* c = reinterpret_cast<const float4*>(scsh + ((int64_t)b * 2 + 1) * C + c0);
+        const float4 a0 = __ldg(a), a1 = __ldg(a + 1), c0v = __ldg(c), c1 = __ldg(c + 1);
+        n.sc[0] = a0.x; n.sc[1] = a0.y; n.sc[2] = a0.z; n.sc[3] = a0.w; n.sc[4] = a1.x; n.sc[5] = a1.y; n.sc[6] = a1.z; n.sc[7] = a1.w;
+        n.sh[0] = c0v.x; n.sh[1] = c0v.y; n.sh[2] = c0v.z; n.sh[3] = c0v.w; n.sh[4] = c1.x; n.sh[5] = c1.y; n.sh[6] = c1.z; n.sh[7] = c1.w;
+    }
+    return n;
+}
+// unpack 8 bf16 and, when enabled, normalise + SiLU + round to bf16 (what the separate pass would have stored)
+__device__ __forceinline__ void unpack_norm(const uint4& raw, const Norm8& n, bool inside, float* f) {
+    unpack8(raw, f);
+    if (n.on && inside) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = __bfloat162float(__float2bfloat16(silu_f(fmaf(f[j], n.sc[j], n.sh[j]))));
+    }
+}
+
 // Both bf16 kernels are separable and walk a band of rows with a sliding window in registers: thread = (column,
 // 8-channel chunk); every input row is filtered horizontally once (3 or 4 loads, neighbours shared through L1)
 // and reused by the two output rows it contributes to, so the kernels move ~1x the tensor instead of issuing
@@ -31,31 +60,37 @@ __device__ __forceinline__ void zero8(float* a) {
 }
 
 // raw 16-byte loads of the 4 input columns around output column wo of input row hh (zero outside the image)
-__device__ __forceinline__ void load_row_down(const bf16* __restrict__ img, int ld, int H, int W, int hh, int wo, int c0,
-                                              uint4* raw) {
+// returns the mask of columns that lie inside the image
+__device__ __forceinline__ int load_row_down(const bf16* __restrict__ img, int ld, int H, int W, int hh, int wo, int c0,
+                                             uint4* raw) {
     const bool row_ok = hh >= 0 && hh < H;
     const bf16* row = img + (int64_t)(row_ok ? hh : 0) * W * ld + c0;
+    int mask = 0;
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
         const int ww = 2 * wo - 1 + t;
-        raw[t] = (row_ok && ww >= 0 && ww < W) ? __ldg(reinterpret_cast<const uint4*>(row + (int64_t)ww * ld)) : make_uint4(0, 0, 0, 0);
+        const bool ok = row_ok && ww >= 0 && ww < W;
+        raw[t] = ok ? __ldg(reinterpret_cast<const uint4*>(row + (int64_t)ww * ld)) : make_uint4(0, 0, 0, 0);
+        mask |= ok ? (1 << t) : 0;
     }
+    return mask;
 }
 // horizontal [1,3,3,1]/8
-__device__ __forceinline__ void hfilt_down(const uint4* raw, float* r) {
+__device__ __forceinline__ void hfilt_down(const uint4* raw, int mask, const Norm8& nm, float* r) {
     const float k[4] = {0.125f, 0.375f, 0.375f, 0.125f};
     zero8(r);
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
         float f[8];
-        unpack8(raw[t], f);
+        unpack_norm(raw[t], nm, (mask >> t) & 1, f);
 #pragma unroll
         for (int j = 0; j < 8; ++j) r[j] = fmaf(k[t], f[j], r[j]);
     }
 }
 
 __global__ void __launch_bounds__(256)
-fir_down2_kernel(const bf16* __restrict__ x, int ld, int C, int H, int W, bf16* __restrict__ out, int out_ld, int band) {
+fir_down2_kernel(const bf16* __restrict__ x, int ld, int C, int H, int W, bf16* __restrict__ out, int out_ld, int band,
+                 const float* __restrict__ scsh) {
     const int tpp = C >> 3, cols = blockDim.x / tpp;
     const int c0 = (threadIdx.x % tpp) * 8;
     const int Ho = H >> 1, Wo = W >> 1;
@@ -65,20 +100,21 @@ fir_down2_kernel(const bf16* __restrict__ x, int ld, int C, int H, int W, bf16* 
     const bf16* img = x + (int64_t)b * H * W * ld;
     const int ho0 = blockIdx.y * band;
     const int ho1 = min(ho0 + band, Ho);
+    const Norm8 nm = load_norm(scsh, b, C, c0);
     float r0[8], r1[8], r2[8], r3[8];   // horizontally filtered rows 2ho-1 .. 2ho+2
     uint4 ra[4], rb[4];
-    load_row_down(img, ld, H, W, 2 * ho0 - 1, wo, c0, ra);
-    load_row_down(img, ld, H, W, 2 * ho0, wo, c0, rb);
-    hfilt_down(ra, r0);
-    hfilt_down(rb, r1);
-    load_row_down(img, ld, H, W, 2 * ho0 + 1, wo, c0, ra);   // the two new rows of the first output row
-    load_row_down(img, ld, H, W, 2 * ho0 + 2, wo, c0, rb);
+    int ma = load_row_down(img, ld, H, W, 2 * ho0 - 1, wo, c0, ra);
+    int mb = load_row_down(img, ld, H, W, 2 * ho0, wo, c0, rb);
+    hfilt_down(ra, ma, nm, r0);
+    hfilt_down(rb, mb, nm, r1);
+    ma = load_row_down(img, ld, H, W, 2 * ho0 + 1, wo, c0, ra);   // the two new rows of the first output row
+    mb = load_row_down(img, ld, H, W, 2 * ho0 + 2, wo, c0, rb);
     for (int ho = ho0; ho < ho1; ++ho) {
-        hfilt_down(ra, r2);
-        hfilt_down(rb, r3);
+        hfilt_down(ra, ma, nm, r2);
+        hfilt_down(rb, mb, nm, r3);
         if (ho + 1 < ho1) {   // next output row's loads are in flight while this one is finished
-            load_row_down(img, ld, H, W, 2 * ho + 3, wo, c0, ra);
-            load_row_down(img, ld, H, W, 2 * ho + 4, wo, c0, rb);
+            ma = load_row_down(img, ld, H, W, 2 * ho + 3, wo, c0, ra);
+            mb = load_row_down(img, ld, H, W, 2 * ho + 4, wo, c0, rb);
         }
         float o[8];
 #pragma unroll
@@ -91,28 +127,32 @@ fir_down2_kernel(const bf16* __restrict__ x, int ld, int C, int H, int W, bf16* 
 
 // horizontal interpolation of input row hh at input column wi: ea -> output column 2wi, eb -> 2wi+1
 __device__ __forceinline__ void hfilt_up(const bf16* __restrict__ img, int ld, int H, int W, int hh, int wi, int c0,
-                                         float* ea, float* eb) {
+                                         const Norm8& nm, float* ea, float* eb) {
     zero8(ea);
     zero8(eb);
     if (hh < 0 || hh >= H) return;
     const bf16* row = img + (int64_t)hh * W * ld + c0;
-    const V8 m = ld8(row + (int64_t)wi * ld);
+    float m[8];
+    unpack_norm(__ldg(reinterpret_cast<const uint4*>(row + (int64_t)wi * ld)), nm, true, m);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { ea[j] = 0.75f * m.f[j]; eb[j] = 0.75f * m.f[j]; }
+    for (int j = 0; j < 8; ++j) { ea[j] = 0.75f * m[j]; eb[j] = 0.75f * m[j]; }
     if (wi > 0) {
-        const V8 l = ld8(row + (int64_t)(wi - 1) * ld);
+        float l[8];
+        unpack_norm(__ldg(reinterpret_cast<const uint4*>(row + (int64_t)(wi - 1) * ld)), nm, true, l);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) ea[j] = fmaf(0.25f, l.f[j], ea[j]);
+        for (int j = 0; j < 8; ++j) ea[j] = fmaf(0.25f, l[j], ea[j]);
     }
     if (wi + 1 < W) {
-        const V8 rr = ld8(row + (int64_t)(wi + 1) * ld);
+        float rr[8];
+        unpack_norm(__ldg(reinterpret_cast<const uint4*>(row + (int64_t)(wi + 1) * ld)), nm, true, rr);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) eb[j] = fmaf(0.25f, rr.f[j], eb[j]);
+        for (int j = 0; j < 8; ++j) eb[j] = fmaf(0.25f, rr[j], eb[j]);
     }
 }
 
 __global__ void __launch_bounds__(256)
-fir_up2_kernel(const bf16* __restrict__ x, int ld, int C, int H, int W, bf16* __restrict__ out, int out_ld, int band) {
+fir_up2_kernel(const bf16* __restrict__ x, int ld, int C, int H, int W, bf16* __restrict__ out, int out_ld, int band,
+               const float* __restrict__ scsh) {
     const int tpp = C >> 3, cols = blockDim.x / tpp;
     const int c0 = (threadIdx.x % tpp) * 8;
     const int wi = blockIdx.x * cols + threadIdx.x / tpp;
@@ -124,10 +164,11 @@ fir_up2_kernel(const bf16* __restrict__ x, int ld, int C, int H, int W, bf16* __
     const int h0 = blockIdx.y * band;
     const int h1 = min(h0 + band, H);
     float pa[8], pb[8], ca[8], cb[8], na[8], nb[8];   // rows hi-1, hi, hi+1 (a: even output column, b: odd)
-    hfilt_up(img, ld, H, W, h0 - 1, wi, c0, pa, pb);
-    hfilt_up(img, ld, H, W, h0, wi, c0, ca, cb);
+    const Norm8 nm = load_norm(scsh, b, C, c0);
+    hfilt_up(img, ld, H, W, h0 - 1, wi, c0, nm, pa, pb);
+    hfilt_up(img, ld, H, W, h0, wi, c0, nm, ca, cb);
     for (int hi = h0; hi < h1; ++hi) {
-        hfilt_up(img, ld, H, W, hi + 1, wi, c0, na, nb);
+        hfilt_up(img, ld, H, W, hi + 1, wi, c0, nm, na, nb);
         float o[8];
         bf16* r_even = oimg + ((int64_t)(2 * hi) * Wo + 2 * wi) * out_ld;
         bf16* r_odd = r_even + (int64_t)Wo * out_ld;
@@ -217,7 +258,7 @@ fir_up2_f4_kernel(const float4* __restrict__ x, int H, int W, float4* __restrict
 
 }  // namespace
 
-int fir_down2_launch(const ActView* x, const ActView* out, cudaStream_t s) {
+int fir_down2_launch(const ActView* x, const ActView* out, cudaStream_t s, const float* scsh) {
     SNRSE_CHECK_ARG(x->H % 2 == 0 && x->W % 2 == 0 && x->C % 8 == 0, "fir_down2: H, W must be even, C %% 8 == 0");
     SNRSE_CHECK_ARG(x->C <= 2048 && x->B <= 65535, "fir_down2: C <= 2048, B <= 65535");
     const int tpp = x->C / 8, nthr = tpp * (256 / tpp > 0 ? 256 / tpp : 1), cols = nthr / tpp;
@@ -225,19 +266,19 @@ int fir_down2_launch(const ActView* x, const ActView* out, cudaStream_t s) {
     int band = FIR_BAND;
     while (band > 1 && (int64_t)cdiv(x->W / 2, cols) * cdiv(x->H / 2, band) * x->B < 592) band >>= 1;
     dim3 grid((unsigned)cdiv(x->W / 2, cols), (unsigned)cdiv(x->H / 2, band), (unsigned)x->B);
-    fir_down2_kernel<<<grid, nthr, 0, s>>>(x->ptr, x->ld, x->C, x->H, x->W, out->ptr, out->ld, band);
+    fir_down2_kernel<<<grid, nthr, 0, s>>>(x->ptr, x->ld, x->C, x->H, x->W, out->ptr, out->ld, band, scsh);
     SNRSE_LAUNCH_CHECK();
     return SNRSE_OK;
 }
 
-int fir_up2_launch(const ActView* x, const ActView* out, cudaStream_t s) {
+int fir_up2_launch(const ActView* x, const ActView* out, cudaStream_t s, const float* scsh) {
     SNRSE_CHECK_ARG(x->C % 8 == 0, "fir_up2: C %% 8 == 0");
     SNRSE_CHECK_ARG(x->C <= 2048 && x->B <= 65535, "fir_up2: C <= 2048, B <= 65535");
     const int tpp = x->C / 8, nthr = tpp * (256 / tpp > 0 ? 256 / tpp : 1), cols = nthr / tpp;
     int band = FIR_BAND;
     while (band > 1 && (int64_t)cdiv(x->W, cols) * cdiv(x->H, band) * x->B < 592) band >>= 1;
     dim3 grid((unsigned)cdiv(x->W, cols), (unsigned)cdiv(x->H, band), (unsigned)x->B);
-    fir_up2_kernel<<<grid, nthr, 0, s>>>(x->ptr, x->ld, x->C, x->H, x->W, out->ptr, out->ld, band);
+    fir_up2_kernel<<<grid, nthr, 0, s>>>(x->ptr, x->ld, x->C, x->H, x->W, out->ptr, out->ld, band, scsh);
     SNRSE_LAUNCH_CHECK();
     return SNRSE_OK;
 }

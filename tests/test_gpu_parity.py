@@ -319,6 +319,19 @@ def test_fir(ops, golden_dir):
         assert ((got - ref).abs() <= 2 ** -8 * ref.abs() + 1e-6).all()
 
 
+@pytest.mark.parametrize("shape", [(2, 128, 16, 24), (1, 256, 8, 8), (3, 384, 6, 10)])
+@pytest.mark.parametrize("up", [True, False])
+def test_gn_silu_fir_fused_equals_two_passes(ops, shape, up):
+    """FIR with GroupNorm+SiLU applied on load == GroupNorm pass followed by the FIR pass, bit for bit."""
+    B, C, H, W = shape
+    g = torch.Generator().manual_seed(C + H + int(up))
+    x = (torch.randn(B, H, W, C, generator=g) * 1.5 + 0.3).to(torch.bfloat16).to(DEV)
+    gamma, beta = (torch.rand(C, generator=g) + 0.5).to(DEV), (torch.randn(C, generator=g) * 0.2).to(DEV)
+    fused = ops.gn_silu_fir_nhwc(x, gamma, beta, up)
+    two = ops.fir_nhwc(ops.groupnorm_nhwc(x, gamma, beta, silu=True), up)
+    assert torch.equal(fused, two)
+
+
 @pytest.mark.parametrize("n", [4, 12, 64, 200, 128, 512, 1984])   # n % 64 == 0: tensor-core path
 def test_attention(ops, n):
     g = torch.Generator().manual_seed(n)
@@ -349,7 +362,7 @@ def _network_report(engine, sd, x, t, flags):
     return ref[:, 0], out.cpu(), rep
 
 
-@pytest.mark.parametrize("flags", [2, 4, 8, 16, 0], ids=["cuda-core-conv", "tcgen05gen1-conv", "tcgen05halo1-conv",
+@pytest.mark.parametrize("flags", [2, 4, 8, 16, 32, 0], ids=["cuda-core-conv", "tcgen05gen1-conv", "tcgen05halo1-conv", "tcgen05-gn-in-fir",
                                                        "tcgen05-unfused-gn", "tcgen05-conv"])
 def test_ncsnpp_forward_vs_golden(engine, sd, golden_dir, flags):
     z = np.load(os.path.join(golden_dir, "ncsnpp_forward.npz"))
