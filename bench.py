@@ -201,6 +201,20 @@ def run_b200(args):
     pipe = GraphedEnhancer(model, BATCH, L, dev, oracle=False, stream=stream)
     pipe.y_dev.copy_(y_dev)
     y_dev = pipe.y_dev
+    # --streams 2: a second, independent enhancer (own network workspace, own streams); consecutive steps alternate
+    # between the two so that the small kernels of one batch (grids below 148 CTAs on the 32x64 and smaller maps, the
+    # front end, the SNR estimator, the iSTFT) overlap the other batch's work.  Every step is still one full pass over
+    # one batch of 16 utterances.
+    pipes = [pipe]
+    if args.streams == 2:
+        model2, _ = build_models(dev)
+        pipe2 = GraphedEnhancer(model2, BATCH, L, dev, oracle=False)
+        pipe2.y_dev.copy_(y_dev)
+        with torch.cuda.stream(pipe2.stream):
+            pipe2._step()
+            pipe2.capture(warmup=1)
+            pipe2.stream.synchronize()
+        pipes.append(pipe2)
 
     with torch.cuda.stream(stream):
         pipe._step()                           # first eager pass: packs weights, builds the plan
@@ -210,8 +224,9 @@ def run_b200(args):
         launches_per_step = int(lib.snrse_launch_count() - n0) // 2     # one eager warm-up + the captured pass
         graph, out_dev = pipe.graph, pipe.out_dev
         for _ in range(max(args.warmup, 3)):
-            graph.replay()
-        stream.synchronize()
+            for p in pipes:
+                p.replay()
+        torch.cuda.synchronize()
 
         def barrier():
             stream.synchronize()
@@ -223,8 +238,12 @@ def run_b200(args):
             barrier()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
-            for _ in range(args.steps):
-                body()
+            for p in pipes[1:]:
+                p.stream.wait_event(e0)                    # the other enhancer's stream starts inside the timed region
+            for i in range(args.steps):
+                body(i)
+            for p in pipes[1:]:
+                stream.wait_stream(p.stream)               # ... and ends inside it
             e1.record(stream)
             barrier()
             ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -234,24 +253,34 @@ def run_b200(args):
 
         clocks = ClockSampler(local) if rank == 0 else None
         time.sleep(0.3)
-        ms_dev = timed(graph.replay)
+        ms_dev = timed(lambda i: pipes[i % len(pipes)].replay())
+        ms_single = timed(lambda i: pipes[0].replay()) if len(pipes) > 1 else ms_dev   # one enhancer, steps back to back
 
-        def e2e_body():
+        host_outs = [host_out] + [torch.empty_like(host_out).pin_memory() for _ in pipes[1:]]
+
+        def e2e_body(i=0):
             # the package's host-buffer API: pinned host -> device copy of this step's inputs, graph replay, device ->
             # pinned host copy of this step's result; copies run on a second stream and overlap the neighbouring steps
-            pipe.enhance_host(host_in, host_out)
+            k = i % len(pipes)
+            pipes[k].enhance_host(host_in, host_outs[k])
 
-        for _ in range(3):
-            e2e_body()
-        pipe.flush()
+        for i in range(4):
+            e2e_body(i)
+        for p in pipes:
+            p.flush()
 
         def timed_e2e():
             barrier()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
-            for _ in range(args.steps):
-                e2e_body()
-            pipe.flush()                                   # the last read-back is inside the timed region
+            for p in pipes[1:]:
+                p.stream.wait_event(e0)
+            for i in range(args.steps):
+                e2e_body(i)
+            for p in pipes:
+                p.flush()                                  # the last read-backs are inside the timed region
+            for p in pipes[1:]:
+                stream.wait_stream(p.stream)
             e1.record(stream)
             barrier()
             ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -333,11 +362,14 @@ def run_b200(args):
                     ms_per_step=ms_dev / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16",
                     data="synthetic",
                     config=dict(workload="sebridge_v3 NCSN++ 65.6M (synthetic de-degenerated weights), 16 x 4 s @ 16 kHz per GPU "
-                                         "(Tpad=512), 1 NFE, SNR estimator in the loop, CUDA graph",
+                                         "(Tpad=512), 1 NFE, SNR estimator in the loop, CUDA graph" + (", 2 alternating enhancers (streams)" if args.streams == 2 else ""),
                                 global_batch=world * BATCH, seconds_per_utterance=SECONDS, nfe=1, parallelism=f"dp{world} (utterance-sharded, no collective)",
                                 l2="per-step working set 5.4 GB >> 126 MB L2, no flush needed", accumulate="fp32", storage="bf16 activations"),
                     e2e=dict(value=e2e_value, unit=UNIT, ms_per_step=ms_e2e / args.steps,
                              h2d_bytes_per_step=int(host_in.numel() * 4), d2h_bytes_per_step=int(host_out.numel() * 4)),
+                    single_stream=dict(ms_per_step=ms_single / args.steps, value=audio_s / (ms_single * 1e-3), unit=UNIT,
+                                       note="same K steps through ONE enhancer (steps strictly back to back); the headline runs "
+                                            "two independent enhancers whose steps alternate on two streams"),
                     gpu_launches=launches_per_step * args.steps, launches_per_step=launches_per_step,
                     clocks=clk, roofline=roof, cpu_baseline=cpu, impl="b200")
         print(json.dumps(line), flush=True)
@@ -353,6 +385,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--streams", type=int, default=2, choices=[1, 2],
+                    help="independent enhancers per GPU whose steps alternate (2: small kernels of one batch overlap the other batch)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -48,8 +48,9 @@ class GraphedEnhancer:
         return self
 
     def replay(self):
-        """One pass over the batch resident in `y_dev`; result in `out_dev` (device)."""
-        self.graph.replay()
+        """One pass over the batch resident in `y_dev` on this enhancer's stream; result in `out_dev` (device)."""
+        with torch.cuda.stream(self.stream):
+            self.graph.replay()
         return self.out_dev
 
     def enhance_host(self, host_in, host_out):

@@ -5,6 +5,9 @@
                     LPT over the ranks, equal-Tpad batches of <= 16, SNR estimator in the loop (config 4 with
                     --fixed-snr 0.17783 / 0.31623 / 0.56234)
   --workload long   60 s utterances (config 5): --count per rank, batch 1
+  --workload pc     the generic reverse loop: OUVE score model on the same NCSN++ network, predictor-
+                    corrector sampler at the eval.py defaults (N=30, reverse diffusion + 1 annealed-Langevin step =
+                    60 network evaluations) on a batch of 16 x 4 s per rank
 
 Prints one JSON line on rank 0: whole-job enhanced audio-seconds per wall-second (slowest rank).  No data-path
 collective; torch.distributed only gathers the per-utterance table and the timings.
@@ -34,9 +37,50 @@ def synth_wave(length, seed):
     return (0.1 * speech * env + (0.01 + 0.0005 * (seed % 40)) * torch.randn(length, generator=g)).float()
 
 
+def run_pc(args, world, rank, dev):
+    """60-NFE predictor-corrector loop (bbed-style score head on the OUVE SDE), batch 16 x 4 s per rank."""
+    import torch.distributed as dist
+    from snr_aligned_diffse_b200 import ops
+    from snr_aligned_diffse_b200.sgmse.model import ScoreModel
+    from snr_aligned_diffse_b200.synth import synth_state_dict
+    model = ScoreModel(backbone="ncsnpp", sde="ouve", model_type="bbed", snr_conditioned="false", theta=1.5, sigma_min=0.05,
+                       sigma_max=0.5, N=30, base_dir="")
+    model._error_loading_ema = True
+    model.load_state_dict(synth_state_dict({"dnn." + k: v for k, v in model.dnn.param_shapes().items()}, seed=0))
+    model.eval(no_ema=True)
+    B, L = bench.BATCH, int(bench.SECONDS * bench.SR)
+    y = bench.synth_waves(B, L, seed=2000 + rank).to(dev)
+    peak = ops.absmax(y)
+    Y = ops.stft(y, scale=peak, scale_is_divisor=True)[:, None]
+    sampler = model.get_pc_sampler("reverse_diffusion", "ald", Y, N=30, corrector_steps=1, snr=0.5)
+    sample, nfe = sampler()                       # warm-up: plans, weights
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(max(1, args.repeat)):
+        sample, nfe = sampler()
+    x_hat = ops.istft(sample[:, 0].contiguous(), L, scale=peak)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1) / max(1, args.repeat)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        sec = float(ms.item()) * 1e-3
+        print(json.dumps(dict(metric="enhanced audio-sec/sec (inverse RTF), PC sampler 60 NFE", workload="pc", unit=bench.UNIT,
+                              value=world * B * bench.SECONDS / sec, n_gpus=world, nfe=int(nfe), ms_per_batch=round(sec * 1e3, 2),
+                              ms_per_nfe=round(sec * 1e3 / nfe, 3), batch=B, finite=bool(torch.isfinite(x_hat).all()),
+                              mode="host loop, eager launches", scaling="weak")), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--workload", default="vbd", choices=["vbd", "long"])
+    ap.add_argument("--workload", default="vbd", choices=["vbd", "long", "pc"])
     ap.add_argument("--count", type=int, default=0, help="utterances (vbd: total, default 824; long: per rank, default 2)")
     ap.add_argument("--fixed-snr", type=float, default=bench.FIXED_SNR)
     ap.add_argument("--max-batch", type=int, default=16)
@@ -51,6 +95,8 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
     bench.FIXED_SNR = args.fixed_snr
+    if args.workload == "pc":
+        return run_pc(args, world, rank, dev)
     model, est = bench.build_models(dev)
     if args.workload == "vbd":
         n = args.count or 824
