@@ -136,6 +136,13 @@ class NCSNppEngine:
             _lib.check(1, "plan")
         return n
 
+    def reserve(self, nbytes):
+        """One shared activation arena of `nbytes` for every plan created from now on (instead of one buffer per
+        (B,F,T) bucket).  Forwards of one engine run on one stream, so all buckets can live in the same memory: a sweep
+        over many utterance lengths then needs the LARGEST bucket's workspace, not the sum over buckets."""
+        self._arena = torch.empty(int(nbytes) + 1024, dtype=torch.uint8, device=self.device)
+        return self
+
     def prepare(self, B, F, T, flags=0):
         key = (B, F, T)
         cur = self._ws.get(key)
@@ -144,7 +151,8 @@ class NCSNppEngine:
         if self.blob is None:
             raise RuntimeError("load_state_dict() first")
         n = self.workspace_bytes(B, F, T, flags)
-        ws = torch.empty(n + 1024, dtype=torch.uint8, device=self.device)
+        arena = getattr(self, "_arena", None)
+        ws = arena if (arena is not None and arena.numel() >= n + 1024) else torch.empty(n + 1024, dtype=torch.uint8, device=self.device)
         base = ws.data_ptr()
         aligned = (base + 1023) // 1024 * 1024
         _lib.check(self.lib.snrse_ncsnpp_plan_bind(self.h, B, F, T, c_void_p(aligned), n), "plan_bind")

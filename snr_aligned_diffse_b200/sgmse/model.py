@@ -235,6 +235,22 @@ class ScoreModel(CheckpointedModule):
             return x_hat, dict(t=t, t_index=idx, norm_factor=norm, Y=Y, X_T=X_T, sample=sample, ratio=ratio)
         return x_hat
 
+    def enhance_snr_sweep(self, x, noise, snrs=range(0, 41, 5), oracle=True, noise_draws=None):
+        """The SNR sweep of deep_eval.py:112-122 for one file as ONE batch: for every SNR in `snrs` the mixture
+        y = x + noise * 10^(-SNR/20) is enhanced with clean_rms = 1, noise_rms = 10^((-SNR+5)/20) (oracle) or with the
+        SNR estimator (oracle=False).  x, noise: [1, L] waveforms (clean, y - x).  Returns a list of 1-D float32 numpy
+        arrays, one per SNR, equal to what `enhance` returns for each mixture on its own.
+        noise_draws: optional explicit complex normal draws [len(snrs), 1, 256, Tpad]."""
+        snrs = list(snrs)
+        xd = (x if x.is_cuda else x.cuda()).to(torch.float32).reshape(1, -1)
+        nd = (noise if noise.is_cuda else noise.cuda()).to(torch.float32).reshape(1, -1)
+        gains = torch.tensor([10.0 ** (-s / 20.0) for s in snrs], dtype=torch.float32, device=xd.device)[:, None]
+        y = xd + nd * gains                                                   # [len(snrs), L]
+        ratios = [10.0 ** ((-s + 5) / 20.0) for s in snrs] if oracle else None
+        out = self.enhance_batch(y, oracle=oracle, noise_over_clean=ratios, noise=noise_draws)
+        out = out.detach().cpu().numpy()
+        return [out[k] for k in range(len(snrs))]
+
     def enhance(self, x, y, sampler_type="pc", predictor="reverse_diffusion", corrector="ald", N=30,
                 corrector_steps=1, snr=0.5, timeit=False, oracle=False, clean_rms=1, noise_rms=1, **kwargs):
         """One-call enhancement of noisy speech `y` [1,L] (model.py:702-839).  `x` (clean) is accepted for

@@ -208,3 +208,19 @@ def test_graphed_enhancer_pipeline_matches_eager(v3):
     for a, o in zip(ins, outs):
         ref = v3.enhance_batch(a.cuda(), oracle=True, noise_over_clean=[0.4, 0.2], noise=Z).cpu()
         assert torch.equal(o, ref)
+
+
+def test_snr_sweep_batch_equals_per_snr_calls(v3):
+    """deep_eval.py's nine-SNR loop as one batch == nine separate enhance() calls (same noise draws), bit for bit."""
+    g = torch.Generator().manual_seed(31)
+    L = 9000
+    x = (0.1 * torch.sin(torch.arange(L) * 0.04) * (1 + 0.5 * torch.sin(torch.arange(L) * 0.001)))[None]
+    n0 = torch.randn(1, L, generator=g) * 0.05
+    snrs = list(range(0, 41, 5))
+    Z = torch.view_as_complex(torch.randn(len(snrs), 1, 256, 128, 2, generator=g) * 0.5 ** 0.5)
+    sweep = v3.enhance_snr_sweep(x, n0, snrs, oracle=True, noise_draws=Z)
+    assert len(sweep) == 9 and all(o.shape == (L,) for o in sweep)
+    for k, s in enumerate(snrs):
+        y = x + n0 * 10 ** (-s / 20)
+        one = v3.enhance(x, y, oracle=True, clean_rms=1, noise_rms=10 ** ((-s + 5) / 20), noise=Z[k:k + 1])
+        assert np.array_equal(one, sweep[k]), s

@@ -1,0 +1,35 @@
+#!/usr/bin/env python
+"""Per-kind time of one NCSN++ forward for a (B, T) bucket, measured with CUDA events between launch groups
+(snrse_ncsnpp_profile_forward).  Usage: python tools/profile_shape.py B T [flags]"""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle.topology import NCSNppConfig, param_specs  # noqa: E402
+from snr_aligned_diffse_b200.engine import NCSNppEngine  # noqa: E402
+from snr_aligned_diffse_b200.synth import synth_state_dict  # noqa: E402
+
+B, T = int(sys.argv[1]), int(sys.argv[2])
+flags = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+eng = NCSNppEngine().load_state_dict(synth_state_dict(param_specs(NCSNppConfig()), seed=0), "cuda")
+g = torch.Generator().manual_seed(0)
+x = torch.view_as_complex(torch.randn(B, 256, T, 2, generator=g)).cuda()
+y = torch.view_as_complex(torch.randn(B, 256, T, 2, generator=g)).cuda()
+t = torch.full((B,), 0.5, device="cuda")
+names = {0: "other", 1: "conv_tcgen05", 2: "groupnorm", 3: "fir", 4: "attention", 5: "thin_conv", 6: "pack_temb_head"}
+for _ in range(2):
+    prof = eng.profile_forward(x, y, t, mode=1)
+tot = sum(p["ms"] for p in prof)
+by = {}
+for p in prof:
+    d = by.setdefault(names[p["kind"]], [0.0, 0, 0.0])
+    d[0] += p["ms"]; d[1] += 1; d[2] += p["flops"]
+print(f"B={B} T={T}: {tot:.3f} ms per forward, {B * T * 128 / 16000 / (tot * 1e-3):.0f} audio-s/s (network only)")
+for k, (ms, n, fl) in by.items():
+    extra = f"  {fl / (ms * 1e-3) / 1e12:.0f} TFLOP/s" if fl > 0 else ""
+    print(f"  {k:16s} {ms:8.3f} ms {n:4d} groups {100 * ms / tot:5.1f} %{extra}")
+slow = sorted(prof, key=lambda p: -p["ms"])[:8]
+print("  slowest groups:", [(names[p["kind"]], round(p["ms"], 3)) for p in slow])
