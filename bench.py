@@ -156,8 +156,9 @@ def _cpu_model():
     return "unknown"
 
 
-def build_models(device):
-    """Score model + SNR estimator with seeded synthetic weights, packed on `device`."""
+def build_models(device, with_estimator=True):
+    """Score model + SNR estimator with seeded synthetic weights, packed on `device`.  with_estimator=False: another
+    score model that shares the process-wide estimator already installed (sgmse.model.set_snr_model)."""
     from snr_aligned_diffse_b200.sgmse import model as sg_model
     from snr_aligned_diffse_b200.sgmse.model import ScoreModel
     from snr_aligned_diffse_b200.sgmse.snr_estimator import SNRModel
@@ -167,6 +168,8 @@ def build_models(device):
     model._error_loading_ema = True
     model.load_state_dict(synth_state_dict({"dnn." + k: v for k, v in model.dnn.param_shapes().items()}, seed=0))
     model.eval(no_ema=True)
+    if not with_estimator:
+        return model, sg_model.get_snr_model()
     est = SNRModel(base_dir="")
     est._error_loading_ema = True
     est.load_state_dict(synth_state_dict(est.dnn.engine.param_shapes(), seed=1))
@@ -206,8 +209,8 @@ def run_b200(args):
     # front end, the SNR estimator, the iSTFT) overlap the other batch's work.  Every step is still one full pass over
     # one batch of 16 utterances.
     pipes = [pipe]
-    if args.streams == 2:
-        model2, _ = build_models(dev)
+    for _ in range(args.streams - 1):
+        model2, _ = build_models(dev, with_estimator=False)   # the estimator (weights, read-only) is shared
         pipe2 = GraphedEnhancer(model2, BATCH, L, dev, oracle=False)
         pipe2.y_dev.copy_(y_dev)
         with torch.cuda.stream(pipe2.stream):
@@ -362,7 +365,7 @@ def run_b200(args):
                     ms_per_step=ms_dev / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16",
                     data="synthetic",
                     config=dict(workload="sebridge_v3 NCSN++ 65.6M (synthetic de-degenerated weights), 16 x 4 s @ 16 kHz per GPU "
-                                         "(Tpad=512), 1 NFE, SNR estimator in the loop, CUDA graph" + (", 2 alternating enhancers (streams)" if args.streams == 2 else ""),
+                                         "(Tpad=512), 1 NFE, SNR estimator in the loop, CUDA graph" + (f", {args.streams} alternating enhancers (streams)" if args.streams > 1 else ""),
                                 global_batch=world * BATCH, seconds_per_utterance=SECONDS, nfe=1, parallelism=f"dp{world} (utterance-sharded, no collective)",
                                 l2="per-step working set 5.4 GB >> 126 MB L2, no flush needed", accumulate="fp32", storage="bf16 activations"),
                     e2e=dict(value=e2e_value, unit=UNIT, ms_per_step=ms_e2e / args.steps,
@@ -385,7 +388,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--streams", type=int, default=2, choices=[1, 2],
+    ap.add_argument("--streams", type=int, default=2, choices=[1, 2, 3, 4],
                     help="independent enhancers per GPU whose steps alternate (2: small kernels of one batch overlap the other batch)")
     args = ap.parse_args()
     if args.impl == "reference":
