@@ -53,7 +53,8 @@ int snrse_stft(const float* wave, const int* len, const float* scale, int scale_
                        beta, planar, S(stream));
 }
 
-int64_t snrse_istft_workspace_bytes(int B, int tpad) { return (int64_t)B * tpad * 512 * 4; }
+// the overlap-add runs in shared memory since the FFT kernels; a token workspace keeps the ABI and its callers unchanged
+int64_t snrse_istft_workspace_bytes(int B, int tpad) { (void)B; (void)tpad; return 256; }
 
 int snrse_istft(const void* spec, const int* len, const float* scale, float* wave, void* workspace, int B, int lstride,
                 int tpad, int transform, float alpha, float beta, void* stream) {

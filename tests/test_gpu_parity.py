@@ -67,7 +67,7 @@ def test_stft_matches_oracle_and_golden(ops, golden_dir):
     assert torch.count_nonzero(torch.view_as_real(Y[..., nf:])) == 0           # pad_spec region is exactly zero
     ref = _c(z["spec"]).squeeze(1)
     peak = ref.abs().max()
-    assert (Y.cpu() - ref).abs().max() <= 2e-5 * peak                           # fp32 direct DFT vs torch.stft
+    assert (Y.cpu() - ref).abs().max() <= 2e-5 * peak                           # fp32 shared-memory FFT vs torch.stft
     raw = ops.stft(wave, transform=False, tpad=nf)
     assert (raw.cpu() - _c(z["stft"])).abs().max() <= 2e-5 * _c(z["stft"]).abs().max()
     # SNR-branch features: y / max|y|, raw STFT, planar re/im, padded to a multiple of 16 (model.py:715-719)
