@@ -138,6 +138,15 @@ int snrse_groupnorm_nhwc(const void* x, const float* gamma, const float* beta, v
  * op/upfirdn2d.cpp:12-23, op/upfirdn2d_kernel.cu modes 3 and 5) */
 int snrse_fir_nhwc(const void* x, void* out, int B, int H, int W, int C, int up, void* stream);
 int snrse_fir_f4(const float* x, float* out, int B, int H, int W, int up, void* stream);
+/* snrse_upfirdn2d: the reference's one native operator, general form -- replaces
+ *   `upfirdn2d_op.upfirdn2d(input[N,H,W,1], kernel[kh,kw], up_x, up_y, down_x, down_y, pad_x0, pad_x1, pad_y0, pad_y1)`
+ *   (ncsnpp_utils/op/upfirdn2d.cpp:12-23, op/upfirdn2d_kernel.cu:213-311; pure-torch statement op/upfirdn2d.py:159-200).
+ *   input fp32 [major][in_h][in_w] (minor = 1 as every reference call site passes), kernel fp32 [kh][kw] (device),
+ *   out fp32 [major][out_h][out_w] with out_h = (in_h*up_y + pad_y0 + pad_y1 - kh)/down_y + 1 (same for w); negative
+ *   pads crop.  The caller allocates `out`; launches on `stream`; no synchronisation. */
+int snrse_upfirdn2d(const float* input, const float* kernel, float* out, int64_t major, int in_h, int in_w, int kernel_h,
+                    int kernel_w, int up_x, int up_y, int down_x, int down_y, int pad_x0, int pad_x1, int pad_y0, int pad_y1,
+                    void* stream);
 /* FIR resampling of silu(GroupNorm32(x)), normalisation applied on load (layerspp.py:245-257); workspace:
  * snrse_groupnorm_workspace_bytes(B) */
 int snrse_gn_silu_fir_nhwc(const void* x, const float* gamma, const float* beta, float eps, void* out, int B, int H, int W,

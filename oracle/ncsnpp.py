@@ -181,3 +181,24 @@ def ncsnpp_forward(sd, x, t, cfg: NCSNppConfig = NCSNppConfig(), prefix: str = "
     h = F.conv2d(h, sd[prefix + "output_layer.weight"], sd[prefix + "output_layer.bias"])  # :401
     h = h.permute(0, 2, 3, 1).contiguous()
     return torch.view_as_complex(h)[:, None]
+
+
+def upfirdn2d_general(x, kernel, up_x, up_y, down_x, down_y, pad_x0, pad_x1, pad_y0, pad_y1):
+    """General upfirdn2d restated in numpy float64 loops over taps (ncsnpp_utils/op/upfirdn2d.py:159-200):
+    zero-insert by (up_x, up_y), pad (negative = crop), correlate with the flipped kernel, keep every
+    (down_y, down_x)-th sample.  x [N, C, H, W], kernel [kh, kw] -> float32 tensor [N, C, out_h, out_w]."""
+    import numpy as np
+    xn = np.asarray(x, dtype=np.float64)
+    kn = np.asarray(kernel, dtype=np.float64)
+    N, C, H, W = xn.shape
+    kh, kw = kn.shape
+    U = np.zeros((N, C, H * up_y, W * up_x))
+    U[:, :, ::up_y, ::up_x] = xn
+    P = np.pad(U, ((0, 0), (0, 0), (max(pad_y0, 0), max(pad_y1, 0)), (max(pad_x0, 0), max(pad_x1, 0))))
+    P = P[:, :, max(-pad_y0, 0):P.shape[2] - max(-pad_y1, 0), max(-pad_x0, 0):P.shape[3] - max(-pad_x1, 0)]
+    fh, fw = P.shape[2] - kh + 1, P.shape[3] - kw + 1
+    full = np.zeros((N, C, fh, fw))
+    for ky in range(kh):
+        for kx in range(kw):
+            full += kn[kh - 1 - ky, kw - 1 - kx] * P[:, :, ky:ky + fh, kx:kx + fw]
+    return torch.from_numpy(full[:, :, ::down_y, ::down_x].astype(np.float32))

@@ -51,6 +51,7 @@ PROTOTYPES = {
     "snrse_groupnorm_nhwc": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, vp, vp]),
     "snrse_fir_nhwc": (i32, [vp, vp, i32, i32, i32, i32, i32, vp]),
     "snrse_fir_f4": (i32, [vp, vp, i32, i32, i32, i32, vp]),
+    "snrse_upfirdn2d": (i32, [vp, vp, vp, i64] + [i32] * 12 + [vp]),
     "snrse_gn_silu_fir_nhwc": (i32, [vp, vp, vp, f32, vp, i32, i32, i32, i32, i32, vp, vp]),
     "snrse_attention_workspace_bytes": (i64, [i32, i32, i32]),
     "snrse_attention_nhwc": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, vp]),

@@ -199,6 +199,14 @@ int snrse_gn_silu_fir_nhwc(const void* x, const float* gamma, const float* beta,
     return up ? fir_up2_launch(&vx, &vo, S(stream), scsh) : fir_down2_launch(&vx, &vo, S(stream), scsh);
 }
 
+int snrse_upfirdn2d(const float* input, const float* kernel, float* out, int64_t major, int in_h, int in_w, int kernel_h,
+                    int kernel_w, int up_x, int up_y, int down_x, int down_y, int pad_x0, int pad_x1, int pad_y0, int pad_y1,
+                    void* stream) {
+    SNRSE_CHECK_ARG(input && kernel && out, "upfirdn2d: null pointer");
+    return upfirdn2d_launch(input, kernel, out, major, in_h, in_w, kernel_h, kernel_w, up_x, up_y, down_x, down_y, pad_x0,
+                            pad_x1, pad_y0, pad_y1, S(stream));
+}
+
 int snrse_fir_f4(const float* x, float* out, int B, int H, int W, int up, void* stream) {
     SNRSE_CHECK_ARG(x && out, "fir_f4: null pointer");
     return up ? fir_up2_f4_launch(x, out, B, H, W, S(stream)) : fir_down2_f4_launch(x, out, B, H, W, S(stream));

@@ -256,7 +256,65 @@ fir_up2_f4_kernel(const float4* __restrict__ x, int H, int W, float4* __restrict
     out[idx] = acc;
 }
 
+// General upfirdn2d (ncsnpp_utils/op/upfirdn2d.cpp:12-23; the "large" path of op/upfirdn2d_kernel.cu:25-104 and the
+// pure-torch statement op/upfirdn2d.py:159-200): zero-insertion upsampling by (up_x, up_y), padding (negative = crop),
+// correlation with the flipped kernel, decimation by (down_x, down_y).  fp32 planes [major][in_h][in_w] (the reference
+// always passes minor = 1).  One thread per output sample, filter taps from shared memory; only the taps that land on
+// a real (non-inserted) input sample are visited.
+__global__ void __launch_bounds__(256)
+upfirdn2d_kernel(const float* __restrict__ x, const float* __restrict__ k, float* __restrict__ out, int in_h, int in_w,
+                 int kh, int kw, int up_x, int up_y, int down_x, int down_y, int pad_x0, int pad_y0, int out_h, int out_w,
+                 int64_t total) {
+    extern __shared__ float ks[];
+    for (int i = threadIdx.x; i < kh * kw; i += blockDim.x) ks[i] = k[i];
+    __syncthreads();
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int ox = (int)(idx % out_w);
+    const int64_t r = idx / out_w;
+    const int oy = (int)(r % out_h);
+    const int64_t m = r / out_h;
+    const float* xp = x + m * in_h * in_w;
+    // output (oy, ox) = sum_{ky,kx} k[kh-1-ky][kw-1-kx] * U[oy*down_y + ky - pad_y0][ox*down_x + kx - pad_x0],
+    // U[uy][ux] = x[uy/up_y][ux/up_x] when both divide exactly and the indices are inside the image, else 0
+    const int by = oy * down_y - pad_y0, bx = ox * down_x - pad_x0;
+    int ky0 = ((-by) % up_y + up_y) % up_y;        // first ky with (by + ky) % up_y == 0
+    int kx0 = ((-bx) % up_x + up_x) % up_x;
+    float acc = 0.f;
+    for (int ky = ky0; ky < kh; ky += up_y) {
+        const int uy = by + ky;
+        if (uy < 0) continue;
+        const int iy = uy / up_y;
+        if (iy >= in_h) break;
+        for (int kx = kx0; kx < kw; kx += up_x) {
+            const int ux = bx + kx;
+            if (ux < 0) continue;
+            const int ix = ux / up_x;
+            if (ix >= in_w) break;
+            acc = fmaf(xp[(int64_t)iy * in_w + ix], ks[(kh - 1 - ky) * kw + (kw - 1 - kx)], acc);
+        }
+    }
+    out[idx] = acc;
+}
+
 }  // namespace
+
+int upfirdn2d_launch(const float* x, const float* kernel, float* out, int64_t major, int in_h, int in_w, int kh, int kw,
+                     int up_x, int up_y, int down_x, int down_y, int pad_x0, int pad_x1, int pad_y0, int pad_y1,
+                     cudaStream_t s) {
+    SNRSE_CHECK_ARG(major > 0 && in_h > 0 && in_w > 0 && kh > 0 && kw > 0, "upfirdn2d: empty input or kernel");
+    SNRSE_CHECK_ARG(up_x >= 1 && up_y >= 1 && down_x >= 1 && down_y >= 1, "upfirdn2d: up / down factors must be >= 1");
+    SNRSE_CHECK_ARG(kh * kw <= 4096, "upfirdn2d: kernel larger than 4096 taps");
+    const int out_h = (in_h * up_y + pad_y0 + pad_y1 - kh) / down_y + 1;
+    const int out_w = (in_w * up_x + pad_x0 + pad_x1 - kw) / down_x + 1;
+    SNRSE_CHECK_ARG(in_h * up_y + pad_y0 + pad_y1 >= kh && in_w * up_x + pad_x0 + pad_x1 >= kw && out_h > 0 && out_w > 0,
+                    "upfirdn2d: padded input smaller than the kernel");
+    const int64_t total = major * out_h * out_w;
+    upfirdn2d_kernel<<<(unsigned)cdiv64(total, 256), 256, kh * kw * sizeof(float), s>>>(
+        x, kernel, out, in_h, in_w, kh, kw, up_x, up_y, down_x, down_y, pad_x0, pad_y0, out_h, out_w, total);
+    SNRSE_LAUNCH_CHECK();
+    return SNRSE_OK;
+}
 
 int fir_down2_launch(const ActView* x, const ActView* out, cudaStream_t s, const float* scsh) {
     SNRSE_CHECK_ARG(x->H % 2 == 0 && x->W % 2 == 0 && x->C % 8 == 0, "fir_down2: H, W must be even, C %% 8 == 0");

@@ -120,6 +120,10 @@ int fir_up2_launch(const ActView* x, const ActView* out, cudaStream_t s, const f
 int fir_down2_launch(const ActView* x, const ActView* out, cudaStream_t s, const float* scsh = nullptr);
 int fir_up2_f4_launch(const float* x, float* out, int B, int H, int W, cudaStream_t s);      // in [B,H,W,4]
 int fir_down2_f4_launch(const float* x, float* out, int B, int H, int W, cudaStream_t s);    // in [B,H,W,4]
+// general upfirdn2d on fp32 planes [major][in_h][in_w] (op/upfirdn2d.cpp:12-23)
+int upfirdn2d_launch(const float* x, const float* kernel, float* out, int64_t major, int in_h, int in_w, int kh, int kw,
+                     int up_x, int up_y, int down_x, int down_y, int pad_x0, int pad_x1, int pad_y0, int pad_y1,
+                     cudaStream_t s);
 
 // ----------------------------------------------------------------------------- attention.cu
 // q,k,v: [B, n, C] bf16 views (tokens = H*W); scores: [B, n, n] f32 workspace; o: bf16 view.

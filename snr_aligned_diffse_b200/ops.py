@@ -186,6 +186,30 @@ def fir_nhwc(x, up):
     return out
 
 
+def upfirdn2d(input, kernel, up=(1, 1), down=(1, 1), pad=(0, 0, 0, 0)):
+    """General upfirdn2d (op/upfirdn2d.cpp:12-23): input [N, C, H, W], kernel [kh, kw], up / down = (x, y),
+    pad = (x0, x1, y0, y1) -> [N, C, out_h, out_w] in the input's dtype and on the input's device."""
+    lib = _lib_dev()
+    if input.dim() != 4 or kernel.dim() != 2:
+        raise RuntimeError("upfirdn2d: input must be [N, C, H, W] and kernel [kh, kw]")
+    dev, dt = input.device, input.dtype
+    x = input.to("cuda", torch.float32).contiguous()
+    k = kernel.to("cuda", torch.float32).contiguous()
+    N, C, H, W = x.shape
+    kh, kw = k.shape
+    (ux, uy), (dx, dy), (px0, px1, py0, py1) = up, down, pad
+    if min(ux, uy, dx, dy) < 1:
+        raise RuntimeError("upfirdn2d: up / down factors must be >= 1")
+    oh = (H * uy + py0 + py1 - kh) // dy + 1
+    ow = (W * ux + px0 + px1 - kw) // dx + 1
+    if N * C == 0 or H * uy + py0 + py1 < kh or W * ux + px0 + px1 < kw:
+        raise RuntimeError("upfirdn2d: padded input smaller than the kernel")
+    out = torch.empty(N, C, oh, ow, dtype=torch.float32, device=x.device)
+    _lib.check(lib.snrse_upfirdn2d(_lib.ptr(x), _lib.ptr(k), _lib.ptr(out), N * C, H, W, kh, kw, ux, uy, dx, dy, px0, px1,
+                                   py0, py1, _lib.stream_ptr()), "upfirdn2d")
+    return out.to(dev, dt)
+
+
 def attention_nhwc(q, k, v):
     """q,k,v [B, n, C] bf16 -> [B, n, C] bf16."""
     lib = _lib_dev()

@@ -11,6 +11,8 @@ import sys
 
 _SUBMODULES = ("util", "util.registry", "util.other", "data_module", "sdes", "sampling", "sampling.predictors",
                "sampling.correctors", "backbones", "backbones.shared", "backbones.ncsnpp", "backbones.snrnet",
+               "backbones.ncsnpp_utils", "backbones.ncsnpp_utils.op", "backbones.ncsnpp_utils.op.upfirdn2d",
+               "backbones.ncsnpp_utils.up_or_down_sampling",
                "snr_estimator", "model")
 
 

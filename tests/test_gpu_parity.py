@@ -319,6 +319,39 @@ def test_fir(ops, golden_dir):
         assert ((got - ref).abs() <= 2 ** -8 * ref.abs() + 1e-6).all()
 
 
+def test_upfirdn2d_general_matches_reference_vectors(ops, golden_dir):
+    """snrse_upfirdn2d (the reference's one native operator, general form) vs `upfirdn2d_native` outputs of the
+    unmodified reference: output sizes exact, values within fp32 rounding (1e-6 of the peak)."""
+    from snr_aligned_diffse_b200.sgmse.backbones.ncsnpp_utils import up_or_down_sampling as uds
+    from snr_aligned_diffse_b200.sgmse.backbones.ncsnpp_utils.op.upfirdn2d import upfirdn2d, upfirdn2d_native
+    z = np.load(os.path.join(golden_dir, "upfirdn2d.npz"))
+    for i, c in enumerate(z["cases"]):
+        c = [int(v) for v in c]
+        x, k, ref = _c(z[f"x{i}"]), _c(z[f"k{i}"]), _c(z[f"y{i}"])
+        got = upfirdn2d_native(x.to(DEV), k.to(DEV), *c[6:])
+        assert got.is_cuda and tuple(got.shape) == tuple(ref.shape)
+        assert (got.cpu() - ref).abs().max() <= 2e-6 * max(1.0, float(ref.abs().max()))
+        oracle = o_ncsnpp.upfirdn2d_general(x, k, *c[6:])
+        assert (got.cpu() - oracle).abs().max() <= 2e-6 * max(1.0, float(ref.abs().max()))
+    # the reference's helpers on top of it, CPU tensor in -> CPU tensor out (the reference dispatches on device)
+    fz = np.load(os.path.join(golden_dir, "fir.npz"))
+    x = _c(fz["x"])
+    up, dn = uds.upsample_2d(x, [1, 3, 3, 1], factor=2), uds.downsample_2d(x, [1, 3, 3, 1], factor=2)
+    assert not up.is_cuda and (up - _c(fz["up"])).abs().max() <= 1e-6 and (dn - _c(fz["down"])).abs().max() <= 1e-6
+    assert torch.equal(upfirdn2d(x, torch.ones(2, 2) / 4, down=2), uds.downsample_2d(x, factor=2))   # default k = box
+    # a larger seeded case against the oracle, and half precision in -> half precision out
+    g = torch.Generator().manual_seed(9)
+    xb, kb = torch.randn(3, 5, 33, 47, generator=g), torch.randn(5, 7, generator=g)
+    got = ops.upfirdn2d(xb.to(DEV), kb.to(DEV), (2, 3), (3, 2), (4, 1, 0, 6)).cpu()
+    ref = o_ncsnpp.upfirdn2d_general(xb, kb, 2, 3, 3, 2, 4, 1, 0, 6)
+    assert got.shape == ref.shape and (got - ref).abs().max() <= 1e-5
+    assert ops.upfirdn2d(xb.half().to(DEV), kb.to(DEV), (1, 1), (1, 1), (3, 3, 2, 2)).dtype == torch.float16
+    with pytest.raises(RuntimeError):
+        ops.upfirdn2d(xb[:, :, :2, :2].to(DEV), kb.to(DEV))          # padded input smaller than the kernel
+    with pytest.raises(RuntimeError):
+        ops.upfirdn2d(xb[0].to(DEV), kb.to(DEV))                      # not [N, C, H, W]
+
+
 @pytest.mark.parametrize("shape", [(2, 128, 16, 24), (1, 256, 8, 8), (3, 384, 6, 10)])
 @pytest.mark.parametrize("up", [True, False])
 def test_gn_silu_fir_fused_equals_two_passes(ops, shape, up):

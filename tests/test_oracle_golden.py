@@ -126,3 +126,20 @@ def test_pc_sampler(golden_dir):
     assert (out - ref).abs().max() <= 1e-4 * ref.abs().max()
     b = np.load(os.path.join(golden_dir, "bbed.npz"))
     assert torch.allclose(o_sampler.BBED(0.999, 2.6, 0.52).std(_c(b["t"])), _c(b["std"]), atol=1e-7)
+
+
+def test_upfirdn2d_general_oracle_matches_reference_vectors(golden_dir):
+    """General upfirdn2d restatement vs `upfirdn2d_native` outputs of the reference (oracle/make_golden_upfirdn2d.py)."""
+    z = np.load(os.path.join(golden_dir, "upfirdn2d.npz"))
+    for i, c in enumerate(z["cases"]):
+        c = [int(v) for v in c]
+        got = o_ncsnpp.upfirdn2d_general(z[f"x{i}"], z[f"k{i}"], *c[6:])
+        ref = _c(z[f"y{i}"])
+        assert tuple(got.shape) == tuple(ref.shape)                                  # output size: exact
+        assert (got - ref).abs().max() <= 2e-6 * max(1.0, float(ref.abs().max()))
+    # the two NCSN++ configurations are special cases of the general operator
+    x = _c(np.load(os.path.join(golden_dir, "fir.npz"))["x"])
+    k = np.outer([1, 3, 3, 1], [1, 3, 3, 1]) / 64.0
+    fz = np.load(os.path.join(golden_dir, "fir.npz"))
+    assert (o_ncsnpp.upfirdn2d_general(x, k * 4, 2, 2, 1, 1, 2, 1, 2, 1) - _c(fz["up"])).abs().max() < 1e-6
+    assert (o_ncsnpp.upfirdn2d_general(x, k, 1, 1, 2, 2, 1, 1, 1, 1) - _c(fz["down"])).abs().max() < 1e-6

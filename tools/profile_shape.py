@@ -8,13 +8,13 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from oracle.topology import NCSNppConfig, param_specs  # noqa: E402
 from snr_aligned_diffse_b200.engine import NCSNppEngine  # noqa: E402
 from snr_aligned_diffse_b200.synth import synth_state_dict  # noqa: E402
 
 B, T = int(sys.argv[1]), int(sys.argv[2])
 flags = int(sys.argv[3]) if len(sys.argv) > 3 else 0
-eng = NCSNppEngine().load_state_dict(synth_state_dict(param_specs(NCSNppConfig()), seed=0), "cuda")
+eng = NCSNppEngine()
+eng.load_state_dict(synth_state_dict(eng.param_shapes(), seed=0), "cuda")
 g = torch.Generator().manual_seed(0)
 x = torch.view_as_complex(torch.randn(B, 256, T, 2, generator=g)).cuda()
 y = torch.view_as_complex(torch.randn(B, 256, T, 2, generator=g)).cuda()
@@ -33,3 +33,15 @@ for k, (ms, n, fl) in by.items():
     print(f"  {k:16s} {ms:8.3f} ms {n:4d} groups {100 * ms / tot:5.1f} %{extra}")
 slow = sorted(prof, key=lambda p: -p["ms"])[:8]
 print("  slowest groups:", [(names[p["kind"]], round(p["ms"], 3)) for p in slow])
+# implicit-GEMM convolution launches grouped by (flops, bytes) signature: where the time above the tensor roofline sits
+sig = {}
+for p in prof:
+    if p["kind"] == 1:
+        d = sig.setdefault((p["flops"], p["bytes"]), [0, 0.0])
+        d[0] += 1; d[1] += p["ms"]
+PEAK = 1414.8e12
+rows = sorted(sig.items(), key=lambda kv: -(kv[1][1] - kv[0][0] * kv[1][0] / PEAK * 1e3))
+print("  conv signatures (GFLOP, MB, launches, ms total, TFLOP/s, ms above the sustained-peak time):")
+for (fl, by), (n, ms) in rows[:24]:
+    print(f"    {fl / 1e9:9.1f} GF {by / 1e6:8.1f} MB x{n:3d} {ms:7.3f} ms {fl * n / (ms * 1e-3) / 1e12:7.0f} TF/s "
+          f"{ms - fl * n / PEAK * 1e3:+7.3f} ms")
