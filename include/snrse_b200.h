@@ -51,6 +51,8 @@ int snrse_istft(const void* spec, const int* len, const float* scale, float* wav
 int snrse_spec_transform(const void* in, void* out, int64_t n, int inverse, float alpha, float beta, void* stream);
 /* max|y| per utterance (model.py:715,726) */
 int snrse_absmax(const float* wave, const int* len, int B, int lstride, float* out, void* stream);
+/* SI-SDR in dB of est[b][0..len[b]) against ref[b] (util/other.py:71-75; B/eval.py:140-144), double accumulation */
+int snrse_si_sdr(const float* ref, const float* est, const int* len, int B, int lstride, double* out, void* stream);
 
 /* ---------------------------------------------------------------- SNR -> timestep --------------
  * calculate_snr_direct + t_30 snap + calculate_normfac_direct (model.py:22-23,627-634,726-740):
@@ -67,6 +69,18 @@ int snrse_snr_ratio(const float* g, float* ratio, int B, void* stream);  /* est_
  * and X_T = Y + sigma*t*Z (model.py:822-823). */
 int snrse_lincomb(const void* x, const void* y, const void* s, const void* z, const float* a, const float* b,
                   const float* c, const float* d, void* out_mean, void* out_x, int B, int64_t n, void* stream);
+
+/* Embedded Runge-Kutta helpers for the probability-flow ODE sampler kept on the device (replaces the numpy round trip
+ * per RHS evaluation of `ode_sampler`, sampling/__init__.py:149-161; step control follows scipy.integrate RK45, the
+ * third-party solver the reference calls at :156).  K: nk (<= 8) stage derivatives of n complex64 values each, back
+ * to back; coef: nk HOST floats.
+ *   snrse_rk_combine       : out = y + h * sum_j coef[j] K[j]                       (y may be NULL)
+ *   snrse_rk_scaled_sqnorm : partial[i] (i < snrse_rk_partials(n), device doubles) = block sums of
+ *                            |h * sum_j coef[j] K[j]|^2 / (atol + rtol * max(|y|, |y2|))^2   (y2 may be NULL) */
+int snrse_rk_combine(const void* y, const void* K, int nk, int64_t n, float h, const float* coef, void* out, void* stream);
+int snrse_rk_partials(int64_t n);
+int snrse_rk_scaled_sqnorm(const void* K, int nk, int64_t n, float h, const float* coef, const void* y, const void* y2,
+                           float atol, float rtol, double* partial, void* stream);
 
 /* ---------------------------------------------------------------- NCSN++ score network ---------
  * Replaces NCSNpp.forward (backbones/ncsnpp.py:247-404) and the head of ScoreModel.forward

@@ -25,10 +25,14 @@ PROTOTYPES = {
     "snrse_istft_workspace_bytes": (i64, [i32, i32]),
     "snrse_istft": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, f32, vp]),
     "snrse_spec_transform": (i32, [vp, vp, i64, i32, f32, f32, vp]),
+    "snrse_si_sdr": (i32, [vp, vp, vp, i32, i32, vp, vp]),
     "snrse_absmax": (i32, [vp, vp, i32, i32, vp, vp]),
     "snrse_v3_scalars": (i32, [vp, vp, f64, f32, vp, vp, vp, vp, i32, vp]),
     "snrse_snr_ratio": (i32, [vp, vp, i32, vp]),
     "snrse_lincomb": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i64, vp]),
+    "snrse_rk_combine": (i32, [vp, vp, i32, i64, f32, vp, vp, vp]),
+    "snrse_rk_partials": (i32, [i64]),
+    "snrse_rk_scaled_sqnorm": (i32, [vp, i32, i64, f32, vp, vp, vp, f32, f32, vp, vp]),
     "snrse_ncsnpp_create": (i32, [POINTER(vp), i32, POINTER(i32), i32, i32, POINTER(i32), i32, i32]),
     "snrse_ncsnpp_destroy": (None, [vp]),
     "snrse_ncsnpp_num_modules": (i32, [vp]),

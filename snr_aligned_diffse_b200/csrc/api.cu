@@ -68,6 +68,10 @@ int snrse_spec_transform(const void* in, void* out, int64_t n, int inverse, floa
     return spec_transform_launch(static_cast<const float2*>(in), static_cast<float2*>(out), n, inverse, alpha, beta, S(stream));
 }
 
+int snrse_si_sdr(const float* ref, const float* est, const int* len, int B, int lstride, double* out, void* stream) {
+    return si_sdr_launch(ref, est, len, B, lstride, out, S(stream));
+}
+
 int snrse_absmax(const float* wave, const int* len, int B, int lstride, float* out, void* stream) {
     SNRSE_CHECK_ARG(wave && out, "absmax: null pointer");
     return absmax_launch(wave, len, B, lstride, out, S(stream));
@@ -86,6 +90,19 @@ int snrse_lincomb(const void* x, const void* y, const void* sc, const void* z, c
     return lincomb_launch(static_cast<const float2*>(x), static_cast<const float2*>(y), static_cast<const float2*>(sc),
                           static_cast<const float2*>(z), a, b, c, d, static_cast<float2*>(out_mean),
                           static_cast<float2*>(out_x), B, n, S(stream));
+}
+
+int snrse_rk_combine(const void* y, const void* K, int nk, int64_t n, float h, const float* coef, void* out, void* stream) {
+    return rk_combine_launch(static_cast<const float2*>(y), static_cast<const float2*>(K), nk, n, h, coef,
+                             static_cast<float2*>(out), S(stream));
+}
+
+int snrse_rk_partials(int64_t n) { return rk_partials(n); }
+
+int snrse_rk_scaled_sqnorm(const void* K, int nk, int64_t n, float h, const float* coef, const void* y, const void* y2,
+                           float atol, float rtol, double* partial, void* stream) {
+    return rk_scaled_sqnorm_launch(static_cast<const float2*>(K), nk, n, h, coef, static_cast<const float2*>(y),
+                                   static_cast<const float2*>(y2), atol, rtol, partial, S(stream));
 }
 
 // ---- single-operator entry points (NHWC bf16), used by the parity tests and usable as drop-in ops

@@ -153,6 +153,13 @@ int final_launch(const float* p4, const float* t, const float* w, const float* b
 int lincomb_launch(const float2* x, const float2* y, const float2* sc, const float2* z, const float* a, const float* b,
                    const float* c, const float* d, float2* out_mean, float2* out_x, int B, int64_t n, cudaStream_t s);
 
+// embedded Runge-Kutta helpers of the on-device ODE sampler (coef: nk host floats; K: nk stages of n complex values)
+int rk_combine_launch(const float2* y, const float2* K, int nk, int64_t n, float h, const float* coef, float2* out,
+                      cudaStream_t s);
+int rk_partials(int64_t n);
+int rk_scaled_sqnorm_launch(const float2* K, int nk, int64_t n, float h, const float* coef, const float2* y,
+                            const float2* y2, float atol, float rtol, double* partial, cudaStream_t s);
+
 // SNR -> (snapped t, norm factor): ratio[b] = noise/clean amplitude ratio, peak[b] = max|y|, t30: 30 doubles (device)
 int v3_scalars_launch(const float* ratio, const float* peak, double snr_scale, float nf_const, const double* t30,
                       float* t_out, float* nf_out, int* idx_out, int B, cudaStream_t s);
@@ -164,5 +171,6 @@ int stft_launch(const float* wave, const int* len, const float* scale, int scale
                 int lstride, int tpad, int transform, float alpha, float beta, int planar, cudaStream_t s);
 int spec_transform_launch(const float2* in, float2* out, int64_t n, int inverse, float alpha, float beta, cudaStream_t s);
 int absmax_launch(const float* wave, const int* len, int B, int lstride, float* out, cudaStream_t s);
+int si_sdr_launch(const float* ref, const float* est, const int* len, int B, int lstride, double* out, cudaStream_t s);
 int istft_launch(const float2* spec, const int* len, const float* scale, float* wave, float* frames_ws, int B,
                  int lstride, int tpad, int transform, float alpha, float beta, cudaStream_t s);

@@ -120,7 +120,88 @@ __global__ void snr_ratio_kernel(const float* __restrict__ g, float* __restrict_
     if (b < B) ratio[b] = g[b] / (1.0f - g[b]);
 }
 
+// ---- embedded Runge-Kutta (Dormand-Prince 5(4)) helpers for the on-device probability-flow ODE sampler, replacing
+// scipy.integrate.solve_ivp's numpy round trip per RHS evaluation (sampling/__init__.py:149-161).
+struct RKCoef {
+    float v[8];
+};
+
+// out = y + h * sum_{j<nk} c[j] * K[j]   (K: nk stage derivatives, n complex values each, back to back)
+__global__ void __launch_bounds__(256)
+rk_combine_kernel(const float2* __restrict__ y, const float2* __restrict__ K, int nk, float h, RKCoef c,
+                  float2* __restrict__ out, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float re = 0.f, im = 0.f;
+    for (int j = 0; j < nk; ++j) {
+        if (c.v[j] == 0.f) continue;
+        const float2 k = K[(int64_t)j * n + i];
+        re = fmaf(c.v[j], k.x, re);
+        im = fmaf(c.v[j], k.y, im);
+    }
+    float2 v = make_float2(h * re, h * im);
+    if (y) { const float2 b = y[i]; v.x += b.x; v.y += b.y; }
+    out[i] = v;
+}
+
+// partial[block] = sum over the block's elements of |h * sum_j c[j] K[j]|^2 / (atol + rtol * max(|y|, |y2|))^2 in
+// double; fixed grid + fixed reduction tree, so the sum (and with it every accept / reject decision) is reproducible.
+__global__ void __launch_bounds__(256)
+rk_scaled_sqnorm_kernel(const float2* __restrict__ K, int nk, float h, RKCoef c, const float2* __restrict__ y,
+                        const float2* __restrict__ y2, float atol, float rtol, double* __restrict__ partial, int64_t n) {
+    __shared__ double sm[8];
+    double acc = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        float re = 0.f, im = 0.f;
+        for (int j = 0; j < nk; ++j) {
+            if (c.v[j] == 0.f) continue;
+            const float2 k = K[(int64_t)j * n + i];
+            re = fmaf(c.v[j], k.x, re);
+            im = fmaf(c.v[j], k.y, im);
+        }
+        re *= h;
+        im *= h;
+        const float2 a = y[i];
+        float mag = sqrtf(a.x * a.x + a.y * a.y);
+        if (y2) { const float2 b = y2[i]; mag = fmaxf(mag, sqrtf(b.x * b.x + b.y * b.y)); }
+        const double sc = (double)atol + (double)rtol * (double)mag;
+        acc += ((double)re * re + (double)im * im) / (sc * sc);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += sm[w];
+        partial[blockIdx.x] = t;
+    }
+}
+
 }  // namespace
+
+int rk_combine_launch(const float2* y, const float2* K, int nk, int64_t n, float h, const float* coef, float2* out,
+                      cudaStream_t s) {
+    SNRSE_CHECK_ARG(K && out && coef && nk >= 1 && nk <= 8 && n > 0, "rk_combine: bad arguments (1..8 stages)");
+    RKCoef c;
+    for (int j = 0; j < 8; ++j) c.v[j] = j < nk ? coef[j] : 0.f;
+    rk_combine_kernel<<<(unsigned)cdiv64(n, 256), 256, 0, s>>>(y, K, nk, h, c, out, n);
+    SNRSE_LAUNCH_CHECK();
+    return SNRSE_OK;
+}
+
+int rk_partials(int64_t n) { return (int)(cdiv64(n, 256 * 8) < 1024 ? (cdiv64(n, 256 * 8) > 0 ? cdiv64(n, 256 * 8) : 1) : 1024); }
+
+int rk_scaled_sqnorm_launch(const float2* K, int nk, int64_t n, float h, const float* coef, const float2* y,
+                            const float2* y2, float atol, float rtol, double* partial, cudaStream_t s) {
+    SNRSE_CHECK_ARG(K && y && coef && partial && nk >= 1 && nk <= 8 && n > 0, "rk_scaled_sqnorm: bad arguments");
+    RKCoef c;
+    for (int j = 0; j < 8; ++j) c.v[j] = j < nk ? coef[j] : 0.f;
+    rk_scaled_sqnorm_kernel<<<rk_partials(n), 256, 0, s>>>(K, nk, h, c, y, y2, atol, rtol, partial, n);
+    SNRSE_LAUNCH_CHECK();
+    return SNRSE_OK;
+}
+
 
 int v3_scalars_launch(const float* ratio, const float* peak, double snr_scale, float nf_const, const double* t30,
                       float* t_out, float* nf_out, int* idx_out, int B, cudaStream_t s) {

@@ -399,7 +399,58 @@ spec_transform_kernel(const float2* __restrict__ in, float2* __restrict__ out, i
     out[i] = z;
 }
 
+// SI-SDR of an enhanced batch against clean references on the device (util/other.py:71-75, evaluated per utterance
+// in B/eval.py:140-144 on host numpy arrays): alpha = <s_hat, s> / |s|^2;  10 log10(|alpha s|^2 / |alpha s - s_hat|^2).
+// One block per utterance, two passes (alpha, then the two energies) in double with a fixed reduction tree.
+__device__ __forceinline__ double block_sum_256(double v, double* sm) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += sm[w];
+    return t;
+}
+
+__global__ void __launch_bounds__(256)
+si_sdr_kernel(const float* __restrict__ ref, const float* __restrict__ est, const int* __restrict__ len, int lstride,
+              double* __restrict__ out) {
+    __shared__ double sm[8];
+    const int b = blockIdx.x;
+    const int L = len ? len[b] : lstride;
+    const float* s = ref + (int64_t)b * lstride;
+    const float* e = est + (int64_t)b * lstride;
+    double dot = 0.0, ss = 0.0;
+    for (int i = threadIdx.x; i < L; i += 256) {
+        const double a = s[i], c = e[i];
+        dot += a * c;
+        ss += a * a;
+    }
+    dot = block_sum_256(dot, sm);
+    ss = block_sum_256(ss, sm);
+    const double alpha = dot / ss;
+    double num = 0.0, den = 0.0;
+    for (int i = threadIdx.x; i < L; i += 256) {
+        const double a = alpha * (double)s[i], d = a - (double)e[i];
+        num += a * a;
+        den += d * d;
+    }
+    num = block_sum_256(num, sm);
+    den = block_sum_256(den, sm);
+    if (threadIdx.x == 0) out[b] = 10.0 * log10(num / den);
+}
+
 }  // namespace
+
+int si_sdr_launch(const float* ref, const float* est, const int* len, int B, int lstride, double* out, cudaStream_t s) {
+    SNRSE_CHECK_ARG(ref && est && out && B > 0 && lstride > 0, "si_sdr: bad arguments");
+    si_sdr_kernel<<<B, 256, 0, s>>>(ref, est, len, lstride, out);
+    SNRSE_LAUNCH_CHECK();
+    return SNRSE_OK;
+}
+
 
 int spec_transform_launch(const float2* in, float2* out, int64_t n, int inverse, float alpha, float beta, cudaStream_t s) {
     spec_transform_kernel<<<(unsigned)cdiv64(n, 256), 256, 0, s>>>(in, out, n, inverse, alpha, beta);

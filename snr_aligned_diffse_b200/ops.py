@@ -63,6 +63,17 @@ def istft(spec, length, lengths=None, scale=None, transform=True, alpha=0.5, bet
     return wave
 
 
+def si_sdr(ref, est, lengths=None):
+    """SI-SDR (dB, float64 [B]) of est [B, L] against ref [B, L] over the first lengths[b] samples, on the device."""
+    lib = _lib_dev()
+    assert ref.is_cuda and est.is_cuda and ref.shape == est.shape and ref.dim() == 2
+    ref, est = ref.to(torch.float32).contiguous(), est.to(torch.float32).contiguous()
+    out = torch.empty(ref.shape[0], dtype=torch.float64, device=ref.device)
+    _lib.check(lib.snrse_si_sdr(_lib.ptr(ref), _lib.ptr(est), _lib.ptr(lengths), ref.shape[0], ref.shape[1], _lib.ptr(out),
+                                _lib.stream_ptr()), "si_sdr")
+    return out
+
+
 def absmax(wave, lengths=None):
     lib = _lib_dev()
     wave = wave.contiguous()
@@ -105,6 +116,34 @@ def lincomb(x=None, y=None, s=None, z=None, a=None, b=None, c=None, d=None, want
                                  _lib.ptr(c), _lib.ptr(d), _lib.ptr(out_mean), _lib.ptr(out_x), B, n,
                                  _lib.stream_ptr()), "lincomb")
     return out_mean, out_x
+
+
+def rk_combine(y, K, coef, h):
+    """y + h * sum_j coef[j] * K[j]; K complex64 [nk, ...] (stages), y complex64 [...] or None."""
+    import ctypes
+    lib = _lib_dev()
+    nk = len(coef)
+    n = K[0].numel()
+    out = torch.empty_like(K[0])
+    c = (ctypes.c_float * nk)(*[float(v) for v in coef])
+    _lib.check(lib.snrse_rk_combine(_lib.ptr(y), _lib.ptr(K), nk, n, float(h), c, _lib.ptr(out), _lib.stream_ptr()),
+               "rk_combine")
+    return out
+
+
+def rk_scaled_norm(K, coef, h, y, y2, atol, rtol):
+    """RMS of (h * sum_j coef[j] K[j]) / (atol + rtol * max(|y|, |y2|)) over all complex elements (host float).
+    One device->host read of <= 1024 block sums, added on the host in a fixed order."""
+    import ctypes
+    import math
+    lib = _lib_dev()
+    nk = len(coef)
+    n = K[0].numel()
+    part = torch.empty(int(lib.snrse_rk_partials(n)), dtype=torch.float64, device=K.device)
+    c = (ctypes.c_float * nk)(*[float(v) for v in coef])
+    _lib.check(lib.snrse_rk_scaled_sqnorm(_lib.ptr(K), nk, n, float(h), c, _lib.ptr(y), _lib.ptr(y2), float(atol),
+                                          float(rtol), _lib.ptr(part), _lib.stream_ptr()), "rk_scaled_sqnorm")
+    return math.sqrt(math.fsum(part.cpu().tolist()) / n)
 
 
 # ------------------------------------------------------------------------------ single NHWC operators

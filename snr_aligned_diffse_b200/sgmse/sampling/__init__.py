@@ -57,9 +57,10 @@ def get_pc_sampler(predictor_name, corrector_name, sde, score_fn, Y, Y_prior=Non
 
 
 def get_ode_sampler(sde, score_fn, y, Y_prior=None, inverse_scaler=None, denoise=True, rtol=1e-5, atol=1e-5,
-                    timestep_type=None, method='RK45', eps=3e-2, device='cuda', **kwargs):
-    """Probability-flow ODE sampler driven by scipy's RK45, host round trip per RHS evaluation as in the
-    reference (sampling/__init__.py:95-171)."""
+                    timestep_type=None, method='RK45', eps=3e-2, device='cuda', on_device=False, **kwargs):
+    """Probability-flow ODE sampler (sampling/__init__.py:95-171).  Default: scipy's RK45 with a host round trip per
+    RHS evaluation, as in the reference.  `on_device=True` (extension, RK45 only): the same Dormand-Prince scheme and
+    step control with the state and all stage arithmetic resident on the GPU (`sampling/ode.py`)."""
     if not y.is_cuda:
         y = y.cuda()
     predictor = ReverseDiffusionPredictor(sde, score_fn, probability_flow=False)
@@ -81,10 +82,24 @@ def get_ode_sampler(sde, score_fn, y, Y_prior=None, inverse_scaler=None, denoise
                 vec_t = torch.ones(y.shape[0], device=x.device) * t
                 return to_flattened_numpy(rsde.sde(x, vec_t, y)[0])
 
-            solution = integrate.solve_ivp(ode_func, (sde.T, eps), to_flattened_numpy(xt), rtol=rtol, atol=atol,
-                                           method=method, **kw)
-            nfe = solution.nfev
-            x = torch.tensor(solution.y[:, -1]).reshape(y.shape).to(device).type(torch.complex64)
+            if on_device:
+                if method != 'RK45':
+                    raise NotImplementedError("on_device=True implements RK45 only")
+                from .ode import rk45_integrate
+
+                def ode_func_dev(t, x):
+                    vec_t = torch.full((y.shape[0],), float(t), dtype=torch.float32, device=x.device)
+                    return rsde.sde(x, vec_t, y)[0]
+
+                res = rk45_integrate(ode_func_dev, float(sde.T), xt.to(torch.complex64), float(eps), rtol=rtol, atol=atol)
+                if res.status != 0:
+                    raise RuntimeError("on-device RK45: required step size below the spacing between numbers")
+                nfe, x = res.nfev, res.y
+            else:
+                solution = integrate.solve_ivp(ode_func, (sde.T, eps), to_flattened_numpy(xt), rtol=rtol, atol=atol,
+                                               method=method, **kw)
+                nfe = solution.nfev
+                x = torch.tensor(solution.y[:, -1]).reshape(y.shape).to(device).type(torch.complex64)
             if denoise:
                 x = denoise_update_fn(x)
             if inverse_scaler is not None:

@@ -5,7 +5,7 @@ independent (per-utterance normalisation, per-sample GroupNorm / attention), so 
   1. partitioned over ranks by LPT on padded frames (`shard.lpt_shards`),
   2. grouped into equal-Tpad batches on every rank (`shard.bucket_batches`),
   3. enhanced batch by batch with `ScoreModel.enhance_batch` (ragged lengths inside a batch),
-with NO collective on the data path.  Only the per-utterance metrics (id, samples, checksum) and the
+with NO collective on the data path.  Only the per-utterance metrics (id, samples, checksum, SI-SDR) and the
 rank timings are gathered at the end (`torch.distributed`: NCCL on GPUs, gloo in the CPU tests).
 """
 import time
@@ -29,15 +29,17 @@ def pack_batch(waves, idx, tpad):
     return y, lens
 
 
-def enhance_sweep(enhance_fn, waves, rank=0, world=1, max_batch=16, device=None, keep_audio=False):
+def enhance_sweep(enhance_fn, waves, rank=0, world=1, max_batch=16, device=None, keep_audio=False, references=None):
     """Enhance the utterances `waves` (list of 1-D float tensors) this rank owns.
 
     enhance_fn(y [B, L] , lengths [B] int32) -> enhanced [B, L] (e.g. `lambda y, n: model.enhance_batch(y, lengths=n)`).
-    Returns dict(ids, samples, checksum, seconds, batches, audio) for this rank's shard."""
+    references: optional list of clean waveforms (same lengths): adds the per-utterance SI-SDR in dB, computed on the
+    device (`ops.si_sdr`; the reference computes it on host numpy arrays per file, B/eval.py:140-144).
+    Returns dict(ids, samples, checksum, si_sdr, seconds, batches, audio) for this rank's shard."""
     lengths = [int(w.numel()) for w in waves]
     mine = lpt_shards(lengths, world)[rank]
     batches = bucket_batches(lengths, mine, max_batch)
-    ids, samples, checks, audio = [], [], [], {}
+    ids, samples, checks, sdrs, audio = [], [], [], [], {}
     t0 = time.perf_counter()
     for tpad, idx in batches:
         y, lens = pack_batch(waves, idx, tpad)
@@ -51,6 +53,10 @@ def enhance_sweep(enhance_fn, waves, rank=0, world=1, max_batch=16, device=None,
             ids.append(i)
             samples.append(lengths[i])
         checks.append(cs)
+        if references is not None:
+            from . import ops
+            x, _ = pack_batch(references, idx, tpad)
+            sdrs.append(ops.si_sdr(x.to(out.device, non_blocking=True), out, lens.to(out.device)))
         if keep_audio:
             for r, i in enumerate(idx):
                 audio[i] = out[r, :lengths[i]].detach().cpu()
@@ -58,14 +64,18 @@ def enhance_sweep(enhance_fn, waves, rank=0, world=1, max_batch=16, device=None,
         torch.cuda.synchronize(checks[0].device)
     seconds = time.perf_counter() - t0
     checksum = torch.cat(checks).cpu().tolist() if checks else []
-    return dict(ids=ids, samples=samples, checksum=checksum, seconds=seconds, batches=len(batches), audio=audio)
+    si_sdr = torch.cat(sdrs).cpu().tolist() if sdrs else [float("nan")] * len(ids)
+    return dict(ids=ids, samples=samples, checksum=checksum, si_sdr=si_sdr, seconds=seconds, batches=len(batches),
+                audio=audio)
 
 
 def gather_metrics(local, world=1):
     """All ranks' (id, samples, checksum) rows sorted by id + the slowest rank's wall time (the job time).
     The only communication of the sweep (a few KB)."""
-    rows = torch.tensor([[float(i), float(n), float(c)] for i, n, c in zip(local["ids"], local["samples"], local["checksum"])],
-                        dtype=torch.float64).reshape(-1, 3)
+    sdr = local.get("si_sdr") or [float("nan")] * len(local["ids"])
+    rows = torch.tensor([[float(i), float(n), float(c), float(q)]
+                         for i, n, c, q in zip(local["ids"], local["samples"], local["checksum"], sdr)],
+                        dtype=torch.float64).reshape(-1, 4)
     sec = torch.tensor([local["seconds"]], dtype=torch.float64)
     if world > 1:
         import torch.distributed as dist
@@ -74,7 +84,7 @@ def gather_metrics(local, world=1):
         counts = [torch.zeros_like(n) for _ in range(world)]
         dist.all_gather(counts, n)
         cap = int(max(int(c.item()) for c in counts))
-        pad = torch.zeros(cap, 3, dtype=torch.float64, device=dev)
+        pad = torch.zeros(cap, 4, dtype=torch.float64, device=dev)
         pad[:rows.shape[0]] = rows.to(dev)
         parts = [torch.zeros_like(pad) for _ in range(world)]
         dist.all_gather(parts, pad)
@@ -85,4 +95,4 @@ def gather_metrics(local, world=1):
     order = torch.argsort(rows[:, 0])
     rows = rows[order]
     return dict(ids=rows[:, 0].long().tolist(), samples=rows[:, 1].long().tolist(), checksum=rows[:, 2].tolist(),
-                job_seconds=float(sec.item()))
+                si_sdr=rows[:, 3].tolist(), job_seconds=float(sec.item()))
