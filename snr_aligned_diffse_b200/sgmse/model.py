@@ -137,6 +137,14 @@ class ScoreModel(CheckpointedModule):
         sde = self.sde.copy()
         sde.N = N
         kwargs = {"eps": self.t_eps, **kwargs}
+        if kwargs.get("graph"):
+            # captured loops are kept per model across sampler objects; they point into the packed weight blob and the
+            # engine's activation arena, so a weight (re)load -- EMA swap, load_state_dict -- drops them
+            self.dnn._ensure_device_weights()
+            tag = self.dnn.engine.blob.data_ptr()
+            if self.__dict__.get("_pc_graph_tag") != tag:
+                self.__dict__["_pc_graph_cache"], self.__dict__["_pc_graph_tag"] = {}, tag
+            kwargs.setdefault("graph_cache", self.__dict__["_pc_graph_cache"])
         if minibatch is None:
             return sampling.get_pc_sampler(predictor_name, corrector_name, sde=sde, score_fn=self, Y=y,
                                            Y_prior=Y_prior, timestep_type=timestep_type, **kwargs)

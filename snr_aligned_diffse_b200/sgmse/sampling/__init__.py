@@ -21,9 +21,81 @@ def timesteps_space(sdeT, sdeN, eps, device, type='linear'):
     return torch.linspace(sdeT, eps, sdeN, device=device)
 
 
+def _time_vector(B, t, device):
+    """[B] float32 device tensor filled with t, tagged with its host value (SDE helpers that need host-side special
+    functions, BBED._std, read the tag instead of copying the tensor back)."""
+    v = torch.full((B,), float(t), dtype=torch.float32, device=device)
+    v._host_value = float(t)
+    return v
+
+
+class GraphedPCLoop:
+    """The reverse loop of `pc_sampler` (sampling/__init__.py:54-75) as one CUDA graph per step.
+
+    Step i = corrector update(s) + predictor update at t_i: 1 + n_steps network evaluations, the complex noise draws
+    and the fused state updates.  Its scalars (t_i, step size, SDE coefficients) are host constants baked into graph i;
+    the state lives in static buffers, the graphs share one memory pool and are replayed in capture order.  Noise comes
+    from torch's CUDA generator, which advances its Philox offset on every replay."""
+
+    def __init__(self, predictor, corrector, timesteps, Y):
+        dev = Y.device
+        self.Y = Y.clone()
+        self.x = torch.empty_like(self.Y)
+        self.mean = torch.empty_like(self.Y)
+        self.stream = torch.cuda.Stream(device=dev)
+        self.graphs = []
+        B = Y.shape[0]
+        n = len(timesteps)
+        steps = []
+        for i in range(n):
+            t = timesteps[i]
+            stepsize = t - timesteps[i + 1] if i != n - 1 else timesteps[-1]
+            steps.append((_time_vector(B, t, dev), stepsize))
+        self._steps = steps                          # the captured kernels read these time vectors: keep them alive
+
+        def one(i):
+            vec_t, stepsize = steps[i]
+            xt, _ = corrector.update_fn(self.x, vec_t, self.Y)
+            xt, xm = predictor.update_fn(xt, vec_t, self.Y, stepsize)
+            self.x.copy_(xt)
+            self.mean.copy_(xm)
+
+        rng = torch.cuda.get_rng_state(dev)          # warm-up draws must not shift the caller's noise sequence
+        self.stream.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(self.stream):
+            self.x.copy_(self.Y)
+            one(0)                                   # eager warm-up: plans, workspaces, function attributes
+            self.stream.synchronize()
+            pool = None
+            for i in range(n):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, pool=pool, stream=self.stream):
+                    one(i)
+                pool = g.pool()
+                self.graphs.append(g)
+        torch.cuda.current_stream(dev).wait_stream(self.stream)
+        torch.cuda.set_rng_state(rng, dev)
+
+    def run(self, x0, Y):
+        cur = torch.cuda.current_stream(Y.device)
+        self.stream.wait_stream(cur)
+        with torch.cuda.stream(self.stream):
+            self.Y.copy_(Y)
+            self.x.copy_(x0)
+            for g in self.graphs:
+                g.replay()
+        cur.wait_stream(self.stream)
+        return self.x, self.mean
+
+
 def get_pc_sampler(predictor_name, corrector_name, sde, score_fn, Y, Y_prior=None, denoise=True, eps=3e-2, snr=0.1,
-                   corrector_steps=1, probability_flow: bool = False, intermediate=False, timestep_type=None, **kwargs):
-    """Predictor-corrector sampler; returns a zero-argument callable -> (sample, nfe)."""
+                   corrector_steps=1, probability_flow: bool = False, intermediate=False, timestep_type=None, graph=False,
+                   graph_cache=None, **kwargs):
+    """Predictor-corrector sampler; returns a zero-argument callable -> (sample, nfe).
+
+    `graph=True` (extension): every step of the reverse loop (corrector + predictor: network evaluations, noise draws,
+    state updates) is replayed from a CUDA graph captured on first use (`GraphedPCLoop`); `graph_cache` (a dict, e.g.
+    one per model) keeps the captured loops across sampler objects of the same shape and settings."""
     predictor_cls = PredictorRegistry.get_by_name(predictor_name)
     corrector_cls = CorrectorRegistry.get_by_name(corrector_name)
     predictor = predictor_cls(sde, score_fn, probability_flow=probability_flow)
@@ -41,17 +113,28 @@ def get_pc_sampler(predictor_name, corrector_name, sde, score_fn, Y, Y_prior=Non
             xt, _ = sde.prior_sampling(Y_prior.shape, Y_prior if Y_prior.is_cuda else Y_prior.cuda())
             # time grid on the host: every step's scalars are known before the first launch
             timesteps = torch.linspace(sde.T, eps, sde.N)
+            ns = len(timesteps) * (corrector.n_steps + 1)
+            if graph:
+                key = (predictor_name, corrector_name, tuple(Y.shape), int(sde.N), float(sde.T), float(eps), float(snr),
+                       int(corrector_steps), bool(probability_flow), type(sde).__name__, id(score_fn))
+                cache = graph_cache if graph_cache is not None else _local_graphs
+                loop = cache.get(key)
+                if loop is None:
+                    loop = cache[key] = GraphedPCLoop(predictor, corrector, timesteps, Y)
+                xt, xt_mean = loop.run(xt, Y)
+                return (xt_mean if denoise else xt), ns
             xt_mean = xt
             B = Y.shape[0]
             for i in range(len(timesteps)):
                 t = timesteps[i]
                 stepsize = t - timesteps[i + 1] if i != len(timesteps) - 1 else timesteps[-1]
-                vec_t = torch.full((B,), float(t), dtype=torch.float32, device=Y.device)
+                vec_t = _time_vector(B, t, Y.device)
                 xt, xt_mean = corrector.update_fn(xt, vec_t, Y)
                 xt, xt_mean = predictor.update_fn(xt, vec_t, Y, stepsize)
             x_result = xt_mean if denoise else xt
-            ns = len(timesteps) * (corrector.n_steps + 1)
             return x_result, ns
+
+    _local_graphs = {}
 
     return pc_sampler
 

@@ -229,6 +229,15 @@ class BBED(SDE):
         return axpby(x=x0, a=1 - time, y=y, b=time)
 
     def _std(self, t):
+        hv = getattr(t, "_host_value", None)
+        if hv is not None:
+            # the sampler loops tag their uniform time vector with its host value: same float32 -> float64 expi
+            # arithmetic as below, but no device->host read (one sync per step less; CUDA-graph capturable)
+            t1 = np.full((1,), np.float32(hv))
+            Eis = sc.expi(2 * (t1 - 1) * self.logk) - self.Eilog
+            var = (self.k ** (2 * t1) - 1 + t1) + 2 * self.k ** 2 * self.logk * (1 - t1) * Eis
+            var = torch.full_like(t, float(np.float32(var[0])), dtype=torch.float32) * (1 - t) * self.theta
+            return torch.sqrt(var)
         t_np = t.detach().cpu().numpy()
         Eis = sc.expi(2 * (t_np - 1) * self.logk) - self.Eilog
         h = 2 * self.k ** 2 * self.logk

@@ -299,3 +299,31 @@ def test_si_sdr_on_device_matches_reference_formula():
         ref = si_sdr_numpy(s[b, :L].double().numpy(), e[b, :L].double().numpy())
         assert abs(float(got[b]) - ref) <= 1e-9 * max(1.0, abs(ref))
     assert torch.equal(ops.si_sdr(s.cuda(), e.cuda(), lens.cuda()).cpu(), got)      # fixed reduction tree: reproducible
+
+
+@pytest.mark.parametrize("sde_name", ["ouve", "bbed"])
+def test_pc_sampler_graph_replay_equals_eager_loop(sd, sde_name):
+    """get_pc_sampler(graph=True): the reverse loop replayed from per-step CUDA graphs returns the same bits as the
+    eager host loop when both see the same noise draws (the generator is re-seeded before each run; eager and captured
+    `randn_like` calls consume the same Philox sequence), and a second run with a new seed differs (fresh noise per
+    replay).  BBED exercises the host-tagged time vector (no device->host read of t inside the loop)."""
+    from snr_aligned_diffse_b200.sgmse.model import ScoreModel
+    kw = dict(theta=1.5, sigma_min=0.05, sigma_max=0.5) if sde_name == "ouve" else dict(theta=0.08, k=2.6, T_sampling=0.5)
+    m = ScoreModel.from_state_dict(sd, backbone="ncsnpp", sde=sde_name, model_type="bbed", snr_conditioned="false",
+                                   base_dir="", **kw).eval(no_ema=True)
+    g = torch.Generator().manual_seed(31)
+    Y = torch.view_as_complex(torch.randn(2, 1, 256, 64, 2, generator=g) * 0.05).cuda()
+    outs = {}
+    for mode in ("eager", "graph", "graph_again"):
+        torch.manual_seed(77)
+        torch.cuda.manual_seed_all(77)
+        s = m.get_pc_sampler("reverse_diffusion", "ald", Y, N=2, corrector_steps=1, snr=0.5, graph=(mode != "eager"))
+        out, nfe = s()
+        assert nfe == 4 and torch.isfinite(torch.view_as_real(out)).all(), mode
+        outs[mode] = out.clone()
+    assert len(m._pc_graph_cache) == 1                      # the second sampler object reused the captured loop
+    assert torch.equal(torch.view_as_real(outs["graph"]), torch.view_as_real(outs["graph_again"]))
+    assert rel_l2(outs["graph"].cpu(), outs["eager"].cpu()) <= 1e-6
+    torch.cuda.manual_seed_all(78)
+    other, _ = m.get_pc_sampler("reverse_diffusion", "ald", Y, N=2, corrector_steps=1, snr=0.5, graph=True)()
+    assert rel_l2(other.cpu(), outs["graph"].cpu()) > 1e-3

@@ -52,7 +52,7 @@ def run_pc(args, world, rank, dev):
     y = bench.synth_waves(B, L, seed=2000 + rank).to(dev)
     peak = ops.absmax(y)
     Y = ops.stft(y, scale=peak, scale_is_divisor=True)[:, None]
-    sampler = model.get_pc_sampler("reverse_diffusion", "ald", Y, N=30, corrector_steps=1, snr=0.5)
+    sampler = model.get_pc_sampler("reverse_diffusion", "ald", Y, N=30, corrector_steps=1, snr=0.5, graph=bool(args.graphs))
     sample, nfe = sampler()                       # warm-up: plans, weights
     torch.cuda.synchronize()
     if world > 1:
@@ -72,7 +72,8 @@ def run_pc(args, world, rank, dev):
         print(json.dumps(dict(metric="enhanced audio-sec/sec (inverse RTF), PC sampler 60 NFE", workload="pc", unit=bench.UNIT,
                               value=world * B * bench.SECONDS / sec, n_gpus=world, nfe=int(nfe), ms_per_batch=round(sec * 1e3, 2),
                               ms_per_nfe=round(sec * 1e3 / nfe, 3), batch=B, finite=bool(torch.isfinite(x_hat).all()),
-                              mode="host loop, eager launches", scaling="weak")), flush=True)
+                              mode="one CUDA graph per reverse step (corrector + predictor)" if args.graphs else "host loop, eager launches",
+                              scaling="weak")), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
