@@ -10,9 +10,10 @@
 // FFT in shared memory.  The real 510-point transform is a complex 255-point transform of the packed signal
 // z[m] = x[2m] + i x[2m+1] plus a split/merge pass.  255 = 3 * 5 * 17 with pairwise coprime factors, so the
 // 255-point DFT is a twiddle-free 3 x 5 x 17 DFT (Good-Thomas): input index (85 n1 + 51 n2 + 15 n3) mod 255,
-// output index k with (k mod 3, k mod 5, k mod 17) = (k1, k2, k3), i.e. k = (85 k1 + 51 k2 + 120 k3) mod 255.
-// 25 complex multiply-adds per point instead of 510: 0.05 MFLOP per frame.  Eight frames per pass: one thread
-// per transform point, the eight frames ride in registers as four float4 (two complex frames each).
+// output index k with (k mod 3, k mod 5, k mod 17) = (k1, k2, k3).  Each 17-, 5- and 3-point DFT is one thread's
+// register-resident butterfly (inputs loaded once, outputs stored in place) that uses the x_j +- x_{R-j} symmetry:
+// ~8.3 k flops per 510-sample frame (a direct DFT needs 522 k), no shared-memory traffic inside the butterflies,
+// twiddles are compile-time immediates.  Eight frames per pass.
 // The inverse kernel also does the overlap-add, the window-envelope division and the rescale: every block
 // recomputes a 4-frame halo so that all frames touching its output samples are in its own shared memory; no
 // frame workspace in HBM, no floating-point atomics.
@@ -21,106 +22,105 @@
 namespace {
 
 constexpr int NFFT = 510, HOP = 128, NBINS = 256, FT = 8, HALF = 255, M255 = 255;
-constexpr int QS = 256;                       // float4 stride between frame pairs in a transform buffer
+constexpr int FS = 256;                       // float2 stride between the frames of a transform buffer
 constexpr int SPAN = (FT - 1) * HOP + NFFT;   // samples touched by FT consecutive frames (1406)
 
-struct Twiddles {
-    float2 w17[17], w5[5], w3[3];             // e^{-2 pi i j / r}
-};
-
-__device__ __forceinline__ void fill_twiddles(Twiddles& tw) {
-    const int i = threadIdx.x;
-    float s, c;
-    if (i < 17) {
-        sincospif((float)(2 * i) / 17.0f, &s, &c);
-        tw.w17[i] = make_float2(c, -s);
-    } else if (i >= 32 && i < 37) {
-        sincospif((float)(2 * (i - 32)) / 5.0f, &s, &c);
-        tw.w5[i - 32] = make_float2(c, -s);
-    } else if (i >= 64 && i < 67) {
-        sincospif((float)(2 * (i - 64)) / 3.0f, &s, &c);
-        tw.w3[i - 64] = make_float2(c, -s);
-    }
-}
+__device__ constexpr float C3[3] = {1.f, -0.5f, -0.5f};
+__device__ constexpr float S3[3] = {0.f, 0.866025404f, -0.866025404f};
+__device__ constexpr float C5[5] = {1.f, 0.309016994f, -0.809016994f, -0.809016994f, 0.309016994f};
+__device__ constexpr float S5[5] = {0.f, 0.951056516f, 0.587785252f, -0.587785252f, -0.951056516f};
+__device__ constexpr float C17[17] = {1.f, 0.932472229f, 0.739008917f, 0.445738356f, 0.0922683595f, -0.27366299f,
+                                      -0.602634636f, -0.850217136f, -0.9829731f, -0.9829731f, -0.850217136f,
+                                      -0.602634636f, -0.27366299f, 0.0922683595f, 0.445738356f, 0.739008917f, 0.932472229f};
+__device__ constexpr float S17[17] = {0.f, 0.361241666f, 0.673695644f, 0.895163291f, 0.995734176f, 0.961825643f,
+                                      0.798017227f, 0.526432163f, 0.183749518f, -0.183749518f, -0.526432163f,
+                                      -0.798017227f, -0.961825643f, -0.995734176f, -0.895163291f, -0.673695644f, -0.361241666f};
 
 __device__ __forceinline__ float hann(int n) { return 0.5f - 0.5f * cospif((float)(2 * n) / (float)NFFT); }
 
-// acc += x * w for the two complex frames packed in one float4
-__device__ __forceinline__ void cmac2(float4& acc, const float4 x, const float2 w) {
-    acc.x = fmaf(x.x, w.x, fmaf(-x.y, w.y, acc.x));
-    acc.y = fmaf(x.x, w.y, fmaf(x.y, w.x, acc.y));
-    acc.z = fmaf(x.z, w.x, fmaf(-x.w, w.y, acc.z));
-    acc.w = fmaf(x.z, w.y, fmaf(x.w, w.x, acc.w));
+// R-point DFT (R odd) of v in registers, e^{-...} (INV = false) or e^{+...} (INV = true), unnormalised.
+//   a_j = v_j + v_{R-j}, b_j = v_j - v_{R-j};  P_k = v_0 + sum_j a_j cos(2 pi j k / R);  Q_k = sum_j b_j sin(2 pi j k / R)
+//   forward: V_k = P_k - i Q_k, V_{R-k} = P_k + i Q_k.
+template <int R, bool INV>
+__device__ __forceinline__ void bfly(float2 (&v)[R], const float (&C)[R], const float (&S)[R]) {
+    constexpr int H = R / 2;
+    float2 a[H], b[H];
+#pragma unroll
+    for (int j = 1; j <= H; ++j) {
+        a[j - 1] = make_float2(v[j].x + v[R - j].x, v[j].y + v[R - j].y);
+        b[j - 1] = make_float2(v[j].x - v[R - j].x, v[j].y - v[R - j].y);
+    }
+    const float2 x0 = v[0];
+    float2 s0 = x0;
+#pragma unroll
+    for (int j = 0; j < H; ++j) {
+        s0.x += a[j].x;
+        s0.y += a[j].y;
+    }
+    v[0] = s0;
+#pragma unroll
+    for (int k = 1; k <= H; ++k) {
+        float pr = x0.x, pi = x0.y, qr = 0.f, qi = 0.f;
+#pragma unroll
+        for (int j = 1; j <= H; ++j) {
+            const int m = (j * k) % R;
+            pr = fmaf(a[j - 1].x, C[m], pr);
+            pi = fmaf(a[j - 1].y, C[m], pi);
+            qr = fmaf(b[j - 1].x, S[m], qr);
+            qi = fmaf(b[j - 1].y, S[m], qi);
+        }
+        const float2 lo = make_float2(pr + qi, pi - qr), hi = make_float2(pr - qi, pi + qr);   // P - iQ, P + iQ
+        v[k] = INV ? hi : lo;
+        v[R - k] = INV ? lo : hi;
+    }
 }
 
-// position (in natural order) of the element a thread stores at linear index j = (n1*5 + n2)*17 + n3
+// natural position of the element stored at linear index j = (n1*5 + n2)*17 + n3 of the transform input
 __device__ __forceinline__ int pfa_input_pos(int j) {
     const int g = j / 17, n3 = j - g * 17, n1 = g / 5, n2 = g - n1 * 5;
     return (85 * n1 + 51 * n2 + 15 * n3) % M255;
 }
+// its inverse: linear input index of natural position p  (85 = 1 mod 3, 51 = 1 mod 5, 15 * 8 = 1 mod 17)
+__device__ __forceinline__ int pfa_input_index(int p) { return ((p % 3) * 5 + (p % 5)) * 17 + (8 * p) % 17; }
+// linear index (k1*5 + k2)*17 + k3 at which output bin k is found after the transform
+__device__ __forceinline__ int pfa_output_index(int k) { return (k % 3) * 85 + (k % 5) * 17 + (k % 17); }
 
-// 255-point DFT of FT frames.  In: A[q*QS + j] (linear PFA order, see pfa_input_pos).  Out: Bf[q*QS + k], natural
-// order.  INV selects e^{+...}.  The caller synchronises after filling A; the result is visible on return.
+// In-place 255-point DFT of FT frames: X[f*FS + j], j in PFA input order (pfa_input_pos); on return bin k of frame f is
+// at X[f*FS + pfa_output_index(k)].  The caller synchronises after filling X; the result is visible on return.
 template <bool INV>
-__device__ __forceinline__ void fft255(float4* __restrict__ A, float4* __restrict__ Bf, const Twiddles& tw) {
-    const int j = threadIdx.x;
-    const float sg = INV ? -1.0f : 1.0f;
-    if (j < M255) {  // 17-point DFTs along n3: j = g*17 + k3
-        const int g = j / 17, k3 = j - g * 17;
-        float4 acc[FT / 2];
+__device__ __forceinline__ void fft255(float2* __restrict__ X) {
+    const int tid = threadIdx.x;
+    if (tid < 15 * FT) {  // 17-point DFTs along n3: 15 (n1, n2) groups per frame
+        const int f = tid / 15, g = tid - f * 15;
+        float2* p = X + f * FS + g * 17;
+        float2 v[17];
 #pragma unroll
-        for (int q = 0; q < FT / 2; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-        int ph = 0;
+        for (int n = 0; n < 17; ++n) v[n] = p[n];
+        bfly<17, INV>(v, C17, S17);
 #pragma unroll
-        for (int n3 = 0; n3 < 17; ++n3) {
-            float2 w = tw.w17[ph];
-            w.y *= sg;
-            ph += k3;
-            if (ph >= 17) ph -= 17;
-#pragma unroll
-            for (int q = 0; q < FT / 2; ++q) cmac2(acc[q], A[q * QS + g * 17 + n3], w);
-        }
-#pragma unroll
-        for (int q = 0; q < FT / 2; ++q) Bf[q * QS + j] = acc[q];
+        for (int n = 0; n < 17; ++n) p[n] = v[n];
     }
     __syncthreads();
-    if (j < M255) {  // 5-point DFTs along n2: j = (n1*5 + k2)*17 + k3
-        const int n1 = j / 85, r = j - n1 * 85, k2 = r / 17, k3 = r - k2 * 17;
-        float4 acc[FT / 2];
+    for (int it = tid; it < 51 * FT; it += 256) {  // 5-point DFTs along n2: 51 (n1, k3) columns per frame
+        const int f = it / 51, col = it - f * 51, n1 = col / 17, k3 = col - n1 * 17;
+        float2* p = X + f * FS + n1 * 85 + k3;
+        float2 v[5];
 #pragma unroll
-        for (int q = 0; q < FT / 2; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-        int ph = 0;
+        for (int n = 0; n < 5; ++n) v[n] = p[n * 17];
+        bfly<5, INV>(v, C5, S5);
 #pragma unroll
-        for (int n2 = 0; n2 < 5; ++n2) {
-            float2 w = tw.w5[ph];
-            w.y *= sg;
-            ph += k2;
-            if (ph >= 5) ph -= 5;
-#pragma unroll
-            for (int q = 0; q < FT / 2; ++q) cmac2(acc[q], Bf[q * QS + (n1 * 5 + n2) * 17 + k3], w);
-        }
-#pragma unroll
-        for (int q = 0; q < FT / 2; ++q) A[q * QS + j] = acc[q];
+        for (int n = 0; n < 5; ++n) p[n * 17] = v[n];
     }
     __syncthreads();
-    if (j < M255) {  // 3-point DFTs along n1: j = (k1*5 + k2)*17 + k3, scattered to natural order
-        const int k1 = j / 85, r = j - k1 * 85, k2 = r / 17, k3 = r - k2 * 17;
-        float4 acc[FT / 2];
+    for (int it = tid; it < 85 * FT; it += 256) {  // 3-point DFTs along n1: 85 (k2, k3) columns per frame
+        const int f = it / 85, r = it - f * 85;
+        float2* p = X + f * FS + r;
+        float2 v[3];
 #pragma unroll
-        for (int q = 0; q < FT / 2; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-        int ph = 0;
+        for (int n = 0; n < 3; ++n) v[n] = p[n * 85];
+        bfly<3, INV>(v, C3, S3);
 #pragma unroll
-        for (int n1 = 0; n1 < 3; ++n1) {
-            float2 w = tw.w3[ph];
-            w.y *= sg;
-            ph += k1;
-            if (ph >= 3) ph -= 3;
-#pragma unroll
-            for (int q = 0; q < FT / 2; ++q) cmac2(acc[q], A[q * QS + n1 * 85 + r], w);
-        }
-        const int k = (85 * k1 + 51 * k2 + 120 * k3) % M255;
-#pragma unroll
-        for (int q = 0; q < FT / 2; ++q) Bf[q * QS + k] = acc[q];
+        for (int n = 0; n < 3; ++n) p[n * 85] = v[n];
     }
     __syncthreads();
 }
@@ -128,103 +128,105 @@ __device__ __forceinline__ void fft255(float4* __restrict__ A, float4* __restric
 __global__ void __launch_bounds__(256)
 stft_kernel(const float* __restrict__ wave, const int* __restrict__ len, const float* __restrict__ scale,
             int scale_is_divisor, float* __restrict__ out, int lstride, int tpad, int transform, float alpha,
-            float beta, int planar) {
-    __shared__ __align__(16) float4 A[(FT / 2) * QS];
-    __shared__ __align__(16) float4 Bf[(FT / 2) * QS];
+            float beta, int planar, int npass) {
+    __shared__ __align__(16) float2 X[FT * FS];
     __shared__ __align__(16) float xs[SPAN + 2];
-    __shared__ Twiddles tw;
-    const int b = blockIdx.y, f0 = blockIdx.x * FT, tid = threadIdx.x;
+    const int b = blockIdx.y, tid = threadIdx.x;
     const int L = len ? len[b] : lstride;
     const int nframes = 1 + L / HOP;
-    fill_twiddles(tw);
     float sc = 1.0f;
     if (scale) sc = scale[b];
     const float* wb = wave + (int64_t)b * lstride;
-    for (int e = tid; e < SPAN; e += 256) {
-        int i = f0 * HOP + e - HALF;
-        if (i < 0) i = -i;
-        if (i >= L) i = 2 * (L - 1) - i;
-        i = max(0, min(i, L - 1));  // beyond one reflection: only frames >= nframes (written as zeros) or len <= 255
-        float v = wb[i];
-        if (scale) v = scale_is_divisor ? v / sc : v * sc;
-        xs[e] = v;
-    }
-    __syncthreads();
-    if (tid < M255) {  // windowed, packed z[m] = x[2m] + i x[2m+1] in PFA input order
-        const int m = pfa_input_pos(tid);
-        const float w0 = hann(2 * m), w1 = hann(2 * m + 1);
-#pragma unroll
-        for (int q = 0; q < FT / 2; ++q) {
-            const float2 x0 = *reinterpret_cast<const float2*>(&xs[(2 * q) * HOP + 2 * m]);
-            const float2 x1 = *reinterpret_cast<const float2*>(&xs[(2 * q + 1) * HOP + 2 * m]);
-            A[q * QS + tid] = make_float4(x0.x * w0, x0.y * w1, x1.x * w0, x1.y * w1);
-        }
-    }
-    __syncthreads();
-    fft255<false>(A, Bf, tw);
-    // split: X[k] = (Z[k] + conj Z[255-k])/2 - (i/2) e^{-2 pi i k/510} (Z[k] - conj Z[255-k]),  k = 0..255
+    // per-thread constants, reused by every pass: packed-input position + window (thread = transform point),
+    // split indices + e^{-i pi k/255} = (ec, -es) (thread = output bin k)
+    const int m2 = 2 * pfa_input_pos(tid < M255 ? tid : 0);
+    const float w0 = hann(m2), w1 = hann(m2 + 1);
     const int k = tid;
-    const int ka = (k == M255) ? 0 : k, kb = (M255 - k) % M255;
+    const int ia = pfa_output_index(k == M255 ? 0 : k), ib = pfa_output_index((M255 - k) % M255);
     float es, ec;
-    sincospif((float)k / (float)M255, &es, &ec);  // e^{-i pi k/255} = (ec, -es)
-    float re[FT], im[FT];
+    sincospif((float)k / (float)M255, &es, &ec);
+    for (int pass = 0; pass < npass; ++pass) {
+        const int f0 = (blockIdx.x * npass + pass) * FT;
+        if (f0 >= tpad) break;                                   // block-uniform
+        if (pass) __syncthreads();                               // the previous pass has read X
+        const int s0 = f0 * HOP - HALF;
+        if (s0 >= 0 && s0 + SPAN <= L) {                         // interior: no reflection
+            for (int e = tid; e < SPAN; e += 256) {
+                float v = wb[s0 + e];
+                if (scale) v = scale_is_divisor ? v / sc : v * sc;
+                xs[e] = v;
+            }
+        } else {
+            for (int e = tid; e < SPAN; e += 256) {
+                int i = s0 + e;
+                if (i < 0) i = -i;
+                if (i >= L) i = 2 * (L - 1) - i;
+                i = max(0, min(i, L - 1));  // beyond one reflection: only frames >= nframes (written as zeros) or len <= 255
+                float v = wb[i];
+                if (scale) v = scale_is_divisor ? v / sc : v * sc;
+                xs[e] = v;
+            }
+        }
+        __syncthreads();
+        if (tid < M255) {  // windowed, packed z[m] = x[2m] + i x[2m+1] in PFA input order
 #pragma unroll
-    for (int q = 0; q < FT / 2; ++q) {
-        const float4 za = Bf[q * QS + ka], zb = Bf[q * QS + kb];
-        const float zr[2] = {za.x, za.z}, zi[2] = {za.y, za.w}, cr[2] = {zb.x, zb.z}, ci[2] = {-zb.y, -zb.w};
+            for (int f = 0; f < FT; ++f) {
+                const float2 x = *reinterpret_cast<const float2*>(&xs[f * HOP + m2]);
+                X[f * FS + tid] = make_float2(x.x * w0, x.y * w1);
+            }
+        }
+        __syncthreads();
+        fft255<false>(X);
+        // split: X[k] = (Z[k] + conj Z[255-k])/2 - (i/2) e^{-2 pi i k/510} (Z[k] - conj Z[255-k]),  k = 0..255
+        float re[FT], im[FT];
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const float sr = zr[h] + cr[h], si = zi[h] + ci[h], dr = zr[h] - cr[h], di = zi[h] - ci[h];
+        for (int f = 0; f < FT; ++f) {
+            const float2 za = X[f * FS + ia], zb = X[f * FS + ib];
+            const float sr = za.x + zb.x, si = za.y - zb.y, dr = za.x - zb.x, di = za.y + zb.y;   // Z[k] +- conj Z[255-k]
             // E*d with E = (ec, -es):  (ec dr + es di,  ec di - es dr);  -i (a + i b) = b - i a
             const float pr = fmaf(ec, dr, es * di), pi = fmaf(ec, di, -es * dr);
-            re[2 * q + h] = 0.5f * (sr + pi);
-            im[2 * q + h] = 0.5f * (si - pr);
+            float r = 0.5f * (sr + pi), i = 0.5f * (si - pr);
+            if (f0 + f >= nframes) {
+                r = 0.f;
+                i = 0.f;
+            } else if (transform == 1) {
+                // beta * |X|^alpha * e^{i arg X} = X * beta * |X|^(alpha-1), 0 -> 0  (data_module.py:241-247)
+                const float mag = sqrtf(r * r + i * i);
+                float g = 0.f;
+                if (mag > 0.f) g = (alpha == 0.5f) ? beta / sqrtf(mag) : beta * powf(mag, alpha - 1.0f);
+                r *= g;
+                i *= g;
+            }
+            re[f] = r;
+            im[f] = i;
         }
-    }
+        if (planar) {
+            float* o0 = out + (((int64_t)b * 2 + 0) * NBINS + k) * tpad + f0;
+            float* o1 = out + (((int64_t)b * 2 + 1) * NBINS + k) * tpad + f0;
+            if ((tpad & 3) == 0 && f0 + FT <= tpad) {
+                reinterpret_cast<float4*>(o0)[0] = make_float4(re[0], re[1], re[2], re[3]);
+                reinterpret_cast<float4*>(o0)[1] = make_float4(re[4], re[5], re[6], re[7]);
+                reinterpret_cast<float4*>(o1)[0] = make_float4(im[0], im[1], im[2], im[3]);
+                reinterpret_cast<float4*>(o1)[1] = make_float4(im[4], im[5], im[6], im[7]);
+            } else {
 #pragma unroll
-    for (int f = 0; f < FT; ++f) {
-        const int t = f0 + f;
-        float r = re[f], i = im[f];
-        if (t >= nframes) {
-            r = 0.f;
-            i = 0.f;
-        } else if (transform == 1) {
-            // beta * |X|^alpha * e^{i arg X} = X * beta * |X|^(alpha-1), 0 -> 0  (data_module.py:241-247)
-            const float mag = sqrtf(r * r + i * i);
-            float g = 0.f;
-            if (mag > 0.f) g = (alpha == 0.5f) ? beta / sqrtf(mag) : beta * powf(mag, alpha - 1.0f);
-            r *= g;
-            i *= g;
-        }
-        re[f] = r;
-        im[f] = i;
-    }
-    if (planar) {
-        float* o0 = out + (((int64_t)b * 2 + 0) * NBINS + k) * tpad + f0;
-        float* o1 = out + (((int64_t)b * 2 + 1) * NBINS + k) * tpad + f0;
-        if ((tpad & 3) == 0 && f0 + FT <= tpad) {
-            reinterpret_cast<float4*>(o0)[0] = make_float4(re[0], re[1], re[2], re[3]);
-            reinterpret_cast<float4*>(o0)[1] = make_float4(re[4], re[5], re[6], re[7]);
-            reinterpret_cast<float4*>(o1)[0] = make_float4(im[0], im[1], im[2], im[3]);
-            reinterpret_cast<float4*>(o1)[1] = make_float4(im[4], im[5], im[6], im[7]);
+                for (int f = 0; f < FT; ++f)
+                    if (f0 + f < tpad) {
+                        o0[f] = re[f];
+                        o1[f] = im[f];
+                    }
+            }
         } else {
+            float2* o = reinterpret_cast<float2*>(out) + ((int64_t)b * NBINS + k) * tpad + f0;
+            if ((tpad & 1) == 0 && f0 + FT <= tpad) {
 #pragma unroll
-            for (int f = 0; f < FT; ++f)
-                if (f0 + f < tpad) {
-                    o0[f] = re[f];
-                    o1[f] = im[f];
-                }
-        }
-    } else {
-        float2* o = reinterpret_cast<float2*>(out) + ((int64_t)b * NBINS + k) * tpad + f0;
-        if ((tpad & 1) == 0 && f0 + FT <= tpad) {
+                for (int q = 0; q < FT / 2; ++q)
+                    reinterpret_cast<float4*>(o)[q] = make_float4(re[2 * q], im[2 * q], re[2 * q + 1], im[2 * q + 1]);
+            } else {
 #pragma unroll
-            for (int q = 0; q < FT / 2; ++q)
-                reinterpret_cast<float4*>(o)[q] = make_float4(re[2 * q], im[2 * q], re[2 * q + 1], im[2 * q + 1]);
-        } else {
-#pragma unroll
-            for (int f = 0; f < FT; ++f)
-                if (f0 + f < tpad) o[f] = make_float2(re[f], im[f]);
+                for (int f = 0; f < FT; ++f)
+                    if (f0 + f < tpad) o[f] = make_float2(re[f], im[f]);
+            }
         }
     }
 }
@@ -234,35 +236,31 @@ stft_kernel(const float* __restrict__ wave, const int* __restrict__ len, const f
 // them in shared memory in ascending frame order, divides by the window envelope and writes wave[p - 255].
 constexpr int PASSES = 4, HALO = 4, NEWF = PASSES * FT - HALO;      // 28 new frames per block
 constexpr int OLA_SPAN = (PASSES * FT - 1) * HOP + NFFT;             // 4478 samples
-constexpr int ISTFT_SMEM = 2 * (FT / 2) * QS * 16 + OLA_SPAN * 4 + NFFT * 4 + (int)sizeof(Twiddles) + 64;
+constexpr int ISTFT_SMEM = 2 * FT * FS * 8 + OLA_SPAN * 4 + NFFT * 4 + 64;
 
 __global__ void __launch_bounds__(256)
 istft_kernel(const float2* __restrict__ spec, const int* __restrict__ len, const float* __restrict__ scale,
              float* __restrict__ wave, int lstride, int tpad, int transform, float alpha, float beta) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float4* A = reinterpret_cast<float4*>(smem_raw);
-    float4* Bf = A + (FT / 2) * QS;
-    float* ola = reinterpret_cast<float*>(Bf + (FT / 2) * QS);
+    float2* X = reinterpret_cast<float2*>(smem_raw);                 // transform buffer [FT][FS]
+    float2* T = X + FT * FS;                                          // spectrogram tile [256][FT], later frames [FT][512 floats]
+    float* ola = reinterpret_cast<float*>(T + FT * FS);
     float* hw = ola + OLA_SPAN;                                       // Hann window
-    Twiddles& tw = *reinterpret_cast<Twiddles*>(hw + NFFT + 2);
     const int b = blockIdx.y, F0 = blockIdx.x * NEWF, tid = threadIdx.x;
     const int L = len ? len[b] : lstride;
-    fill_twiddles(tw);
     for (int i = tid; i < NFFT; i += 256) hw[i] = hann(i);
     for (int i = tid; i < OLA_SPAN; i += 256) ola[i] = 0.f;
     const float2* sb = spec + (int64_t)b * NBINS * tpad;
     const float inv_beta = 1.0f / beta;
     const bool vec_ok = (tpad & 1) == 0;
-    // merge factors of this thread's transform point
-    const int kz = (tid < M255) ? pfa_input_pos(tid) : 0;
+    // merge factors of this thread's bin pair (k, 255-k), k = tid < 128:  e^{+i pi k/255} = (ec, es)
     float es, ec;
-    sincospif((float)kz / (float)M255, &es, &ec);                    // e^{+i pi k/255} = (ec, es)
+    sincospif((float)(tid & 127) / (float)M255, &es, &ec);
     for (int pass = 0; pass < PASSES; ++pass) {
         const int fb = F0 - HALO + pass * FT;                        // first frame of this pass (even)
         if (fb + FT <= 0 || fb >= tpad) continue;                     // block-uniform: nothing to add
-        __syncthreads();                                              // previous pass done with A / Bf
-        // spectrogram tile -> Bf as float2 [k][FT], spec_back applied (data_module.py:256-262)
-        float2* T = reinterpret_cast<float2*>(Bf);
+        __syncthreads();                                              // previous pass done with X / T
+        // spectrogram tile -> T as float2 [k][FT], spec_back applied (data_module.py:256-262)
         for (int e = tid; e < NBINS * (FT / 2); e += 256) {
             const int k = e >> 2, c = e & 3, t = fb + 2 * c;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -287,33 +285,37 @@ istft_kernel(const float2* __restrict__ spec, const int* __restrict__ len, const
             reinterpret_cast<float4*>(T)[e] = v;
         }
         __syncthreads();
-        // merge: Z'[k] = (X[k] + conj X[255-k]) + i e^{+2 pi i k/510} (X[k] - conj X[255-k]),  k = 0..254
-        if (tid < M255) {
-            const float4* Ta = reinterpret_cast<const float4*>(T) + kz * 4;
-            const float4* Tb = reinterpret_cast<const float4*>(T) + (M255 - kz) * 4;
+        // merge: Z'[k] = (S[k] + conj S[255-k]) + i e^{+2 pi i k/510} (S[k] - conj S[255-k]),  k = 0..254, written
+        // straight to the transform's input order.  One thread per pair (k, 255-k): Z'[255-k] uses -conj(E).
+        if (tid < 128) {
+            const int k = tid, k2 = M255 - k;                         // k2 = 255 (Nyquist row) for k = 0
+            const int ja = pfa_input_index(k), jb = pfa_input_index(k2 % M255);
 #pragma unroll
-            for (int q = 0; q < FT / 2; ++q) {
-                const float4 xa = Ta[q], xb = Tb[q];
-                float4 z;
+            for (int f = 0; f < FT; ++f) {
+                const float2 xa = T[k * FT + f], xb = T[k2 * FT + f];
                 {
                     const float sr = xa.x + xb.x, si = xa.y - xb.y, dr = xa.x - xb.x, di = xa.y + xb.y;
-                    const float pr = fmaf(ec, dr, -es * di), pi = fmaf(ec, di, es * dr);  // E*d
-                    z.x = sr - pi;
-                    z.y = si + pr;
+                    const float pr = fmaf(ec, dr, -es * di), pi = fmaf(ec, di, es * dr);   // E * d
+                    X[f * FS + ja] = make_float2(sr - pi, si + pr);
                 }
-                {
-                    const float sr = xa.z + xb.z, si = xa.w - xb.w, dr = xa.z - xb.z, di = xa.w + xb.w;
-                    const float pr = fmaf(ec, dr, -es * di), pi = fmaf(ec, di, es * dr);
-                    z.z = sr - pi;
-                    z.w = si + pr;
+                if (k != 0) {   // partner bin: roles swapped, E' = -conj(E) = (-ec, es)
+                    const float sr = xb.x + xa.x, si = xb.y - xa.y, dr = xb.x - xa.x, di = xb.y + xa.y;
+                    const float pr = fmaf(-ec, dr, -es * di), pi = fmaf(-ec, di, es * dr);
+                    X[f * FS + jb] = make_float2(sr - pi, si + pr);
                 }
-                A[q * QS + tid] = z;
             }
         }
         __syncthreads();
-        fft255<true>(A, Bf, tw);
+        fft255<true>(X);
+        // back to natural order: frame f becomes 510 consecutive floats (x[2m] = Re z[m], x[2m+1] = Im z[m])
+        if (tid < M255) {
+            const int j = pfa_output_index(tid);
+#pragma unroll
+            for (int f = 0; f < FT; ++f) T[f * FS + tid] = X[f * FS + j];
+        }
+        __syncthreads();
         // overlap-add the FT frames of this pass (ascending frame order), windowed and scaled by 1/510
-        const float* zf = reinterpret_cast<const float*>(Bf);
+        const float* zf = reinterpret_cast<const float*>(T);
         for (int s = tid; s < SPAN; s += 256) {
             int fhi = s / HOP;
             if (fhi > FT - 1) fhi = FT - 1;
@@ -322,8 +324,7 @@ istft_kernel(const float2* __restrict__ spec, const int* __restrict__ len, const
             float acc = 0.f;
             for (int f = flo; f <= fhi; ++f) {
                 const int n = s - f * HOP;
-                const float v = zf[((f >> 1) * QS + (n >> 1)) * 4 + (f & 1) * 2 + (n & 1)];
-                acc = fmaf(v, hw[n], acc);
+                acc = fmaf(zf[f * 2 * FS + n], hw[n], acc);
             }
             ola[pass * FT * HOP + s] += acc * (1.0f / (float)NFFT);
         }
@@ -462,8 +463,13 @@ int stft_launch(const float* wave, const int* len, const float* scale, int scale
                 int lstride, int tpad, int transform, float alpha, float beta, int planar, cudaStream_t s) {
     SNRSE_CHECK_ARG(B > 0 && tpad > 0 && lstride > HALF, "stft: need B>0, Tpad>0 and more than 255 samples");
     SNRSE_CHECK_ARG(transform == 0 || transform == 1, "stft: transform must be 0 (none) or 1 (exponent)");
-    dim3 grid(cdiv(tpad, FT), B);
-    stft_kernel<<<grid, 256, 0, s>>>(wave, len, scale, scale_is_divisor, out, lstride, tpad, transform, alpha, beta, planar);
+    // one pass of FT frames per block.  (2-4 passes per block, which amortise the per-thread window / twiddle / index
+    // constants, measured the same time on 64 x 60 s -- 1.07 ms either way: the kernel is bound by issue slots and by
+    // load / barrier latency, not by those constants -- and a longer critical path on small problems.)
+    const int npass = 1;
+    dim3 grid(cdiv(tpad, FT * npass), B);
+    stft_kernel<<<grid, 256, 0, s>>>(wave, len, scale, scale_is_divisor, out, lstride, tpad, transform, alpha, beta, planar,
+                                     npass);
     SNRSE_LAUNCH_CHECK();
     return SNRSE_OK;
 }
