@@ -29,12 +29,15 @@ def pack_batch(waves, idx, tpad):
     return y, lens
 
 
-def enhance_sweep(enhance_fn, waves, rank=0, world=1, max_batch=16, device=None, keep_audio=False, references=None):
+def enhance_sweep(enhance_fn, waves, rank=0, world=1, max_batch=16, device=None, keep_audio=False, references=None,
+                  on_audio=None):
     """Enhance the utterances `waves` (list of 1-D float tensors) this rank owns.
 
     enhance_fn(y [B, L] , lengths [B] int32) -> enhanced [B, L] (e.g. `lambda y, n: model.enhance_batch(y, lengths=n)`).
     references: optional list of clean waveforms (same lengths): adds the per-utterance SI-SDR in dB, computed on the
     device (`ops.si_sdr`; the reference computes it on host numpy arrays per file, B/eval.py:140-144).
+    on_audio(i, waveform): optional sink called with every enhanced utterance (host tensor) right after its batch, while
+    the following batches are still being enqueued (used by `wavio.enhance_files` to write wavs off the critical path).
     Returns dict(ids, samples, checksum, si_sdr, seconds, batches, audio) for this rank's shard."""
     lengths = [int(w.numel()) for w in waves]
     mine = lpt_shards(lengths, world)[rank]
@@ -57,9 +60,14 @@ def enhance_sweep(enhance_fn, waves, rank=0, world=1, max_batch=16, device=None,
             from . import ops
             x, _ = pack_batch(references, idx, tpad)
             sdrs.append(ops.si_sdr(x.to(out.device, non_blocking=True), out, lens.to(out.device)))
-        if keep_audio:
+        if keep_audio or on_audio is not None:
+            host = out.detach().to("cpu", non_blocking=False)     # one copy per batch
             for r, i in enumerate(idx):
-                audio[i] = out[r, :lengths[i]].detach().cpu()
+                a = host[r, :lengths[i]].clone()
+                if keep_audio:
+                    audio[i] = a
+                if on_audio is not None:
+                    on_audio(i, a)
     if checks and checks[0].is_cuda:
         torch.cuda.synchronize(checks[0].device)
     seconds = time.perf_counter() - t0

@@ -327,3 +327,34 @@ def test_pc_sampler_graph_replay_equals_eager_loop(sd, sde_name):
     torch.cuda.manual_seed_all(78)
     other, _ = m.get_pc_sampler("reverse_diffusion", "ald", Y, N=2, corrector_steps=1, snr=0.5, graph=True)()
     assert rel_l2(other.cpu(), outs["graph"].cpu()) > 1e-3
+
+
+def test_enhance_files_matches_per_file_enhance(v3, tmp_path):
+    """wavio.enhance_files (the eval.py file loop: wav in -> batched sweep -> wav out + SI-SDR column) writes, for every
+    file, the PCM16 rounding of what a per-file `enhance_batch` call returns on the same input."""
+    from snr_aligned_diffse_b200 import wavio
+    g = torch.Generator().manual_seed(5)
+    files, waves = [], []
+    for i, n in enumerate((6000, 9100, 6100)):
+        w = (torch.randn(n, generator=g) * 0.05 + 0.1 * torch.sin(torch.arange(n) * 0.04)).clamp(-0.9, 0.9)
+        f = str(tmp_path / "noisy" / f"u{i}.wav")
+        wavio.write_wav(f, w)
+        wavio.write_wav(str(tmp_path / "clean" / f"u{i}.wav"), w * 0.9)
+        files.append(f)
+        waves.append(wavio.read_wav(f)[0])
+
+    def fn(y, n):
+        return v3.enhance_batch(y, lengths=n, oracle=True, noise_over_clean=[0.3] * y.shape[0],
+                                noise=torch.zeros(y.shape[0], 1, 256, (y.shape[1] + 1) // 128, dtype=torch.complex64))
+
+    res = wavio.enhance_files(fn, files, str(tmp_path / "out"), clean_dir=str(tmp_path / "clean"), max_batch=2, device="cuda")
+    assert sorted(res["files"]) == ["u0.wav", "u1.wav", "u2.wav"] and all(q == q for q in res["si_sdr"])
+    for i, f in enumerate(files):
+        L = waves[i].numel()
+        tpad = 64 * (-(-(1 + L // 128) // 64))
+        y = torch.zeros(1, 128 * tpad - 1)
+        y[0, :L] = waves[i]
+        alone = fn(y.cuda(), torch.tensor([L], dtype=torch.int32, device="cuda"))[0, :L].cpu()
+        got, _ = wavio.read_wav(str(tmp_path / "out" / os.path.basename(f)))
+        want = torch.from_numpy(np.clip(np.rint(alone.double().numpy() * 32767.0), -32768, 32767).astype(np.float32) / 32768.0)
+        assert got.shape == want.shape and torch.equal(got, want)

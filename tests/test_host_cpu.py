@@ -160,3 +160,31 @@ def test_sharding_lpt():
     assert sorted(i for _, idx in batches for i in idx) == list(range(824))
     for tpad, idx in batches:
         assert len(idx) <= 16 and all(64 * (-(-(1 + L[i] // 128) // 64)) == tpad for i in idx)
+
+
+def test_wav_io_round_trip_and_file_loop(tmp_path):
+    """wavio: PCM16 read (x / 32768, torchaudio's normalisation) and write; the eval.py-style file loop with a fake
+    enhancer (halves the signal) writes one wav per input and reports SI-SDR-less metrics in id order."""
+    import numpy as np
+    from snr_aligned_diffse_b200 import wavio
+    g = torch.Generator().manual_seed(0)
+    noisy_dir, out_dir = tmp_path / "noisy", tmp_path / "out"
+    files = []
+    for i, n in enumerate((3000, 5200, 4100)):
+        w = (torch.randn(n, generator=g) * 0.1).clamp(-0.99, 0.99)
+        f = str(noisy_dir / f"p{i:03d}.wav")
+        wavio.write_wav(f, w)
+        back, sr = wavio.read_wav(f)
+        assert sr == 16000 and back.shape == w.shape and (back - w).abs().max() <= 1.0 / 32767 + 1e-7
+        files.append(f)
+    res = wavio.enhance_files(lambda y, n: 0.5 * y, files, str(out_dir), max_batch=2)
+    assert sorted(res["files"]) == ["p000.wav", "p001.wav", "p002.wav"] and len(res["ids"]) == 3
+    for f in files:
+        a, _ = wavio.read_wav(f)
+        b, _ = wavio.read_wav(str(out_dir / os.path.basename(f)))
+        assert b.shape == a.shape and (b - 0.5 * a).abs().max() <= 1.5 / 32767
+    with pytest.raises(ValueError):
+        import wave
+        with wave.open(str(tmp_path / "stereo.wav"), "wb") as w:
+            w.setnchannels(2); w.setsampwidth(2); w.setframerate(16000); w.writeframes(b"\x00" * 8)
+        wavio.read_wav(str(tmp_path / "stereo.wav"))

@@ -45,3 +45,14 @@ print("  conv signatures (GFLOP, MB, launches, ms total, TFLOP/s, ms above the s
 for (fl, by), (n, ms) in rows[:24]:
     print(f"    {fl / 1e9:9.1f} GF {by / 1e6:8.1f} MB x{n:3d} {ms:7.3f} ms {fl * n / (ms * 1e-3) / 1e12:7.0f} TF/s "
           f"{ms - fl * n / PEAK * 1e3:+7.3f} ms")
+# time by launch size class (latency-bound small maps vs throughput-bound large maps)
+cls = {}
+for (fl, by), (n, ms) in sig.items():
+    key = "<3 GF" if fl < 3e9 else "<30 GF" if fl < 30e9 else "<100 GF" if fl < 100e9 else ">=100 GF"
+    d = cls.setdefault(key, [0, 0.0, 0.0])
+    d[0] += n; d[1] += ms; d[2] += fl * n
+print("  conv launches by size class (launches, ms, ms at sustained peak, TFLOP/s):")
+for key in ("<3 GF", "<30 GF", "<100 GF", ">=100 GF"):
+    if key in cls:
+        n, ms, fl = cls[key]
+        print(f"    {key:9s} x{n:3d} {ms:7.3f} ms  ideal {fl / PEAK * 1e3:6.3f} ms  {fl / (ms * 1e-3) / 1e12:6.0f} TF/s")
