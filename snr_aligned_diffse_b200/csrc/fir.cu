@@ -40,9 +40,10 @@ __device__ __forceinline__ Norm8 load_norm(const float* __restrict__ scsh, int b
     return n;
 }
 // unpack 8 bf16 and, when enabled, normalise + SiLU + round to bf16 (what the separate pass would have stored)
+template <bool NORM>
 __device__ __forceinline__ void unpack_norm(const uint4& raw, const Norm8& n, bool inside, float* f) {
     unpack8(raw, f);
-    if (n.on && inside) {
+    if (NORM && inside) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) f[j] = __bfloat162float(__float2bfloat16(silu_f(fmaf(f[j], n.sc[j], n.sh[j]))));
     }
@@ -76,18 +77,24 @@ __device__ __forceinline__ int load_row_down(const bf16* __restrict__ img, int l
     return mask;
 }
 // horizontal [1,3,3,1]/8
+template <bool NORM>
 __device__ __forceinline__ void hfilt_down(const uint4* raw, int mask, const Norm8& nm, float* r) {
-    const float k[4] = {0.125f, 0.375f, 0.375f, 0.125f};
-    zero8(r);
+    float f0[8], f1[8], f2[8], f3[8];
+    unpack_norm<NORM>(raw[0], nm, mask & 1, f0);
+    unpack_norm<NORM>(raw[1], nm, (mask >> 1) & 1, f1);
+    unpack_norm<NORM>(raw[2], nm, (mask >> 2) & 1, f2);
+    unpack_norm<NORM>(raw[3], nm, (mask >> 3) & 1, f3);
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {
-        float f[8];
-        unpack_norm(raw[t], nm, (mask >> t) & 1, f);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) r[j] = fmaf(k[t], f[j], r[j]);
-    }
+    for (int j = 0; j < 8; ++j) r[j] = fmaf(0.125f, f3[j], fmaf(0.375f, f2[j], fmaf(0.375f, f1[j], fmaf(0.125f, f0[j], 0.f))));
 }
 
+// interior rows / columns: four unconditional 16-byte loads, no masks
+__device__ __forceinline__ void load_row_down_fast(const bf16* __restrict__ p, int ld, uint4* raw) {
+#pragma unroll
+    for (int t = 0; t < 4; ++t) raw[t] = __ldg(reinterpret_cast<const uint4*>(p + (int64_t)t * ld));
+}
+
+template <bool NORM>
 __global__ void __launch_bounds__(256)
 fir_down2_kernel(const bf16* __restrict__ x, int ld, int C, int H, int W, bf16* __restrict__ out, int out_ld, int band,
                  const float* __restrict__ scsh) {
@@ -101,31 +108,45 @@ fir_down2_kernel(const bf16* __restrict__ x, int ld, int C, int H, int W, bf16* 
     const int ho0 = blockIdx.y * band;
     const int ho1 = min(ho0 + band, Ho);
     const Norm8 nm = load_norm(scsh, b, C, c0);
+    // columns 2wo-1 .. 2wo+2 all inside the image: rows inside the image need no bounds logic at all
+    const bool col_in = wo > 0 && 2 * wo + 2 < W;
+    const int64_t rstride = (int64_t)W * ld;
+    const bf16* pcol = img + (int64_t)(2 * wo - 1) * ld + c0;   // column 2wo-1 of row 0 (only dereferenced when col_in)
+    auto load_row = [&](int hh, uint4* raw) -> int {
+        if (col_in && hh >= 0 && hh < H) {
+            load_row_down_fast(pcol + hh * rstride, ld, raw);
+            return 15;
+        }
+        return load_row_down(img, ld, H, W, hh, wo, c0, raw);
+    };
     float r0[8], r1[8], r2[8], r3[8];   // horizontally filtered rows 2ho-1 .. 2ho+2
     uint4 ra[4], rb[4];
-    int ma = load_row_down(img, ld, H, W, 2 * ho0 - 1, wo, c0, ra);
-    int mb = load_row_down(img, ld, H, W, 2 * ho0, wo, c0, rb);
-    hfilt_down(ra, ma, nm, r0);
-    hfilt_down(rb, mb, nm, r1);
-    ma = load_row_down(img, ld, H, W, 2 * ho0 + 1, wo, c0, ra);   // the two new rows of the first output row
-    mb = load_row_down(img, ld, H, W, 2 * ho0 + 2, wo, c0, rb);
-    for (int ho = ho0; ho < ho1; ++ho) {
-        hfilt_down(ra, ma, nm, r2);
-        hfilt_down(rb, mb, nm, r3);
+    int ma = load_row(2 * ho0 - 1, ra);
+    int mb = load_row(2 * ho0, rb);
+    hfilt_down<NORM>(ra, ma, nm, r0);
+    hfilt_down<NORM>(rb, mb, nm, r1);
+    ma = load_row(2 * ho0 + 1, ra);   // the two new rows of the first output row
+    mb = load_row(2 * ho0 + 2, rb);
+    bf16* op = out + (((int64_t)b * Ho + ho0) * Wo + wo) * out_ld + c0;
+    const int64_t ostride = (int64_t)Wo * out_ld;
+    for (int ho = ho0; ho < ho1; ++ho, op += ostride) {
+        hfilt_down<NORM>(ra, ma, nm, r2);
+        hfilt_down<NORM>(rb, mb, nm, r3);
         if (ho + 1 < ho1) {   // next output row's loads are in flight while this one is finished
-            ma = load_row_down(img, ld, H, W, 2 * ho + 3, wo, c0, ra);
-            mb = load_row_down(img, ld, H, W, 2 * ho + 4, wo, c0, rb);
+            ma = load_row(2 * ho + 3, ra);
+            mb = load_row(2 * ho + 4, rb);
         }
         float o[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) o[j] = 0.125f * (r0[j] + r3[j]) + 0.375f * (r1[j] + r2[j]);
-        *reinterpret_cast<uint4*>(out + (((int64_t)b * Ho + ho) * Wo + wo) * out_ld + c0) = pack8(o);
+        *reinterpret_cast<uint4*>(op) = pack8(o);
 #pragma unroll
         for (int j = 0; j < 8; ++j) { r0[j] = r2[j]; r1[j] = r3[j]; }
     }
 }
 
 // horizontal interpolation of input row hh at input column wi: ea -> output column 2wi, eb -> 2wi+1
+template <bool NORM>
 __device__ __forceinline__ void hfilt_up(const bf16* __restrict__ img, int ld, int H, int W, int hh, int wi, int c0,
                                          const Norm8& nm, float* ea, float* eb) {
     zero8(ea);
@@ -133,23 +154,24 @@ __device__ __forceinline__ void hfilt_up(const bf16* __restrict__ img, int ld, i
     if (hh < 0 || hh >= H) return;
     const bf16* row = img + (int64_t)hh * W * ld + c0;
     float m[8];
-    unpack_norm(__ldg(reinterpret_cast<const uint4*>(row + (int64_t)wi * ld)), nm, true, m);
+    unpack_norm<NORM>(__ldg(reinterpret_cast<const uint4*>(row + (int64_t)wi * ld)), nm, true, m);
 #pragma unroll
     for (int j = 0; j < 8; ++j) { ea[j] = 0.75f * m[j]; eb[j] = 0.75f * m[j]; }
     if (wi > 0) {
         float l[8];
-        unpack_norm(__ldg(reinterpret_cast<const uint4*>(row + (int64_t)(wi - 1) * ld)), nm, true, l);
+        unpack_norm<NORM>(__ldg(reinterpret_cast<const uint4*>(row + (int64_t)(wi - 1) * ld)), nm, true, l);
 #pragma unroll
         for (int j = 0; j < 8; ++j) ea[j] = fmaf(0.25f, l[j], ea[j]);
     }
     if (wi + 1 < W) {
         float rr[8];
-        unpack_norm(__ldg(reinterpret_cast<const uint4*>(row + (int64_t)(wi + 1) * ld)), nm, true, rr);
+        unpack_norm<NORM>(__ldg(reinterpret_cast<const uint4*>(row + (int64_t)(wi + 1) * ld)), nm, true, rr);
 #pragma unroll
         for (int j = 0; j < 8; ++j) eb[j] = fmaf(0.25f, rr[j], eb[j]);
     }
 }
 
+template <bool NORM>
 __global__ void __launch_bounds__(256)
 fir_up2_kernel(const bf16* __restrict__ x, int ld, int C, int H, int W, bf16* __restrict__ out, int out_ld, int band,
                const float* __restrict__ scsh) {
@@ -165,10 +187,10 @@ fir_up2_kernel(const bf16* __restrict__ x, int ld, int C, int H, int W, bf16* __
     const int h1 = min(h0 + band, H);
     float pa[8], pb[8], ca[8], cb[8], na[8], nb[8];   // rows hi-1, hi, hi+1 (a: even output column, b: odd)
     const Norm8 nm = load_norm(scsh, b, C, c0);
-    hfilt_up(img, ld, H, W, h0 - 1, wi, c0, nm, pa, pb);
-    hfilt_up(img, ld, H, W, h0, wi, c0, nm, ca, cb);
+    hfilt_up<NORM>(img, ld, H, W, h0 - 1, wi, c0, nm, pa, pb);
+    hfilt_up<NORM>(img, ld, H, W, h0, wi, c0, nm, ca, cb);
     for (int hi = h0; hi < h1; ++hi) {
-        hfilt_up(img, ld, H, W, hi + 1, wi, c0, nm, na, nb);
+        hfilt_up<NORM>(img, ld, H, W, hi + 1, wi, c0, nm, na, nb);
         float o[8];
         bf16* r_even = oimg + ((int64_t)(2 * hi) * Wo + 2 * wi) * out_ld;
         bf16* r_odd = r_even + (int64_t)Wo * out_ld;
@@ -324,7 +346,8 @@ int fir_down2_launch(const ActView* x, const ActView* out, cudaStream_t s, const
     int band = FIR_BAND;
     while (band > 1 && (int64_t)cdiv(x->W / 2, cols) * cdiv(x->H / 2, band) * x->B < 592) band >>= 1;
     dim3 grid((unsigned)cdiv(x->W / 2, cols), (unsigned)cdiv(x->H / 2, band), (unsigned)x->B);
-    fir_down2_kernel<<<grid, nthr, 0, s>>>(x->ptr, x->ld, x->C, x->H, x->W, out->ptr, out->ld, band, scsh);
+    if (scsh) fir_down2_kernel<true><<<grid, nthr, 0, s>>>(x->ptr, x->ld, x->C, x->H, x->W, out->ptr, out->ld, band, scsh);
+    else fir_down2_kernel<false><<<grid, nthr, 0, s>>>(x->ptr, x->ld, x->C, x->H, x->W, out->ptr, out->ld, band, scsh);
     SNRSE_LAUNCH_CHECK();
     return SNRSE_OK;
 }
@@ -336,7 +359,8 @@ int fir_up2_launch(const ActView* x, const ActView* out, cudaStream_t s, const f
     int band = FIR_BAND;
     while (band > 1 && (int64_t)cdiv(x->W, cols) * cdiv(x->H, band) * x->B < 592) band >>= 1;
     dim3 grid((unsigned)cdiv(x->W, cols), (unsigned)cdiv(x->H, band), (unsigned)x->B);
-    fir_up2_kernel<<<grid, nthr, 0, s>>>(x->ptr, x->ld, x->C, x->H, x->W, out->ptr, out->ld, band, scsh);
+    if (scsh) fir_up2_kernel<true><<<grid, nthr, 0, s>>>(x->ptr, x->ld, x->C, x->H, x->W, out->ptr, out->ld, band, scsh);
+    else fir_up2_kernel<false><<<grid, nthr, 0, s>>>(x->ptr, x->ld, x->C, x->H, x->W, out->ptr, out->ld, band, scsh);
     SNRSE_LAUNCH_CHECK();
     return SNRSE_OK;
 }

@@ -184,12 +184,12 @@ class NCSNppEngine:
         b, c, h, w = (int(d) for d in dims)
         return buf[: b * c * h * w].view(b, c, h, w).clone()
 
-    def profile_forward(self, x, y, t, mode=MODE_RAW):
+    def profile_forward(self, x, y, t, mode=MODE_RAW, flags=0):
         """Eager forward with CUDA events between launch groups (measurement only).
         Returns a list of dict(kind, flops, bytes, ms); kind 1 = implicit-GEMM convolution."""
         from ctypes import c_double, c_float
         B, F, T = x.shape[0], x.shape[-2], x.shape[-1]
-        self.prepare(B, F, T, 0)
+        self.prepare(B, F, T, flags)
         n = self.num_launch_groups(B, F, T)
         kinds, fl, by, ms = (c_int * n)(), (c_double * n)(), (c_double * n)(), (c_float * n)()
         cnt = c_int()

@@ -150,6 +150,12 @@ def test_snrnet_matches_golden(ops, golden_dir):
     ref = o_snrnet.snrnet_forward(synth_state_dict(snrnet_param_specs(), seed=1), feat)[:, 0]
     got = net.forward(feat.to(DEV)).cpu()
     assert (got - ref).abs().max() <= 2e-5
+    # a single 16-frame cluster (utterances shorter than 16 frames): the unbiased std over one element is NaN in the
+    # reference (torch.std, snrnet.py:84) and the NaN propagates to the estimate -- same here, for that sample only
+    one = torch.randn(2, 2, 256, 16, generator=torch.Generator().manual_seed(4))
+    ref1 = o_snrnet.snrnet_forward(synth_state_dict(snrnet_param_specs(), seed=1), one)[:, 0]
+    got1 = net.forward(one.to(DEV)).cpu()
+    assert torch.isnan(ref1).all() and torch.isnan(got1).all()
 
 
 # ----------------------------------------------------------------------------------------------- operators

@@ -21,7 +21,7 @@ y = torch.view_as_complex(torch.randn(B, 256, T, 2, generator=g)).cuda()
 t = torch.full((B,), 0.5, device="cuda")
 names = {0: "other", 1: "conv_tcgen05", 2: "groupnorm", 3: "fir", 4: "attention", 5: "thin_conv", 6: "pack_temb_head"}
 for _ in range(2):
-    prof = eng.profile_forward(x, y, t, mode=1)
+    prof = eng.profile_forward(x, y, t, mode=1, flags=flags)
 tot = sum(p["ms"] for p in prof)
 by = {}
 for p in prof:
