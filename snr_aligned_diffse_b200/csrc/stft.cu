@@ -357,19 +357,26 @@ istft_kernel(const float2* __restrict__ spec, const int* __restrict__ len, const
     }
 }
 
+// max |y| per utterance.  One block per 8192-sample chunk (a single block per utterance walked 4 s of audio in 250
+// dependent steps: 116 us for 4 MB); block maxima are merged with an integer atomicMax on the float's bit pattern
+// (non-negative floats order like unsigned integers), which is exact and order-independent.  out[] is zeroed first.
+constexpr int ABSMAX_CHUNK = 8192;
 __global__ void __launch_bounds__(256)
 absmax_kernel(const float* __restrict__ wave, const int* __restrict__ len, int lstride, float* __restrict__ out) {
     __shared__ float sm[8];
-    const int b = blockIdx.x;
+    const int b = blockIdx.y;
     const int L = len ? len[b] : lstride;
+    const int i0 = blockIdx.x * ABSMAX_CHUNK, i1 = min(i0 + ABSMAX_CHUNK, L);
+    if (i0 >= L) return;                                         // block-uniform
+    const float* w = wave + (int64_t)b * lstride;
     float m = 0.f;
-    for (int i = threadIdx.x; i < L; i += blockDim.x) m = fmaxf(m, fabsf(wave[(int64_t)b * lstride + i]));
+    for (int i = i0 + threadIdx.x; i < i1; i += 256) m = fmaxf(m, fabsf(__ldg(w + i)));
     m = warp_max(m);
     if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
     __syncthreads();
     if (threadIdx.x == 0) {
         for (int i = 1; i < 8; ++i) m = fmaxf(m, sm[i]);
-        out[b] = m;
+        atomicMax(reinterpret_cast<unsigned int*>(out + b), __float_as_uint(m));
     }
 }
 
@@ -490,7 +497,8 @@ int istft_launch(const float2* spec, const int* len, const float* scale, float* 
 }
 
 int absmax_launch(const float* wave, const int* len, int B, int lstride, float* out, cudaStream_t s) {
-    absmax_kernel<<<B, 256, 0, s>>>(wave, len, lstride, out);
+    SNRSE_CUDA(cudaMemsetAsync(out, 0, (size_t)B * sizeof(float), s));
+    absmax_kernel<<<dim3((unsigned)cdiv(lstride, ABSMAX_CHUNK), (unsigned)B), 256, 0, s>>>(wave, len, lstride, out);
     SNRSE_LAUNCH_CHECK();
     return SNRSE_OK;
 }

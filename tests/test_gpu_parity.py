@@ -79,6 +79,20 @@ def test_stft_matches_oracle_and_golden(ops, golden_dir):
     assert (feat.cpu() - g).abs().max() <= 2e-5 * g.abs().max()
 
 
+def test_absmax_is_exact_on_ragged_batches(ops):
+    """max |y| per utterance (model.py:715,726): exact (a maximum has no rounding), also with ragged lengths, lengths that
+    are not multiples of the 8192-sample block chunk, and values past len[b] that must be ignored."""
+    g = torch.Generator().manual_seed(6)
+    w = torch.randn(5, 70001, generator=g)
+    lens = torch.tensor([70001, 1, 8192, 8193, 40000], dtype=torch.int32)
+    w[1, 0] = -0.25
+    w[2, 9000] = 99.0                                  # beyond len[2]: must not count
+    got = ops.absmax(w.to(DEV), lens.to(DEV)).cpu()
+    ref = torch.stack([w[b, :int(lens[b])].abs().max() for b in range(5)])
+    assert torch.equal(got, ref)
+    assert torch.equal(ops.absmax(w.to(DEV)).cpu(), w.abs().amax(dim=1))
+
+
 def test_istft_matches_oracle_and_golden(ops, golden_dir):
     z = np.load(os.path.join(golden_dir, "frontend.npz"))
     spec = _c(z["spec"]).squeeze(1).to(DEV)
