@@ -154,6 +154,7 @@ def test_v3_scalars_bit_exact(ops, golden_dir):
         assert np.abs(nf.cpu().numpy() - sel[:, 4]).max() <= 2e-7                       # normfac: 1 ulp
 
 
+@pytest.mark.filterwarnings("ignore:std")     # torch warns about the single-cluster case exercised on purpose
 def test_snrnet_matches_golden(ops, golden_dir):
     z = np.load(os.path.join(golden_dir, "snrnet.npz"))
     net = ops.SNRNetEngine().load_state_dict(synth_state_dict(snrnet_param_specs(), seed=1), DEV)
