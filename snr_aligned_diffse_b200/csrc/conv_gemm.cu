@@ -29,7 +29,7 @@ namespace {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;                      // bf16 elements = 128 bytes = one swizzle row
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_THREADS = 224;   // warp 0: activation TMA, 1: MMA, 2-5: epilogue, 6: weight TMA
 constexpr int MAX_STAGES = 8;
 
 struct GemmArgs {
@@ -47,6 +47,8 @@ struct GemmArgs {
     int out_ld;
     int out_f32;
     int stages;
+    int a_box_bytes;   // bytes one activation TMA box delivers (rows of the tile that exist in the image)
+    long long* dbg;
 };
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -81,7 +83,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
     if (warp == 1) {
         if (lane == 0) {
             for (int s = 0; s < g.stages; ++s) {
-                ptx::mbar_init(ptx::smem_u32(&full_bar[s]), 1);
+                ptx::mbar_init(ptx::smem_u32(&full_bar[s]), 2);   // one arrival per producer warp
                 ptx::mbar_init(ptx::smem_u32(&empty_bar[s]), 1);
             }
             ptx::mbar_init(ptx::smem_u32(&accum_bar), 1);
@@ -104,36 +106,72 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
         // =========================== TMA producer ===========================
         // the whole warp walks the loop (uniform control flow), one elected lane issues
         const bool elected = ptx::elect_one();
+        long long w_empty = 0, t_begin = g.dbg ? clock64() : 0;
+        // ring slot / phase and (tap, chunk) are carried incrementally: a runtime integer division costs ~150 clk of
+        // exposed latency in this single-warp loop, and four of them per K block made the producer (570 clk per block),
+        // not the tensor pipe (130 clk), the bound of the small-map layers
+        int s = 0, tap = 0, chunk = 0;
+        uint32_t ph = 0;
         for (int kb = 0; kb < nkb; ++kb) {
-            const int s = kb % g.stages;
-            const uint32_t ph = (uint32_t)(kb / g.stages) & 1u;
+            long long t0 = g.dbg ? clock64() : 0;
             ptx::mbar_wait(ptx::smem_u32(&empty_bar[s]), ph ^ 1u);
+            if (g.dbg) w_empty += clock64() - t0;
             const uint32_t fb = ptx::smem_u32(&full_bar[s]);
             const uint32_t sa = smem_base + (uint32_t)s * stage_bytes;
             const bool seg0 = kb < nkb0;
-            const int tap = seg0 ? kb / g.c0_chunks : 0;
-            const int chunk = seg0 ? kb - tap * g.c0_chunks : kb - nkb0;
             int dh = 0, dw = 0;
             if (seg0 && g.taps0 == 9) {
-                dh = tap / 3 - 1;
-                dw = tap % 3 - 1;
+                const int t3 = (tap * 11) >> 5;          // tap / 3 for tap in 0..8
+                dh = t3 - 1;
+                dw = tap - 3 * t3 - 1;
             }
             if (elected) {
-                ptx::mbar_arrive_expect_tx(fb, stage_bytes);
+                ptx::mbar_arrive_expect_tx(fb, (uint32_t)g.a_box_bytes);
                 if (seg0) ptx::tma_load_4d(sa, &mapA0, fb, chunk * BLOCK_K, w0 + dw, h0 + dh, b);
                 else ptx::tma_load_4d(sa, &mapA1, fb, chunk * BLOCK_K, w0, h0, b);
+            }
+            __syncwarp();
+            if (++s == g.stages) { s = 0; ph ^= 1u; }
+            if (seg0) {
+                if (++chunk == g.c0_chunks) { chunk = 0; ++tap; }
+                if (kb + 1 == nkb0) chunk = 0;           // second segment (1x1 shortcut operand) restarts at chunk 0
+            } else {
+                ++chunk;
+            }
+        }
+        if (g.dbg && elected && blockIdx.y == 0) {
+            g.dbg[blockIdx.x * 8 + 0] = w_empty;
+            g.dbg[blockIdx.x * 8 + 1] = clock64() - t_begin;
+        }
+    } else if (warp == 6) {
+        // =========================== TMA producer, weights ===========================
+        // the two operands get a producer warp each: every producer step is a chain of dependent special instructions
+        // (barrier wait ~130 clk, expect-tx, TMA issue), and the small-map layers are bound by that chain, not by data
+        const bool elected = ptx::elect_one();
+        int s = 0;
+        uint32_t ph = 0;
+        for (int kb = 0; kb < nkb; ++kb) {
+            ptx::mbar_wait(ptx::smem_u32(&empty_bar[s]), ph ^ 1u);
+            const uint32_t fb = ptx::smem_u32(&full_bar[s]);
+            const uint32_t sa = smem_base + (uint32_t)s * stage_bytes;
+            if (elected) {
+                ptx::mbar_arrive_expect_tx(fb, b_stage_bytes);
                 ptx::tma_load_3d(sa + A_STAGE_BYTES, &mapB, fb, kb * BLOCK_K, n0, g.b_batched ? b : 0);
             }
             __syncwarp();
+            if (++s == g.stages) { s = 0; ph ^= 1u; }
         }
     } else if (warp == 1) {
         // =========================== MMA issuer ===========================
         const uint32_t idesc = ptx::umma_idesc_bf16(BLOCK_M, (uint32_t)g.n_tile);
         const bool elected = ptx::elect_one();
+        long long w_full = 0, w_first = 0, t_begin = g.dbg ? clock64() : 0;
+        int s = 0;
+        uint32_t ph = 0;
         for (int kb = 0; kb < nkb; ++kb) {
-            const int s = kb % g.stages;
-            const uint32_t ph = (uint32_t)(kb / g.stages) & 1u;
+            long long t0 = g.dbg ? clock64() : 0;
             ptx::mbar_wait(ptx::smem_u32(&full_bar[s]), ph);
+            if (g.dbg) { const long long d = clock64() - t0; w_full += d; if (kb == 0) w_first = d; }
             ptx::tc_fence_after();
             const uint32_t sa = smem_base + (uint32_t)s * stage_bytes;
             const uint64_t da = ptx::umma_desc_k_sw128(sa);
@@ -147,9 +185,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
                 ptx::mma_commit(ptx::smem_u32(&empty_bar[s]));  // frees the smem stage when these MMAs retire
             }
             __syncwarp();
+            if (++s == g.stages) { s = 0; ph ^= 1u; }
         }
         if (elected) ptx::mma_commit(ptx::smem_u32(&accum_bar));  // accumulator complete
         __syncwarp();
+        if (g.dbg && elected && blockIdx.y == 0) {
+            g.dbg[blockIdx.x * 8 + 2] = w_full;
+            g.dbg[blockIdx.x * 8 + 3] = clock64() - t_begin;
+            g.dbg[blockIdx.x * 8 + 4] = w_first;
+        }
     } else {
         // =========================== epilogue (warps 2..5) ===========================
         const int quarter = warp & 3;  // TMEM lane quarter this warp may access
@@ -211,6 +255,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
     }
 }
 
+}  // namespace
+extern long long* g_halo_dbg_shared;
+namespace {
 int ilog2(int v) {
     int l = 0;
     while ((1 << l) < v) ++l;
@@ -291,9 +338,11 @@ int conv_gemm_make_plan_ex(ConvGemmPlan* p, const ActView* a0, int taps0, const 
     p->smem_bytes = stages * stage_bytes + 1024;
 
     const int64_t ktot = (int64_t)64 * nkb;
-    SNRSE_TRY(tma_make_act_map(&p->mapA0, a0->ptr, a0->C, a0->W, a0->H, a0->B, a0->ld, 64, tw, th));
+    const int box_h = th;
+    p->a_box_bytes = box_h * tw * 128;
+    SNRSE_TRY(tma_make_act_map(&p->mapA0, a0->ptr, a0->C, a0->W, a0->H, a0->B, a0->ld, 64, tw, box_h));
     if (a1) {
-        SNRSE_TRY(tma_make_act_map(&p->mapA1, a1->ptr, a1->C, a1->W, a1->H, a1->B, a1->ld, 64, tw, th));
+        SNRSE_TRY(tma_make_act_map(&p->mapA1, a1->ptr, a1->C, a1->W, a1->H, a1->B, a1->ld, 64, tw, box_h));
     } else {
         p->mapA1 = p->mapA0;
     }
@@ -333,6 +382,8 @@ int conv_gemm_launch(const ConvGemmPlan* p, cudaStream_t s) {
     g.out_ld = p->out_ld;
     g.out_f32 = p->out_f32;
     g.stages = p->stages;
+    g.a_box_bytes = p->a_box_bytes;
+    g.dbg = g_halo_dbg_shared;
     dim3 grid((unsigned)(p->B * p->tiles_h * p->tiles_w), (unsigned)cdiv(p->N, p->n_tile));
     conv_gemm_kernel<<<grid, NUM_THREADS, p->smem_bytes, s>>>(p->mapA0, p->mapA1, p->mapB, g);
     SNRSE_LAUNCH_CHECK();

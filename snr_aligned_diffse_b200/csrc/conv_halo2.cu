@@ -186,7 +186,9 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
     if (warp == W_PROD_A) {
         // =========================== A producer: one halo tile per channel chunk ===========================
         const bool elected = ptx::elect_one();
-        uint32_t it = 0;   // running stage counter across tiles
+        // ring slot and phase are carried incrementally in every role below: `it % n`, `it / n` with a runtime n are two
+        // integer divisions (~100 clk of exposed latency each) per K step on a single warp's critical path
+        uint32_t s = 0, ph = 0;
         long long w_a = 0;
         DBG_T0();
         const uint32_t fb0 = ptx::mapa_rank0(ptx::smem_u32(&a_full[0]));   // leader's barriers (8 B apart)
@@ -194,8 +196,7 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
             const int tile = 2 * ct + (int)rank;
             const int b = tile / tiles_per_img, rem = tile % tiles_per_img;   // tile == n_tiles -> b == B: zero fill
             const int h0 = (rem / g.tiles_w) * SUB_ROWS * g.sub, w0 = (rem % g.tiles_w) * TW;
-            for (int j = 0; j < n_astage; ++j, ++it) {
-                const uint32_t s = it % (uint32_t)g.na, ph = (it / (uint32_t)g.na) & 1u;
+            for (int j = 0; j < n_astage; ++j) {
                 if (g.dbg) t0__ = clock64();
                 ptx::mbar_wait(ptx::smem_u32(&a_empty[s]), ph ^ 1u);
                 DBG_ADD(w_a);
@@ -218,13 +219,14 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
                     }
                 }
                 __syncwarp();
+                if (++s == (uint32_t)g.na) { s = 0; ph ^= 1u; }
             }
         }
         if (g.dbg && elected && !g.scsh) g.dbg[blockIdx.x * 8 + 6] = w_a;
     } else if (warp == W_PROD_B) {
         // =========================== B producer: weight tiles ===========================
         const bool elected = ptx::elect_one();
-        uint32_t it = 0;
+        uint32_t s = 0, ph = 0;
         long long w_b = 0;
         DBG_T0();
         const uint32_t fb0 = ptx::mapa_rank0(ptx::smem_u32(&b_full[0]));
@@ -233,8 +235,7 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
                 const bool seg0 = !(g.seq[j] & 0x80);
                 const int chunk = g.seq[j] & 0x7f;
                 const int ntap = seg0 ? 9 : 1;
-                for (int tap = 0; tap < ntap; ++tap, ++it) {
-                    const uint32_t s = it % (uint32_t)g.nb, ph = (it / (uint32_t)g.nb) & 1u;
+                for (int tap = 0; tap < ntap; ++tap) {
                     if (g.dbg) t0__ = clock64();
                     ptx::mbar_wait(ptx::smem_u32(&b_empty[s]), ph ^ 1u);
                     DBG_ADD(w_b);
@@ -245,6 +246,7 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
                         ptx::tma_load_3d_2sm(b_base + s * b_bytes, &mapB, fb0 + 8u * s, kb * 64, (int)rank * (g.N / 2), 0);
                     }
                     __syncwarp();
+                    if (++s == (uint32_t)g.nb) { s = 0; ph ^= 1u; }
                 }
             }
         }
@@ -261,7 +263,7 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
         if (rank == 0 && u < g.sub) {
             const uint32_t idesc = ptx::umma_idesc_bf16(256, (uint32_t)g.N);
             const bool elected = ptx::elect_one();
-            uint32_t ita = 0, itb = 0, itt = 0;
+            uint32_t sa = 0, pha = 0, sb = 0, phb = 0, itt = 0;
             long long w_a = 0, w_b = 0, w_acc = 0;
             const long long t_start = g.dbg ? clock64() : 0;
             DBG_T0();
@@ -272,15 +274,13 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
                 ptx::mbar_wait(ptx::smem_u32(&acc_empty[buf]), (use & 1u) ^ 1u);
                 DBG_ADD(w_acc);
                 const uint32_t d = tmem_base + buf * acc_cols + (uint32_t)(u * g.N);
-                for (int j = 0; j < n_astage; ++j, ++ita) {
-                    const uint32_t sa = ita % (uint32_t)g.na, pha = (ita / (uint32_t)g.na) & 1u;
+                for (int j = 0; j < n_astage; ++j) {
                     if (g.dbg) t0__ = clock64();
                     ptx::mbar_wait(ptx::smem_u32(&a_full[sa]), pha);
                     DBG_ADD(w_a);
                     const bool seg0 = !(g.seq[j] & 0x80);
                     const int ntap = seg0 ? 9 : 1;
-                    for (int t = 0; t < ntap; ++t, ++itb) {
-                        const uint32_t sb = itb % (uint32_t)g.nb, phb = (itb / (uint32_t)g.nb) & 1u;
+                    for (int t = 0; t < ntap; ++t) {
                         const uint32_t r = (uint32_t)t / 3u, sft = (uint32_t)t - 3u * r;
                         const uint64_t db = ptx::umma_desc_k_sw128(b_base + sb * b_bytes);
                         const uint32_t acc = (j > 0 || t > 0) ? 1u : 0u;
@@ -300,8 +300,10 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
                             ptx::mma_commit_2sm(ptx::smem_u32(&b_empty[sb]));
                         }
                         __syncwarp();
+                        if (++sb == (uint32_t)g.nb) { sb = 0; phb ^= 1u; }
                     }
                     if (elected) ptx::mma_commit_2sm(ptx::smem_u32(&a_empty[sa]));
+                    if (++sa == (uint32_t)g.na) { sa = 0; pha ^= 1u; }
                 }
                 if (elected) ptx::mma_commit_2sm(ptx::smem_u32(&acc_full[buf]));
                 __syncwarp();
@@ -324,15 +326,14 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
             const int rg = tid >> 3;
             const int rows_total = (SUB_ROWS * g.sub + 2) * HALO_W;
             const uint32_t fb0 = ptx::mapa_rank0(ptx::smem_u32(&a_full[0]));
-            uint32_t it = 0;
+            uint32_t s = 0, ph = 0;
             long long w_land = 0, t_xf = 0, t_sync = 0;
             DBG_T0();
             for (int ct = cluster_id; ct < n_ctiles; ct += n_clusters) {
                 const int tile = 2 * ct + (int)rank;
                 const int b = tile / tiles_per_img, rem = tile % tiles_per_img;
                 const int h0 = (rem / g.tiles_w) * SUB_ROWS * g.sub, w0 = (rem % g.tiles_w) * TW;
-                for (int j = 0; j < n_astage; ++j, ++it) {
-                    const uint32_t s = it % (uint32_t)g.na, ph = (it / (uint32_t)g.na) & 1u;
+                for (int j = 0; j < n_astage; ++j) {
                     const bool live = (b < g.B) && !(g.seq[j] & 0x80);   // the 1x1 shortcut operand is used raw
                     const int chunk = g.seq[j] & 0x7f;
                     // h = x * (scale/2) + shift/2  ==  (x*scale + shift)/2 exactly;  silu(t) = h + h*tanh(h)  (silu_f)
@@ -394,6 +395,7 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
                     asm volatile("bar.sync 1, 256;" ::: "memory");   // all eight normalising warps are done with the tile
                     if (tid == 0) ptx::mbar_arrive_remote(fb0 + 8u * s);
                     DBG_ADD(t_sync);
+                    if (++s == (uint32_t)g.na) { s = 0; ph ^= 1u; }
                 }
             }
             if (g.dbg && tid == 0) {   // measurement builds: replaces the producers' counters

@@ -35,6 +35,7 @@ struct ConvGemmPlan {
     int out_ld;
     int out_f32;  // 0: bf16, 1: f32
     int stages;
+    int a_box_bytes;  // bytes per activation TMA box (box height = min(tile rows, H))
     int smem_bytes;
 };
 // a0: segment-0 input view (taps0 taps); a1: optional segment-1 input (1 tap, may be null).

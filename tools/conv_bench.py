@@ -66,7 +66,7 @@ def main():
             e1.record()
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / args.iters
-            if impl in (0, 3, 5, 6) and args.debug:
+            if impl in (0, 2, 3, 5, 6) and args.debug:
                 from snr_aligned_diffse_b200 import _lib
                 dbg = torch.zeros(148 * 8, dtype=torch.int64, device="cuda")
                 _lib.load().snrse_conv_halo_set_debug(_lib.ptr(dbg))
@@ -76,6 +76,8 @@ def main():
                 d = dbg.view(148, 8).double()
                 d = d[d[:, 3] > 0]
                 names = ["mma_wait_a", "mma_wait_b", "mma_wait_acc", "mma_total", "epi_wait_full", "epi_body", "prodA_wait", "prodB_wait"]
+                if impl == 2:
+                    names = ["prod_wait_empty", "prod_total", "mma_wait_full", "mma_total", "mma_first_wait", "-", "-", "-"]
                 row[f"dbg{impl}_kcycles"] = {n: round(float(d[:, i].mean()) / 1e3, 1) for i, n in enumerate(names)}
             row[f"impl{impl}_ms"] = round(ms, 4)
             row[f"impl{impl}_tflops"] = round(flops / ms / 1e9, 1)
