@@ -100,6 +100,11 @@ class ClockSampler:
         return out
 
 
+# the workload both arms (--impl b200 / --impl reference) are measured on
+WORKLOAD = ("sebridge_v3 NCSN++ 65.6M (synthetic de-degenerated weights), 16 x 4 s @ 16 kHz per GPU (Tpad=512), 1 NFE, "
+            "SNR estimator in the loop")
+
+
 def cpu_reference_step(sd, snr_sd, wave, Z):
     """One utterance through the CPU oracle port of ScoreModel.enhance (sebridge_v3, estimator in the loop)."""
     import torch
@@ -139,8 +144,8 @@ def run_reference(args):
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
                 ms_per_step=1e3 * dt / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
                 data="synthetic", impl="reference",
-                config=dict(workload="sebridge_v3 NCSN++ 65.6M, 16 x 4 s @ 16 kHz, 1 NFE, SNR estimator in the loop",
-                            cpu_model=_cpu_model()),
+                config=dict(workload=WORKLOAD, seconds_per_utterance=SECONDS, nfe=1, cpu_model=_cpu_model(),
+                            implementation="CPU port of the reference path (oracle/), fp32, all host threads"),
                 cpu_baseline=dict(value=value, unit=UNIT, cores=cores, kind="port", sample=sample),
                 e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line), flush=True)
@@ -366,8 +371,8 @@ def run_b200(args):
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
                     ms_per_step=ms_dev / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16",
                     data="synthetic",
-                    config=dict(workload="sebridge_v3 NCSN++ 65.6M (synthetic de-degenerated weights), 16 x 4 s @ 16 kHz per GPU "
-                                         "(Tpad=512), 1 NFE, SNR estimator in the loop, CUDA graph" + (f", {args.streams} alternating enhancers (streams)" if args.streams > 1 else ""),
+                    config=dict(workload=WORKLOAD,
+                                implementation="CUDA graph" + (f", {args.streams} alternating enhancers (streams)" if args.streams > 1 else ""),
                                 global_batch=world * BATCH, seconds_per_utterance=SECONDS, nfe=1, parallelism=f"dp{world} (utterance-sharded, no collective)",
                                 l2="per-step working set 5.4 GB >> 126 MB L2, no flush needed", accumulate="fp32", storage="bf16 activations"),
                     e2e=dict(value=e2e_value, unit=UNIT, ms_per_step=ms_e2e / args.steps,
