@@ -50,7 +50,8 @@ struct Halo2Args {
     int H, W, B;
     int sub;                       // sub-tiles per super-tile (1 or 2)
     int tiles_h, tiles_w, n_tiles;
-    int N;                         // output channels == columns per accumulator (128 or 256)
+    int N;                         // columns per accumulator (128 or 256) == output channels / nsplit
+    int nsplit, n_total;           // small maps: the clusters of the upper half of the grid take output channels N..2N-1
     int na, nb;                    // ring depths
     int acc_bufs;                  // 1 or 2 TMEM accumulator sets
     int stg_bufs;                  // 1 or 2 staging tiles per epilogue warp
@@ -133,7 +134,13 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
 
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // provably warp-uniform
     const uint32_t rank = blockIdx.x & 1u;   // == %cluster_ctarank for cluster dims (2,1,1); 0 = leader (issues the MMAs)
-    const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+    // N-split (maps too small to fill the GPU with pixel tiles): cluster c < n_ctiles computes output channels 0..N-1 of
+    // tile c, cluster n_ctiles + c channels N..2N-1 of the same tile; each cluster then walks exactly one tile
+    const int n_ctiles = (g.n_tiles + 1) >> 1;   // cluster tiles = pairs of super-tiles
+    const int nhalf = (g.nsplit == 2 && (int)(blockIdx.x >> 1) >= n_ctiles) ? 1 : 0;
+    const int cluster_id = (int)(blockIdx.x >> 1) - nhalf * n_ctiles;
+    const int n_clusters = g.nsplit == 2 ? n_ctiles : (int)(gridDim.x >> 1);
+    const int n_off = nhalf * g.N;               // first output channel of this cluster
     const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t a_bytes = halo_stage_bytes(g.sub);                                   // ring slot
     const uint32_t a_tx = (uint32_t)(SUB_ROWS * g.sub + 2) * HALO_W * ROW_B;            // bytes one halo TMA box delivers
@@ -181,7 +188,6 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
     ptx::tc_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_base_smem, 0);
     const int tiles_per_img = g.tiles_h * g.tiles_w;
-    const int n_ctiles = (g.n_tiles + 1) >> 1;   // cluster tiles = pairs of super-tiles
 
     if (warp == W_PROD_A) {
         // =========================== A producer: one halo tile per channel chunk ===========================
@@ -243,7 +249,7 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
                     const int kb = seg0 ? (tap * g.c0_chunks + chunk) : (9 * g.c0_chunks + chunk);
                     if (elected) {
                         if (rank == 0) ptx::mbar_arrive_expect_tx(ptx::smem_u32(&b_full[s]), 2 * b_bytes);
-                        ptx::tma_load_3d_2sm(b_base + s * b_bytes, &mapB, fb0 + 8u * s, kb * 64, (int)rank * (g.N / 2), 0);
+                        ptx::tma_load_3d_2sm(b_base + s * b_bytes, &mapB, fb0 + 8u * s, kb * 64, n_off + (int)rank * (g.N / 2), 0);
                     }
                     __syncwarp();
                     if (++s == (uint32_t)g.nb) { s = 0; ph ^= 1u; }
@@ -457,7 +463,7 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
                 const int bb = b < g.B ? b : g.B - 1;
                 __syncwarp();
                 for (int i = lane; i < half_cols; i += 32) {
-                    const int ch = half * half_cols + i;
+                    const int ch = n_off + half * half_cols + i;
                     float v = g.bias ? __ldg(g.bias + ch) : 0.f;
                     if (g.tbias) v += __ldg(g.tbias + (int64_t)bb * g.tb_stride + ch);
                     bs[i] = v * g.scale;
@@ -482,7 +488,7 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
                     __syncwarp();
                     if (g.has_res && elected) {
                         ptx::mbar_arrive_expect_tx(my_rbar, 4096u);
-                        ptx::tma_load_4d(stg, &mapRes, my_rbar, cbase, w0, hrow, b);
+                        ptx::tma_load_4d(stg, &mapRes, my_rbar, n_off + cbase, w0, hrow, b);
                     }
                     const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * acc_cols + (uint32_t)(u * g.N + cbase);
                     float us[16], uq[16];   // this pixel's unit sums / sums of squares for the 64 channels of the pass
@@ -540,7 +546,7 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
                     ptx::fence_proxy_async();
                     __syncwarp();
                     if (elected) {
-                        ptx::tma_store_4d(&mapOut, stg, cbase, w0, hrow, b);
+                        ptx::tma_store_4d(&mapOut, stg, n_off + cbase, w0, hrow, b);
                         ptx::bulk_commit_group();
                     }
                 }
@@ -550,7 +556,7 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive_remote(ptx::mapa_rank0(ptx::smem_u32(&acc_empty[buf])));
             if (g.ustats && !(lane & 1) && b < g.B) {   // lane l holds unit ((l>>1)&15) of each 64-channel pass
-                unsigned long long* dst = g.ustats + ((int64_t)b * units + half * (units >> 1) + ((lane >> 1) & 15)) * 2;
+                unsigned long long* dst = g.ustats + ((int64_t)b * (g.n_total >> 2) + (n_off >> 2) + half * (units >> 1) + ((lane >> 1) & 15)) * 2;
                 atomicAdd(dst, tile_s0);
                 atomicAdd(dst + 1, tile_q0);
                 if (n_pass == 2) {
@@ -608,15 +614,22 @@ int conv_halo2_make_plan(ConvHaloPlan* p, const ActView* a0, const ActView* a1, 
     p->tiles_h = cdiv(a0->H, SUB_ROWS * sub);
     p->tiles_w = tiles_w;
     p->n_tiles = a0->B * p->tiles_h * p->tiles_w;
-    p->N = n_rows;
-    p->acc_bufs = (sub * n_rows <= 256) ? 2 : 1;
-    const int a_bytes = (int)halo_stage_bytes(sub), b_bytes = (n_rows / 2) * 128;
+    // N-split: with so few pixel tiles that twice as many clusters still fit the GPU, every tile is computed by two
+    // clusters, 128 output channels each (half the MMA and weight-tile time per cluster on the latency-bound small maps)
+    const int n_ctiles0 = (p->n_tiles + 1) / 2;
+    const int nsplit = (n_rows == 256 && 2 * n_ctiles0 <= g_num_sms2 / 2) ? 2 : 1;
+    const int n_loc = n_rows / nsplit;
+    p->nsplit = nsplit;
+    p->n_total = n_rows;
+    p->N = n_loc;
+    p->acc_bufs = (sub * n_loc <= 256) ? 2 : 1;
+    const int a_bytes = (int)halo_stage_bytes(sub), b_bytes = (n_loc / 2) * 128;
     const int budget = 220 * 1024;   // dynamic shared memory (static: barriers + per-warp bias slices, ~4.3 KB)
     // One A slot feeds 9 taps x SUB x 4 MMAs (>= 2300 clk): two slots hide the next tile's load.  With in-flight
     // normalisation the slot also waits for the normalising warps (load + ~2500 clk); at N=128 (64-clock MMAs) that
     // needs a third slot, paid for with single-buffered epilogue staging.
     int na = 2, stg = 2;
-    if (scsh && n_rows == 128 && sub == 2) { na = 3; stg = 1; }
+    if (scsh && n_loc == 128 && sub == 2) { na = 3; stg = 1; }
     int nb = (budget - na * a_bytes - stg * EPI_WARPS * 4096) / b_bytes;
     if (nb < 6 && stg == 2) {
         stg = 1;
@@ -628,7 +641,7 @@ int conv_halo2_make_plan(ConvHaloPlan* p, const ActView* a0, const ActView* a1, 
     p->na = na; p->nb = nb; p->stg_bufs = stg;
     p->smem_bytes = na * a_bytes + nb * b_bytes + stg * EPI_WARPS * 4096 + 1024;
     const int n_ctiles = (p->n_tiles + 1) / 2, max_clusters = g_num_sms2 / 2;
-    p->grid = 2 * (n_ctiles < max_clusters ? n_ctiles : max_clusters);
+    p->grid = nsplit == 2 ? 4 * n_ctiles : 2 * (n_ctiles < max_clusters ? n_ctiles : max_clusters);
     p->bias = bias; p->tbias = tbias; p->tb_stride = tb_stride;
     p->res = res ? res->ptr : nullptr; p->res_ld = res ? res->ld : 0;
     p->scale = scale; p->out = out; p->out_ld = out_ld;
@@ -639,7 +652,7 @@ int conv_halo2_make_plan(ConvHaloPlan* p, const ActView* a0, const ActView* a1, 
     if (a1) SNRSE_TRY(tma_make_act_map(&p->mapA1, a1->ptr, a1->C, a1->W, a1->H, a1->B, a1->ld, 64, TW, SUB_ROWS * sub));
     else p->mapA1 = p->mapA0;
     const int64_t ktot = 64 * (int64_t)(9 * p->c0_chunks + p->c1_chunks);
-    SNRSE_TRY(tma_make_wt_map(&p->mapB, wt, ktot, n_rows, 1, ktot * n_rows, 64, n_rows / 2));
+    SNRSE_TRY(tma_make_wt_map(&p->mapB, wt, ktot, n_rows, 1, ktot * n_rows, 64, n_loc / 2));
     // epilogue tiles: 32 pixels (4 image rows x 8) x 64 channels
     SNRSE_TRY(tma_make_act_map(&p->mapOut, out, n_rows, a0->W, a0->H, a0->B, out_ld, 64, TW, 4));
     if (res) SNRSE_TRY(tma_make_act_map(&p->mapRes, res->ptr, n_rows, a0->W, a0->H, a0->B, res->ld, 64, TW, 4));
@@ -670,6 +683,8 @@ int conv_halo2_make_plan_out4(ConvHaloPlan* p, const ActView* a0, const bf16* wt
     p->tiles_w = tiles_w;
     p->n_tiles = a0->B * p->tiles_h * p->tiles_w;
     p->N = 16;
+    p->nsplit = 1;
+    p->n_total = 16;
     p->acc_bufs = 2;
     const int a_bytes = (int)halo_stage_bytes(sub);
     p->na = 3; p->nb = MAX_B; p->stg_bufs = 1;
@@ -704,7 +719,7 @@ int conv_halo2_launch(const ConvHaloPlan* p, cudaStream_t s) {
     }
     g.H = p->H; g.W = p->W; g.B = p->B;
     g.sub = p->sub; g.tiles_h = p->tiles_h; g.tiles_w = p->tiles_w; g.n_tiles = p->n_tiles;
-    g.N = p->N; g.na = p->na; g.nb = p->nb; g.acc_bufs = p->acc_bufs; g.stg_bufs = p->stg_bufs;
+    g.N = p->N; g.nsplit = p->nsplit; g.n_total = p->n_total; g.na = p->na; g.nb = p->nb; g.acc_bufs = p->acc_bufs; g.stg_bufs = p->stg_bufs;
     g.has_res = p->res != nullptr;
     g.bias = p->bias; g.tbias = p->tbias; g.tb_stride = p->tb_stride;
     g.scale = p->scale;
