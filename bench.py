@@ -306,8 +306,11 @@ def run_b200(args):
         if rank == 0:
             aux = model.enhance_batch(y_dev, oracle=False, return_aux=True)[1]
             eng = model.dnn.engine
-            prof = eng.profile_forward(aux["X_T"], aux["Y"], aux["t"], mode=1)      # warm
-            prof = eng.profile_forward(aux["X_T"], aux["Y"], aux["t"], mode=1)
+            eng.profile_forward(aux["X_T"], aux["Y"], aux["t"], mode=1)             # warm
+            time.sleep(0.3)                                                          # same idle start as the timed regions
+            passes = [eng.profile_forward(aux["X_T"], aux["Y"], aux["t"], mode=1) for _ in range(5)]
+            passes.sort(key=lambda pr: sum(q["ms"] for q in pr))
+            prof = passes[len(passes) // 2]                                          # the pass with the median total time
             gemm = [p for p in prof if p["kind"] == 1]
             tot_ms = sum(p["ms"] for p in prof)
             g_ms = sum(p["ms"] for p in gemm)
