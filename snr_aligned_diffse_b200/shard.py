@@ -1,6 +1,11 @@
 """Utterance sharding for multi-GPU enhancement: utterances are independent, so a list is
-partitioned over ranks by longest-processing-time-first on the padded frame count, and every rank
-batches equal-Tpad utterances (one CUDA graph per bucket).  No collective on the data path."""
+grouped into equal-Tpad batches first and the BATCHES are partitioned over the ranks by
+longest-processing-time-first (`batch_shards`).  No collective on the data path.
+
+Sharding utterances and batching per rank afterwards (`lpt_shards` + `bucket_batches`, the first version) hands every
+rank a slice of every Tpad bucket: at 8 ranks the 824-utterance set became 14 batches per rank filled to 46 %, and
+with a measured fixed cost of ~3.7 ms per batch (graph launch, small-map latency floor, host packing) against
+2.0 us per utterance-frame the sweep scaled 6.5x.  Batch-level LPT keeps the batches full (7-8 per rank)."""
 import numpy as np
 
 HOP = 128
@@ -42,3 +47,26 @@ def bucket_batches(lengths, indices, max_batch=16):
         for k in range(0, len(idx), max_batch):
             out.append((tpad, idx[k:k + max_batch]))
     return out
+
+
+# fixed cost of one batch in utterance-frame units: fitted on B200 from the 1-GPU and 8-GPU sweeps of the 824-utterance
+# set (0.814 s for 59 batches, 0.126 s for 14 batches on the slowest rank): 3.66 ms per batch, 2.01 us per utterance-frame
+BATCH_FIXED_FRAMES = 1800
+
+
+def batch_cost(tpad, n_utt, fixed=BATCH_FIXED_FRAMES):
+    return fixed + int(tpad) * int(n_utt)
+
+
+def batch_shards(lengths, n_ranks, max_batch=16, fixed=BATCH_FIXED_FRAMES):
+    """Equal-Tpad batches of the whole list, assigned to ranks by greedy LPT on `batch_cost`:
+    returns n_ranks lists of (tpad, [utterance indices]), each in descending-Tpad order."""
+    batches = bucket_batches(lengths, range(len(lengths)), max_batch)
+    order = sorted(range(len(batches)), key=lambda k: (-batch_cost(batches[k][0], len(batches[k][1]), fixed), k))
+    loads = [0] * n_ranks
+    out = [[] for _ in range(n_ranks)]
+    for k in order:
+        r = min(range(n_ranks), key=lambda q: (loads[q], q))
+        out[r].append(k)
+        loads[r] += batch_cost(batches[k][0], len(batches[k][1]), fixed)
+    return [[batches[k] for k in sorted(ks)] for ks in out]

@@ -2,8 +2,8 @@
 
 The reference enhances one utterance per `ScoreModel.enhance` call (B/eval.py:119-132).  Utterances are
 independent (per-utterance normalisation, per-sample GroupNorm / attention), so a list is
-  1. partitioned over ranks by LPT on padded frames (`shard.lpt_shards`),
-  2. grouped into equal-Tpad batches on every rank (`shard.bucket_batches`),
+  1. grouped into equal-Tpad batches (`shard.bucket_batches`),
+  2. the batches partitioned over the ranks by LPT on a per-batch cost (`shard.batch_shards`),
   3. enhanced batch by batch with `ScoreModel.enhance_batch` (ragged lengths inside a batch),
 with NO collective on the data path.  Only the per-utterance metrics (id, samples, checksum, SI-SDR) and the
 rank timings are gathered at the end (`torch.distributed`: NCCL on GPUs, gloo in the CPU tests).
@@ -12,7 +12,7 @@ import time
 
 import torch
 
-from .shard import HOP, bucket_batches, lpt_shards
+from .shard import HOP, batch_shards
 
 
 def pack_batch(waves, idx, tpad):
@@ -40,8 +40,7 @@ def enhance_sweep(enhance_fn, waves, rank=0, world=1, max_batch=16, device=None,
     the following batches are still being enqueued (used by `wavio.enhance_files` to write wavs off the critical path).
     Returns dict(ids, samples, checksum, si_sdr, seconds, batches, audio) for this rank's shard."""
     lengths = [int(w.numel()) for w in waves]
-    mine = lpt_shards(lengths, world)[rank]
-    batches = bucket_batches(lengths, mine, max_batch)
+    batches = batch_shards(lengths, world, max_batch)[rank]
     ids, samples, checks, sdrs, audio = [], [], [], [], {}
     t0 = time.perf_counter()
     for tpad, idx in batches:

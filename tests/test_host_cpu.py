@@ -160,6 +160,18 @@ def test_sharding_lpt():
     assert sorted(i for _, idx in batches for i in idx) == list(range(824))
     for tpad, idx in batches:
         assert len(idx) <= 16 and all(64 * (-(-(1 + L[i] // 128) // 64)) == tpad for i in idx)
+    # batch-level sharding (what the sweep uses): a partition into the SAME global batches, full batches stay full,
+    # and the modelled job time (slowest rank) beats utterance-level sharding + per-rank batching
+    from snr_aligned_diffse_b200.shard import batch_cost, batch_shards
+    for g in (1, 2, 4, 8):
+        per_rank = batch_shards(L, g, max_batch=16)
+        got = sorted((tpad, tuple(idx)) for r in per_rank for tpad, idx in r)
+        assert got == sorted((tpad, tuple(idx)) for tpad, idx in batches)
+        new = max(sum(batch_cost(t, len(i)) for t, i in r) for r in per_rank)
+        old = max(sum(batch_cost(t, len(i)) for t, i in bucket_batches(L, s, 16)) for s in lpt_shards(L, g))
+        assert new <= old
+        if g == 8:
+            assert new <= 0.85 * old and max(len(r) for r in per_rank) <= 8
 
 
 def test_wav_io_round_trip_and_file_loop(tmp_path):

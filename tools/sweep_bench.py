@@ -129,9 +129,9 @@ def main():
         max_batch = 1
     waves = [synth_wave(int(l), seed=i) for i, l in enumerate(lengths)]
     # one activation arena for all buckets: sized for the largest (batch, Tpad) this rank will see
-    from snr_aligned_diffse_b200.shard import bucket_batches, lpt_shards
-    mine = lpt_shards([int(l) for l in lengths], world)[rank]
-    need = max(model.dnn.engine.workspace_bytes(len(idx), 256, tpad) for tpad, idx in bucket_batches([int(l) for l in lengths], mine, max_batch))
+    from snr_aligned_diffse_b200.shard import batch_shards
+    need = max(model.dnn.engine.workspace_bytes(len(idx), 256, tpad)
+               for tpad, idx in batch_shards([int(l) for l in lengths], world, max_batch)[rank])
     model.dnn._ensure_device_weights()
     model.dnn.engine.reserve(need)
     from snr_aligned_diffse_b200.pipeline import GraphedEnhancerCache
