@@ -32,7 +32,7 @@ class DeviceRK45Result:
         self.y, self.t, self.nfev, self.n_steps, self.n_rejected, self.status = y, t, nfev, n_steps, n_rejected, status
 
 
-def _initial_step(fun, t0, y0, f0, K, direction, t_bound, rtol, atol):
+def _initial_step(fun, t0, y0, f0, K, direction, t_bound, rtol, atol, ops=ops):
     interval = abs(t_bound - t0)
     one = (1.0,)
     d0 = ops.rk_scaled_norm(y0.reshape((1,) + y0.shape), one, 1.0, y0, None, atol, rtol)
@@ -49,10 +49,13 @@ def _initial_step(fun, t0, y0, f0, K, direction, t_bound, rtol, atol):
     return min(100 * h0, h1, interval)
 
 
-def rk45_integrate(fun, t0, y0, t_bound, rtol=1e-5, atol=1e-5, max_step=math.inf, max_nfev=None):
+def rk45_integrate(fun, t0, y0, t_bound, rtol=1e-5, atol=1e-5, max_step=math.inf, max_nfev=None, _kernels=None):
     """Integrate dy/dt = fun(t, y) from t0 to t_bound.  `fun(t: float, y: complex64 cuda tensor) -> tensor` of the same
-    shape.  Returns DeviceRK45Result with the state at t_bound (status 0) or where the solver stopped (status -1)."""
-    if not (y0.is_cuda and y0.dtype == torch.complex64):
+    shape.  Returns DeviceRK45Result with the state at t_bound (status 0) or where the solver stopped (status -1).
+    `_kernels` (tests only): an object with `rk_combine` / `rk_scaled_norm` standing in for the CUDA operators, so the
+    step controller can be checked against scipy on the CPU; the product path always uses the sm_100a library."""
+    ops = _kernels if _kernels is not None else globals()["ops"]
+    if _kernels is None and not (y0.is_cuda and y0.dtype == torch.complex64):
         raise ValueError("rk45_integrate: the state must be a complex64 CUDA tensor")
     y = y0.contiguous().clone()
     K = torch.empty((7,) + tuple(y.shape), dtype=y.dtype, device=y.device)
@@ -60,7 +63,7 @@ def rk45_integrate(fun, t0, y0, t_bound, rtol=1e-5, atol=1e-5, max_step=math.inf
     t = float(t0)
     K[0].copy_(fun(t, y))
     nfev = 1
-    h_abs = _initial_step(fun, t, y, K[0], K, direction, t_bound, rtol, atol)
+    h_abs = _initial_step(fun, t, y, K[0], K, direction, t_bound, rtol, atol, ops)
     nfev += 1
     n_steps = n_rej = 0
     status = 0

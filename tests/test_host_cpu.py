@@ -200,3 +200,41 @@ def test_wav_io_round_trip_and_file_loop(tmp_path):
         with wave.open(str(tmp_path / "stereo.wav"), "wb") as w:
             w.setnchannels(2); w.setsampwidth(2); w.setframerate(16000); w.writeframes(b"\x00" * 8)
         wavio.read_wav(str(tmp_path / "stereo.wav"))
+
+
+def test_rk45_step_controller_equals_scipy_on_cpu():
+    """The host-side step controller of the on-device ODE sampler (sgmse/sampling/ode.py) restates scipy's RK45
+    (`select_initial_step`, `rk_step`, `_step_impl`).  With the two CUDA operators replaced by float64 torch stand-ins
+    (same formulas as csrc/sampler.cu) it must take exactly scipy's steps: equal nfev and the same end state."""
+    import math
+    from scipy import integrate
+    from snr_aligned_diffse_b200.sgmse.sampling.ode import rk45_integrate
+
+    class CpuKernels:                      # what rk_combine_kernel / rk_scaled_sqnorm_kernel compute, in complex128
+        @staticmethod
+        def rk_combine(y, K, coef, h):
+            acc = sum(float(c) * K[j] for j, c in enumerate(coef))
+            return (y if y is not None else 0) + h * acc
+
+        @staticmethod
+        def rk_scaled_norm(K, coef, h, y, y2, atol, rtol):
+            num = h * sum(float(c) * K[j] for j, c in enumerate(coef))
+            mag = y.abs() if y2 is None else torch.maximum(y.abs(), y2.abs())
+            return math.sqrt(float(((num.abs() / (atol + rtol * mag)) ** 2).mean()))
+
+    g = torch.Generator().manual_seed(12)
+    y0 = torch.view_as_complex(torch.randn(3, 40, 2, generator=g, dtype=torch.float64))
+    lam = torch.view_as_complex(torch.stack([torch.rand(3, 40, generator=g, dtype=torch.float64) * 3 + 0.5,
+                                             torch.randn(3, 40, generator=g, dtype=torch.float64) * 4], -1))
+    lam_n = lam.numpy().reshape(-1)
+    for (t0, t1), rtol, atol in (((1.0, 0.03), 1e-5, 1e-5), ((1.0, 0.03), 1e-3, 1e-6), ((0.0, 0.7), 1e-6, 1e-8)):
+        res = rk45_integrate(lambda t, y: lam * y * (0.5 + t) + (1.0 - t), t0, y0, t1, rtol=rtol, atol=atol,
+                             _kernels=CpuKernels)
+        sol = integrate.solve_ivp(lambda t, y: lam_n * y * (0.5 + t) + (1.0 - t), (t0, t1), y0.numpy().reshape(-1),
+                                  rtol=rtol, atol=atol, method="RK45")
+        assert res.status == 0 and res.t == t1 and res.nfev == sol.nfev
+        ref = torch.from_numpy(sol.y[:, -1]).reshape(y0.shape)
+        assert (res.y - ref).abs().max() <= 1e-12 * float(ref.abs().max())
+    # a CPU state without stand-in kernels is refused: there is no CPU implementation behind the sampler
+    with pytest.raises(ValueError):
+        rk45_integrate(lambda t, y: y, 1.0, y0.to(torch.complex64), 0.5)
