@@ -202,6 +202,113 @@ def main():
     np.savez_compressed(os.path.join(GOLD, "pc_ouve.npz"), Y=Ypc.numpy(), noises=torch.stack(noise_list).numpy(),
                         out=ref_pc.numpy(), nfe=nfe)
 
+    # ---- (6c) Langevin corrector in the loop (correctors.py:38-57) with the reverse-diffusion predictor, OUVE, N=2
+    noise_lv = [torch.view_as_complex(torch.randn(1, 1, 256, 64, 2, generator=g) * (0.5 ** 0.5)) for _ in range(1 + 2 * 2)]
+    feed = iter(noise_lv)
+    torch.randn_like = lambda x, *a, **k: next(feed).to(x.dtype)
+    try:
+        ref_lv, nfe_lv = bb.get_pc_sampler("reverse_diffusion", "langevin", Ypc, N=2, corrector_steps=1, snr=0.5,
+                                           intermediate=False)()
+    finally:
+        torch.randn_like = orig_randn_like
+    ora_lv, _ = o_sampler.pc_sample(sd, Ypc, o_sampler.OUVE(1.5, 0.05, 0.5, N=2), noise_lv, N=2, eps=0.03, snr=0.5,
+                                    corrector="langevin")
+    report["pc_langevin"] = maxabs(torch.view_as_real(ora_lv), torch.view_as_real(ref_lv))
+    report["pc_langevin_absmax"] = float(ref_lv.abs().max())
+    assert nfe_lv == 4 and report["pc_langevin"] <= 1e-4 * report["pc_langevin_absmax"], report
+    np.savez_compressed(os.path.join(GOLD, "pc_langevin.npz"), Y=Ypc.numpy(), noises=torch.stack(noise_lv).numpy(),
+                        out=ref_lv.numpy(), nfe=nfe_lv)
+
+    # ---- (6d) Euler-Maruyama predictor (predictors.py:41-52), called directly as update_fn(x, t, y): through
+    # pc_sampler the reference hands it a 4th positional argument (sampling/__init__.py:72) that reaches
+    # OUVESDE.sde(x, t, y) (sdes.py:121,192) and raises TypeError -- pinned here as behaviour.
+    from sgmse.sampling.predictors import EulerMaruyamaPredictor as RefEM
+    sde_em = bb.sde.copy()
+    sde_em.N = 30
+    em = RefEM(sde_em, bb, probability_flow=False)
+    x_em = Ypc + 0.3 * noise_lv[0]
+    t_em = torch.tensor([0.7])
+    feed = iter([noise_lv[1]])
+    torch.randn_like = lambda x, *a, **k: next(feed).to(x.dtype)
+    try:
+        with torch.no_grad():
+            em_x, em_mean = em.update_fn(x_em, t_em, Ypc)
+    finally:
+        torch.randn_like = orig_randn_like
+    o_x, o_mean = o_sampler.em_step(sd, x_em, t_em, Ypc, o_sampler.OUVE(1.5, 0.05, 0.5, N=30), noise_lv[1], 30)
+    report["em_step"] = max(maxabs(torch.view_as_real(o_x), torch.view_as_real(em_x)),
+                            maxabs(torch.view_as_real(o_mean), torch.view_as_real(em_mean)))
+    assert report["em_step"] <= 1e-4 * float(em_x.abs().max()), report
+    em_in_loop = "no error"
+    try:
+        bb.get_pc_sampler("euler_maruyama", "none", Ypc, N=2)()
+    except TypeError as ex:
+        em_in_loop = "TypeError"
+    report["em_in_pc_sampler"] = em_in_loop
+    np.savez_compressed(os.path.join(GOLD, "em_step.npz"), Y=Ypc.numpy(), x=x_em.numpy(), t=t_em.numpy(),
+                        z=noise_lv[1].numpy(), x_new=em_x.numpy(), x_mean=em_mean.numpy(), in_loop=em_in_loop)
+
+    # ---- (6e) BBED full loop (sdes.py:240-307), reverse_diffusion + ald, T_sampling=0.5, N=2 (B=1: the reference's
+    # drift broadcast `(y-x)/(Tc-t)` with t [B] is only well-formed for one utterance)
+    bbed = make_model("bbed", "false", "bbed", T_sampling=0.5, k=2.6, theta=0.52, sigma_min=0.05, sigma_max=0.5)
+    bbed.sde.logk, bbed.sde.Eilog = float(bbed.sde.logk), float(bbed.sde.Eilog)   # numpy-2 promotion workaround
+    ref_copy = type(bbed.sde).copy
+
+    def _copy(self):
+        c = ref_copy(self)
+        c.logk, c.Eilog = float(c.logk), float(c.Eilog)
+        return c
+    type(bbed.sde).copy = _copy
+    noise_bb = [torch.view_as_complex(torch.randn(1, 1, 256, 64, 2, generator=g) * (0.5 ** 0.5)) for _ in range(1 + 2 * 2)]
+    feed = iter(noise_bb)
+    torch.randn_like = lambda x, *a, **k: next(feed).to(x.dtype)
+    try:
+        ref_bb, nfe_bb = bbed.get_pc_sampler("reverse_diffusion", "ald", Ypc, N=2, corrector_steps=1, snr=0.5,
+                                             intermediate=False)()
+    finally:
+        torch.randn_like = orig_randn_like
+        type(bbed.sde).copy = ref_copy
+    ora_bb, _ = o_sampler.pc_sample(sd, Ypc, o_sampler.BBED(0.5, 2.6, 0.52, N=2), noise_bb, N=2, eps=0.03, snr=0.5)
+    report["pc_bbed"] = maxabs(torch.view_as_real(ora_bb), torch.view_as_real(ref_bb))
+    report["pc_bbed_absmax"] = float(ref_bb.abs().max())
+    assert nfe_bb == 4 and ref_bb.dtype == torch.complex64 and report["pc_bbed"] <= 1e-4 * report["pc_bbed_absmax"], report
+    np.savez_compressed(os.path.join(GOLD, "pc_bbed.npz"), Y=Ypc.numpy(), noises=torch.stack(noise_bb).numpy(),
+                        out=ref_bb.numpy(), nfe=nfe_bb)
+
+    # ---- (5b) the reference's own fixture: dataset/VBD_SNR-5/valid/noisy/p232_001.wav with the oracle ratio of
+    # valid/active_rms.txt row 1 (eval.py:76-83,127-129: enhance(oracle=True, clean_rms, noise_rms)); composed as (5)
+    import wave as _wave
+    wf = _wave.open("/root/reference/dataset/VBD_SNR-5/valid/noisy/p232_001.wav", "rb")
+    assert wf.getframerate() == 16000 and wf.getnchannels() == 1 and wf.getsampwidth() == 2
+    pcm = np.frombuffer(wf.readframes(wf.getnframes()), dtype="<i2")
+    wf.close()
+    y_p = torch.from_numpy(pcm.astype(np.float32) / 32768.0)[None]          # torchaudio.load normalisation
+    row = open("/root/reference/dataset/VBD_SNR-5/valid/active_rms.txt").readline().split()
+    assert row[0] == "p232_001.wav"
+    clean_rms, noise_rms = float(row[1]), float(row[2])
+    ratio_p = noise_rms / clean_rms
+    Lp = y_p.shape[1]
+    tp = 64 * ((1 + Lp // 128 + 63) // 64)
+    Zp = torch.view_as_complex(torch.randn(1, 1, 256, tp, 2, generator=g) * (0.5 ** 0.5))
+    est_snr = torch.FloatTensor([ratio_p])
+    nf = y_p.abs().max().item()
+    t_ = v3.calculate_snr_direct(1, est_snr, v3.fixed_snr).detach().cpu().numpy()
+    idx_p = int(np.abs(ref_model.t_30 - t_).argmin())
+    t_ = ref_model.t_30[idx_p]
+    nf = nf * v3.calculate_normfac_direct(1, torch.FloatTensor([10 ** 0.25 * v3.fixed_snr * t_]), v3.fixed_snr)
+    Yp_ = pad_spec(torch.unsqueeze(v3._forward_transform(v3._stft(y_p / nf)), 0))
+    vt = (torch.ones(1) * t_)[:, None, None, None]
+    with torch.no_grad():
+        samp_p = v3(Yp_ + Zp * v3.sigma_max * t_, vt, Yp_)
+    xh_p = (v3.to_audio(samp_p.squeeze(), Lp) * nf).squeeze()
+    o_p = o_sampler.enhance_v3(sd, y_p, Zp, ratio_p, 0.17783, sigma_max=1.0)
+    report["p232_wave"] = maxabs(o_p["x_hat"], xh_p)
+    report["p232_wave_peak"] = float(xh_p.abs().max())
+    assert o_p["t_index"] == idx_p and report["p232_wave"] <= 1e-4 * report["p232_wave_peak"], report
+    np.savez_compressed(os.path.join(GOLD, "p232_001.npz"), y=pcm, Z_seed_note="Z drawn after all earlier draws of generator 1234",
+                        Z=Zp.numpy().astype(np.complex64), ratio=ratio_p, clean_rms=clean_rms, noise_rms=noise_rms,
+                        t_index=idx_p, t=float(t_), norm_factor=float(nf), x_hat=xh_p.numpy())
+
     # ---- (6b) BBED scalar functions (sdes.py:275-293) under the reference's pinned-numpy semantics
     from sgmse.sdes import BBED as RefBBED
     rb = RefBBED(0.999, 2.6, 0.52, N=30)

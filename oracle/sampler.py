@@ -140,10 +140,26 @@ class BBED:
         return self.std(self.T * torch.ones(batch))
 
 
+def em_step(sd, x, t, Y, sde, z, N, cfg=None, score_fn=None, probability_flow=False):
+    """EulerMaruyamaPredictor.update_fn(x, t, y) (predictors.py:41-52) on the reverse SDE of `sde`
+    (sdes.py:115-131): dt = -1/N, x_mean = x + (f - g^2 score [/2]) dt, x = x_mean + g sqrt(-dt) z.
+    (Through pc_sampler the reference passes a fourth argument and raises TypeError; only the direct call is defined.)"""
+    if score_fn is None:
+        score_fn = lambda x_, t_, y_: score_forward(sd, x_, t_, y_, "bbed", cfg)
+    with torch.no_grad():
+        dt = -1.0 / N
+        drift, g = sde.sde(x, t, Y)
+        g4 = g[:, None, None, None] if torch.is_tensor(g) else g
+        total = drift - g4 ** 2 * score_fn(x, t, Y) * (0.5 if probability_flow else 1.0)
+        x_mean = x + total * dt
+        gd = torch.zeros_like(g) if probability_flow else g
+        return x_mean + gd[:, None, None, None] * np.sqrt(-dt) * z, x_mean
+
+
 def pc_sample(sd, Y, sde, noises, N=30, eps=0.03, snr=0.5, corrector_steps=1, cfg=None,
-              score_fn=None, trace=None):
-    """get_pc_sampler(...)(), reverse_diffusion predictor + ald corrector
-    (sampling/__init__.py:54-75, predictors.py:75-80, correctors.py:69-81, sdes.py:73-91,132-140).
+              score_fn=None, trace=None, corrector="ald"):
+    """get_pc_sampler(...)(), reverse_diffusion predictor + ald (default) or langevin corrector
+    (sampling/__init__.py:54-75, predictors.py:75-80, correctors.py:38-57,69-81, sdes.py:73-91,132-140).
 
     `noises`: iterator over complex64 tensors shaped like Y, consumed in the order the reference
     calls `torch.randn_like` (prior, then per step: corrector noise(s), predictor noise)."""
@@ -164,7 +180,12 @@ def pc_sample(sd, Y, sde, noises, N=30, eps=0.03, snr=0.5, corrector_steps=1, cf
             for _ in range(corrector_steps):
                 grad = score_fn(xt, vec_t, Y)
                 noise = next(noises)
-                step_size = (snr * std) ** 2 * 2
+                if corrector == "langevin":      # correctors.py:46-52: one step size for the whole batch
+                    grad_norm = torch.norm(grad.reshape(B, -1), dim=-1).mean()
+                    noise_norm = torch.norm(noise.reshape(B, -1), dim=-1).mean()
+                    step_size = ((snr * noise_norm / grad_norm) ** 2 * 2).unsqueeze(0)
+                else:
+                    step_size = (snr * std) ** 2 * 2
                 xt_mean = xt + step_size[:, None, None, None] * grad
                 xt = xt_mean + noise * torch.sqrt(step_size * 2)[:, None, None, None]
             # predictor: reverse diffusion

@@ -42,6 +42,11 @@ class EulerMaruyamaPredictor(Predictor):
     """Fixed step dt = -1/N of the reverse SDE's continuous drift and diffusion (predictors.py:41-52)."""
 
     def update_fn(self, x, t, *args):
+        if len(args) != 1:
+            # pc_sampler calls update_fn(x, t, y, stepsize) (sampling/__init__.py:72); in the reference the extra argument
+            # reaches OUVESDE.sde / BBED.sde(x, t, y) through RSDE.rsde_parts (sdes.py:121) and raises exactly this.
+            # Pinned by tests/golden/em_step.npz ("in_loop": TypeError): the predictor only works called as (x, t, y).
+            raise TypeError(f"sde() takes 4 positional arguments but {3 + len(args)} were given")
         dt = -1.0 / self.rsde.N
         z = torch.randn_like(x)
         drift, g = self.rsde.sde(x, t, *args)

@@ -41,3 +41,26 @@ def synth_tensor(name: str, shape: Tuple[int, ...], seed: int = 0) -> torch.Tens
 
 def synth_state_dict(specs: Dict[str, Tuple[int, ...]], seed: int = 0) -> Dict[str, torch.Tensor]:
     return {k: synth_tensor(k, v, seed) for k, v in specs.items()}
+
+
+def synth_waves(batch: int, length: int, seed: int, sr: int = 16000) -> torch.Tensor:
+    """Synthetic VoiceBank-DEMAND-shaped noisy speech [batch, length] float32: six harmonics of a per-utterance pitch
+    under a slow envelope plus white noise whose level grows with the utterance index (so the SNR estimator sees
+    different inputs).  The benchmark, the reference arm and the parity tests all draw their inputs here."""
+    g = torch.Generator().manual_seed(seed)
+    t = torch.arange(length) / sr
+    waves = []
+    for b in range(batch):
+        f0 = 110.0 + 17.0 * b
+        speech = sum(torch.sin(2 * torch.pi * f0 * (k + 1) * t + k) / (k + 1) for k in range(6))
+        env = 0.5 + 0.5 * torch.sin(2 * torch.pi * (2.0 + 0.1 * b) * t)
+        noise = torch.randn(length, generator=g)
+        waves.append(0.1 * speech * env + (0.01 + 0.004 * b) * noise)
+    return torch.stack(waves).to(torch.float32)
+
+
+def synth_noise(batch: int, tpad: int, seed: int) -> torch.Tensor:
+    """Explicit unit complex normal draw Z [batch,1,256,tpad] complex64 (Var re = Var im = 1/2, as randn_like on a
+    complex tensor); parity runs feed the same Z to the reference / oracle and to the CUDA path."""
+    g = torch.Generator().manual_seed(seed)
+    return torch.view_as_complex(torch.randn(batch, 1, 256, tpad, 2, generator=g) * (0.5 ** 0.5))

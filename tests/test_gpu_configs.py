@@ -1,0 +1,186 @@
+"""Parity of the CUDA path against the CPU oracle at every BASELINE.json config shape:
+
+  config 1   1 x 2 s   (Tpad 256)       config 2   16 x 4 s (Tpad 512, the shape bench.py times), items 0 and 15,
+  1 x 4 s    (Tpad 512)                            estimator path and an oracle-SNR pass that visits other t_30 indices
+  config 3/4 1 x 10 s  (Tpad 1280)      config 5   1 x 60 s (Tpad 7552): waveform + the attention blocks at n = 7552
+  plus the reference's own wav fixture (dataset/VBD_SNR-5/valid/noisy/p232_001.wav with the active_rms.txt ratio,
+  reference output stored in tests/golden/p232_001.npz by oracle/make_golden.py).
+
+Inputs are the benchmark's (`synth.synth_waves(B, L, seed=1000)`, the SNR estimator in the loop) with an explicit noise
+draw fed to both sides.  Tolerances (bf16 activations / tensor-core operands vs the fp32 oracle): snapped
+timestep index and t exact, norm factor 1e-6 relative, network output rel-L2 <= 2e-2, enhanced waveform SI-SDR >= 30 dB
+against the oracle waveform and max-abs error <= 4 % of its peak.  Every case appends a row to
+gpurun_out/parity_rows.jsonl (collected into profiles/r02_parity.md).
+"""
+import json
+import os
+import time
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ncsnpp as o_ncsnpp, sampler as o_sampler, snrnet as o_snrnet
+from oracle.topology import NCSNppConfig, param_specs, snrnet_param_specs
+from snr_aligned_diffse_b200.synth import synth_noise, synth_state_dict, synth_waves
+
+pytestmark = pytest.mark.gpu
+
+REL_L2, SI_SDR_DB, MAXABS = 2e-2, 30.0, 4e-2
+FIXED_SNR, SR = 0.17783, 16000
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def rel_l2(a, b):
+    if a.is_complex():
+        a, b = torch.view_as_real(a), torch.view_as_real(b)
+    a, b = a.double().flatten(), b.double().flatten()
+    return float((a - b).norm() / b.norm())
+
+
+def _row(**kw):
+    d = os.path.join(ROOT, "gpurun_out")
+    os.makedirs(d, exist_ok=True)
+    with open(os.path.join(d, "parity_rows.jsonl"), "a") as f:
+        f.write(json.dumps(kw) + "\n")
+
+
+@pytest.fixture(scope="module")
+def sd():
+    return synth_state_dict(param_specs(NCSNppConfig()), seed=0)
+
+
+@pytest.fixture(scope="module")
+def snr_sd():
+    return synth_state_dict(snrnet_param_specs(), seed=1)
+
+
+@pytest.fixture(scope="module")
+def v3(sd, snr_sd):
+    from snr_aligned_diffse_b200.sgmse import model as sg_model
+    from snr_aligned_diffse_b200.sgmse.model import ScoreModel
+    from snr_aligned_diffse_b200.sgmse.snr_estimator import SNRModel
+    est = SNRModel(base_dir="")
+    est._error_loading_ema = True
+    est.load_state_dict(snr_sd)
+    est.eval(no_ema=True)
+    sg_model.set_snr_model(est)
+    m = ScoreModel.from_state_dict(sd, backbone="ncsnpp", sde="ouve", model_type="sebridge_v3", snr_conditioned="true",
+                                   fixed_snr=FIXED_SNR, theta=1.5, sigma_min=0.05, sigma_max=1.0, base_dir="")
+    return m.eval(no_ema=True)
+
+
+def _check_item(name, b, y, Z, ratio, out, aux, sd, t0):
+    """Oracle pass for item b of the batch and the three waveform / spectrogram bounds."""
+    torch.set_num_threads(os.cpu_count() or 1)
+    with torch.no_grad():
+        o = o_sampler.enhance_v3(sd, y[b:b + 1], Z[b:b + 1], ratio, FIXED_SNR, sigma_max=1.0)
+    assert int(aux["t_index"][b]) == o["t_index"] and float(aux["t"][b]) == np.float32(o["t"])
+    assert abs(float(aux["norm_factor"][b]) / o["norm_factor"] - 1) <= 1e-6
+    ref = o["x_hat"].numpy().astype(np.float64)
+    got = out[b].cpu().numpy().astype(np.float64)
+    assert np.isfinite(got).all()
+    r = rel_l2(aux["sample"][b].cpu(), o["sample"][0, 0])
+    sdr = o_sampler.si_sdr(ref, got)
+    mx = float(np.abs(got - ref).max() / np.abs(ref).max())
+    _row(case=name, item=b, t_index=o["t_index"], t=o["t"], rel_l2=r, si_sdr_db=sdr, maxabs_of_peak=mx,
+         oracle_seconds=round(time.perf_counter() - t0, 1))
+    assert r <= REL_L2 and sdr >= SI_SDR_DB and mx <= MAXABS, (name, b, r, sdr, mx)
+
+
+@pytest.mark.parametrize("name,batch,seconds,items", [
+    ("config1_1x2s", 1, 2.0, [0]),
+    ("1x4s", 1, 4.0, [0]),
+    ("config2_16x4s", 16, 4.0, [0, 15]),
+    ("config3_1x10s", 1, 10.0, [0]),
+    ("config5_1x60s", 1, 60.0, [0]),
+])
+def test_enhance_matches_oracle_at_config_shape(v3, sd, snr_sd, name, batch, seconds, items):
+    L = int(seconds * SR)
+    tpad = 64 * ((1 + L // 128 + 63) // 64)
+    y = synth_waves(batch, L, seed=1000)
+    Z = synth_noise(batch, tpad, seed=1001)
+    out, aux = v3.enhance_batch(y, oracle=False, noise=Z, return_aux=True)
+    torch.cuda.synchronize()
+    assert out.shape == (batch, L) and aux["Y"].shape[-1] == tpad
+    for b in items:
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            ratio = float(o_snrnet.estimate_noise_over_clean(snr_sd, y[b:b + 1])[0, 0])
+        assert abs(float(aux["ratio"][b]) / ratio - 1) <= 1e-4
+        _check_item(name, b, y, Z, ratio, out, aux, sd, t0)
+    v3.dnn.engine._ws.clear()          # release this shape's activation arena before the next case
+
+
+def test_bench_batch_with_oracle_snr_visits_other_timesteps(v3, sd):
+    """The 16 x 4 s bench batch again with given noise/clean ratios (enhance(oracle=True, ...), model.py:723): the
+    synthetic estimator snaps every bench utterance to t_30[29]; these ratios land on other grid points."""
+    L, tpad, B = 4 * SR, 512, 16
+    y = synth_waves(B, L, seed=1000)
+    Z = synth_noise(B, tpad, seed=1001)
+    ratios = [10 ** (-s / 20) for s in np.linspace(-5, 35, B)]
+    out, aux = v3.enhance_batch(y, oracle=True, noise_over_clean=ratios, noise=Z, return_aux=True)
+    torch.cuda.synchronize()
+    seen = set()
+    for b in (2, 7, 12):
+        _check_item("config2_16x4s_oracle_snr", b, y, Z, ratios[b], out, aux, sd, time.perf_counter())
+        seen.add(int(aux["t_index"][b]))
+    assert len(seen) == 3
+    v3.dnn.engine._ws.clear()
+
+
+class _Keep(dict):
+    """taps sink that stores only the selected module indices (a 60 s forward has 2 GB activations per module)."""
+
+    def __init__(self, keep):
+        super().__init__()
+        self.keep = set(keep)
+
+    def __setitem__(self, k, v):
+        if k in self.keep:
+            super().__setitem__(k, v.clone())
+
+
+def test_longform_attention_blocks_and_module_taps(sd):
+    """1 x 60 s (Tpad 7552): the four attention blocks run at n = 7552 / 472 tokens (16 x 472, 4 x 118 maps) -- far past
+    the n <= 1984 the operator tests cover -- and are compared per module with the oracle, together with the
+    resolution-16 / 8 / 4 blocks around them and the last full-resolution block."""
+    from snr_aligned_diffse_b200.engine import NCSNppEngine
+    eng = NCSNppEngine().load_state_dict(sd, "cuda")
+    T = 7552
+    g = torch.Generator().manual_seed(5)
+    x = torch.view_as_complex(torch.randn(1, 2, 256, T, 2, generator=g) * 0.3)
+    t = torch.tensor([0.4])
+    keep = [20, 21, 22, 23, 24, 30, 34, 37, 49, 50, 53, 74]     # 21, 23, 50: attention blocks; 34: the middle block after attention 33
+    taps = _Keep(keep)
+    torch.set_num_threads(os.cpu_count() or 1)
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        ref = o_ncsnpp.ncsnpp_forward(sd, x, t, taps=taps)
+    out = eng.forward(x[:, 0].cuda(), x[:, 1].cuda(), t.cuda(), mode=0, flags=1)
+    torch.cuda.synchronize()
+    rep = {i: rel_l2(eng.read_tap(1, 256, T, i).cpu(), taps[i]) for i in sorted(taps)}
+    r_out = rel_l2(out.cpu(), ref[:, 0])
+    _row(case="config5_1x60s_taps", out_rel_l2=r_out, taps={str(k): round(v, 5) for k, v in rep.items()},
+         oracle_seconds=round(time.perf_counter() - t0, 1))
+    assert set(rep) == set(keep)
+    assert max(rep.values()) <= REL_L2 and r_out <= REL_L2, (rep, r_out)
+
+
+def test_reference_wav_fixture_p232(v3, golden_dir):
+    """The reference's own input: valid/noisy/p232_001.wav, oracle ratio from valid/active_rms.txt row 1 (eval.py:76-83),
+    against the unmodified reference's output stored by oracle/make_golden.py (Tpad 256)."""
+    z = np.load(os.path.join(golden_dir, "p232_001.npz"))
+    y = torch.from_numpy(z["y"].astype(np.float32) / 32768.0)[None]
+    Z = torch.from_numpy(z["Z"])
+    x_hat = v3.enhance(y, y, oracle=True, clean_rms=float(z["clean_rms"]), noise_rms=float(z["noise_rms"]), noise=Z)
+    out, aux = v3.enhance_batch(y, oracle=True, noise_over_clean=[float(z["ratio"])], noise=Z, return_aux=True)
+    assert int(aux["t_index"][0]) == int(z["t_index"]) and float(aux["t"][0]) == np.float32(z["t"])
+    assert abs(float(aux["norm_factor"][0]) / float(z["norm_factor"]) - 1) <= 1e-6
+    ref = z["x_hat"].astype(np.float64)
+    assert x_hat.shape == ref.shape == (27861,)
+    sdr = o_sampler.si_sdr(ref, x_hat.astype(np.float64))
+    mx = float(np.abs(x_hat - ref).max() / np.abs(ref).max())
+    _row(case="p232_001.wav (reference fixture)", item=0, t_index=int(z["t_index"]), t=float(z["t"]), rel_l2=None,
+         si_sdr_db=sdr, maxabs_of_peak=mx)
+    assert sdr >= SI_SDR_DB and mx <= MAXABS, (sdr, mx)
