@@ -38,7 +38,7 @@ long long snrse_launch_count(void);       /* kernels launched by this library si
  *   factor (divisor when scale_is_divisor, i.e. y / norm_factor).  n_fft 510, hop 128, periodic
  *   Hann, center/reflect.  out: complex64 [B][256][tpad] (planar=0) or f32 [B][2][256][tpad]
  *   (planar=1, re/im channels).  Frames >= 1 + len/128 are zero.  transform: 0 none,
- *   1 "exponent" beta*|X|^alpha*e^{i arg X}. */
+ *   1 "exponent" beta*|X|^alpha*e^{i arg X}, 2 "log" beta*log(1+|X|)*e^{i arg X} (data_module.py:241-251). */
 int snrse_stft(const float* wave, const int* len, const float* scale, int scale_is_divisor, void* out, int B,
                int lstride, int tpad, int transform, float alpha, float beta, int planar, void* stream);
 /* snrse_istft: spec_back + SpecsDataModule.istft + output rescale (data_module.py:256-267,295-297;
@@ -47,8 +47,10 @@ int snrse_stft(const float* wave, const int* len, const float* scale, int scale_
 int64_t snrse_istft_workspace_bytes(int B, int tpad);
 int snrse_istft(const void* spec, const int* len, const float* scale, float* wave, void* workspace, int B, int lstride,
                 int tpad, int transform, float alpha, float beta, void* stream);
-/* stand-alone spec_fwd (inverse=0) / spec_back (inverse=1) on n complex64 values (data_module.py:241-267) */
-int snrse_spec_transform(const void* in, void* out, int64_t n, int inverse, float alpha, float beta, void* stream);
+/* stand-alone spec_fwd (inverse=0) / spec_back (inverse=1) on n complex64 values (data_module.py:241-267);
+ *   transform 1 "exponent" / 2 "log" as above */
+int snrse_spec_transform(const void* in, void* out, int64_t n, int inverse, int transform, float alpha, float beta,
+                         void* stream);
 /* max|y| per utterance (model.py:715,726) */
 int snrse_absmax(const float* wave, const int* len, int B, int lstride, float* out, void* stream);
 /* SI-SDR in dB of est[b][0..len[b]) against ref[b] (util/other.py:71-75; B/eval.py:140-144), double accumulation */

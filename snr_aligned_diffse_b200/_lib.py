@@ -24,7 +24,7 @@ PROTOTYPES = {
     "snrse_stft": (i32, [vp, vp, vp, i32, vp, i32, i32, i32, i32, f32, f32, i32, vp]),
     "snrse_istft_workspace_bytes": (i64, [i32, i32]),
     "snrse_istft": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, f32, vp]),
-    "snrse_spec_transform": (i32, [vp, vp, i64, i32, f32, f32, vp]),
+    "snrse_spec_transform": (i32, [vp, vp, i64, i32, i32, f32, f32, vp]),
     "snrse_si_sdr": (i32, [vp, vp, vp, i32, i32, vp, vp]),
     "snrse_absmax": (i32, [vp, vp, i32, i32, vp, vp]),
     "snrse_v3_scalars": (i32, [vp, vp, f64, f32, vp, vp, vp, vp, i32, vp]),

@@ -63,9 +63,11 @@ int snrse_istft(const void* spec, const int* len, const float* scale, float* wav
                         tpad, transform, alpha, beta, S(stream));
 }
 
-int snrse_spec_transform(const void* in, void* out, int64_t n, int inverse, float alpha, float beta, void* stream) {
+int snrse_spec_transform(const void* in, void* out, int64_t n, int inverse, int transform, float alpha, float beta,
+                         void* stream) {
     SNRSE_CHECK_ARG(in && out, "spec_transform: null pointer");
-    return spec_transform_launch(static_cast<const float2*>(in), static_cast<float2*>(out), n, inverse, alpha, beta, S(stream));
+    return spec_transform_launch(static_cast<const float2*>(in), static_cast<float2*>(out), n, inverse, transform, alpha,
+                                 beta, S(stream));
 }
 
 int snrse_si_sdr(const float* ref, const float* est, const int* len, int B, int lstride, double* out, void* stream) {

@@ -333,7 +333,9 @@ constexpr int MAX_STAT_ENTRIES = 192;   // tensors with GroupNorm statistics per
 enum { LK_OTHER = 0, LK_GEMM = 1, LK_GN = 2, LK_FIR = 3, LK_ATTN = 4, LK_THIN = 5, LK_HEAD = 6 };
 
 int rec_gemm(Plan& P, int a0, int taps0, int a1, int64_t w_off, int n_rows, int64_t bias_off, int tb_row, int res,
-             float scale, int out, int norm = 0, int want_stats = 0) {
+             float scale, int out, int norm = 0, int want_stats = 0, int algo_cin = 0) {
+    // algo_cin > 0: channel count the ALGORITHM contracts over when the operand is a zero-padded copy (the 4-channel
+    // network input enters as a 64-channel hi/lo tile): FLOPs and bytes are booked at algo_cin, not at the padded width
     P.use(a0);
     if (norm) P.use(P.t_scsh);
     int st = -1;
@@ -371,9 +373,10 @@ int rec_gemm(Plan& P, int a0, int taps0, int a1, int64_t w_off, int n_rows, int6
             return SNRSE_OK;
         }
         const double px = (double)va0.B * va0.H * va0.W;
-        const double kt = (double)taps0 * va0.C + (a1 >= 0 ? va1.C : 0);
+        const double c0 = algo_cin > 0 ? algo_cin : va0.C;
+        const double kt = (double)taps0 * c0 + (a1 >= 0 ? va1.C : 0);
         // algorithmic bytes: each operand / result once (bf16), weights once
-        const double by = 2.0 * (px * (va0.C + (a1 >= 0 ? va1.C : 0) + n_rows + (res >= 0 ? n_rows : 0)) + kt * n_rows);
+        const double by = 2.0 * (px * (c0 + (a1 >= 0 ? va1.C : 0) + n_rows + (res >= 0 ? n_rows : 0)) + kt * n_rows);
         if ((p.flags & 8) && conv_halo_eligible(&va0, taps0, n_rows)) {   // single-CTA halo kernel (cross-check)
             ConvHaloPlan hp;
             SNRSE_TRY(conv_halo_make_plan(&hp, &va0, a1 >= 0 ? &va1 : nullptr, e.wb(w_off), n_rows, bias, tb, tb_stride,
@@ -604,7 +607,7 @@ int record_plan(Plan& P) {
     int h = P.new_t(B, F, T, nf, 2);
     if (x64 >= 0) {
         const Mod m = e.mods[mi];
-        rec_gemm(P, x64, 9, -1, m.o[2], nf, m.o[1], -1, -1, 1.0f, h, 0, fusable(P, x64, nf) ? 1 : 0);
+        rec_gemm(P, x64, 9, -1, m.o[2], nf, m.o[1], -1, -1, 1.0f, h, 0, fusable(P, x64, nf) ? 1 : 0, /*algo_cin=*/4);
         P.taps[(int)mi] = h;
         ++mi;
     } else {

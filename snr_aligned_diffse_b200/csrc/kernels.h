@@ -171,7 +171,8 @@ int snr_ratio_launch(const float* g, float* ratio, int B, cudaStream_t s);
 // ----------------------------------------------------------------------------- stft.cu
 int stft_launch(const float* wave, const int* len, const float* scale, int scale_is_divisor, float* out, int B,
                 int lstride, int tpad, int transform, float alpha, float beta, int planar, cudaStream_t s);
-int spec_transform_launch(const float2* in, float2* out, int64_t n, int inverse, float alpha, float beta, cudaStream_t s);
+int spec_transform_launch(const float2* in, float2* out, int64_t n, int inverse, int transform, float alpha, float beta,
+                          cudaStream_t s);
 int absmax_launch(const float* wave, const int* len, int B, int lstride, float* out, cudaStream_t s);
 int si_sdr_launch(const float* ref, const float* est, const int* len, int B, int lstride, double* out, cudaStream_t s);
 int istft_launch(const float2* spec, const int* len, const float* scale, float* wave, float* frames_ws, int B,

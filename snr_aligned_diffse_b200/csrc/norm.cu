@@ -90,15 +90,16 @@ gn_finalize_kernel(const unsigned long long* __restrict__ src0, int U0, const un
     const int U = U0 + U1, C = 4 * U;
     if (threadIdx.x < GN_GROUPS) {
         const int upg = U / GN_GROUPS;   // units per group
-        long long sm = 0, q = 0;         // exact integer sums of the fixed-point unit values
+        long long sm = 0;                // exact integer sum of the fixed-point unit sums
+        double q = 0.0;                  // unit square sums added in a fixed order (<= 4 terms): deterministic, no wrap
         for (int k = 0; k < upg; ++k) {
             const int u = threadIdx.x * upg + k;
             const unsigned long long* p = u < U0 ? src0 + ((int64_t)b * U0 + u) * 2 : src1 + ((int64_t)b * U1 + (u - U0)) * 2;
             sm += (long long)p[0];
-            q += (long long)p[1];
+            q += gn_unfix_sq(p[1]);
         }
         const double mean = gn_unfix_sum(sm) * inv_count;
-        double var = gn_unfix_sq(q) * inv_count - mean * mean;
+        double var = q * inv_count - mean * mean;
         if (var < 0.0) var = 0.0;
         s_mean[threadIdx.x] = (float)mean;
         s_rstd[threadIdx.x] = (float)(1.0 / sqrt(var + (double)eps));

@@ -23,6 +23,23 @@ namespace {
 
 constexpr int NFFT = 510, HOP = 128, NBINS = 256, FT = 8, HALF = 255, M255 = 255;
 constexpr int FS = 256;                       // float2 stride between the frames of a transform buffer
+
+// gain g with  spec_fwd(X) = g(|X|) X  /  spec_back(S) = g(|S / beta|) S / beta   (data_module.py:241-267):
+//   transform 1 "exponent": beta |X|^(alpha-1)   /  |S|^(1/alpha - 1)
+//   transform 2 "log"     : beta log(1+|X|)/|X|  /  (exp|S| - 1)/|S|
+// 0 -> 0 in every case (abs 0, angle 0 in the reference).
+__device__ __forceinline__ float spec_gain_fwd(float mag, int transform, float alpha, float beta) {
+    if (!(mag > 0.f)) return 0.f;
+    if (transform == 2) return beta * log1pf(mag) / mag;
+    if (alpha == 1.0f) return beta;
+    return (alpha == 0.5f) ? beta / sqrtf(mag) : beta * powf(mag, alpha - 1.0f);
+}
+__device__ __forceinline__ float spec_gain_back(float mag, int transform, float alpha) {
+    if (!(mag > 0.f)) return 0.f;
+    if (transform == 2) return expm1f(mag) / mag;
+    if (alpha == 1.0f) return 1.0f;
+    return (alpha == 0.5f) ? mag : powf(mag, 1.0f / alpha - 1.0f);
+}
 constexpr int SPAN = (FT - 1) * HOP + NFFT;   // samples touched by FT consecutive frames (1406)
 
 __device__ constexpr float C3[3] = {1.f, -0.5f, -0.5f};
@@ -189,11 +206,9 @@ stft_kernel(const float* __restrict__ wave, const int* __restrict__ len, const f
             if (f0 + f >= nframes) {
                 r = 0.f;
                 i = 0.f;
-            } else if (transform == 1) {
-                // beta * |X|^alpha * e^{i arg X} = X * beta * |X|^(alpha-1), 0 -> 0  (data_module.py:241-247)
-                const float mag = sqrtf(r * r + i * i);
-                float g = 0.f;
-                if (mag > 0.f) g = (alpha == 0.5f) ? beta / sqrtf(mag) : beta * powf(mag, alpha - 1.0f);
+            } else if (transform != 0) {
+                // beta * |X|^alpha * e^{i arg X} = X * beta * |X|^(alpha-1), 0 -> 0  (data_module.py:241-251)
+                const float g = spec_gain_fwd(sqrtf(r * r + i * i), transform, alpha, beta);
                 r *= g;
                 i *= g;
             }
@@ -273,12 +288,10 @@ istft_kernel(const float2* __restrict__ spec, const int* __restrict__ len, const
                     if (t + 1 < tpad) { v.z = p[1].x; v.w = p[1].y; }
                 }
             }
-            if (transform == 1) {
+            if (transform != 0) {
                 v.x *= inv_beta; v.y *= inv_beta; v.z *= inv_beta; v.w *= inv_beta;
-                const float m0 = sqrtf(v.x * v.x + v.y * v.y), m1 = sqrtf(v.z * v.z + v.w * v.w);
-                float g0 = 0.f, g1 = 0.f;
-                if (m0 > 0.f) g0 = (alpha == 0.5f) ? m0 : powf(m0, 1.0f / alpha - 1.0f);
-                if (m1 > 0.f) g1 = (alpha == 0.5f) ? m1 : powf(m1, 1.0f / alpha - 1.0f);
+                const float g0 = spec_gain_back(sqrtf(v.x * v.x + v.y * v.y), transform, alpha);
+                const float g1 = spec_gain_back(sqrtf(v.z * v.z + v.w * v.w), transform, alpha);
                 v.x *= g0; v.y *= g0; v.z *= g1; v.w *= g1;
             }
             if (k == 0 || k == NBINS - 1) { v.y = 0.f; v.w = 0.f; }  // one-sided inverse ignores Im of DC / Nyquist
@@ -382,25 +395,19 @@ absmax_kernel(const float* __restrict__ wave, const int* __restrict__ len, int l
 
 // stand-alone spec_fwd / spec_back (data_module.py:241-267) for callers that hold a raw STFT
 __global__ void __launch_bounds__(256)
-spec_transform_kernel(const float2* __restrict__ in, float2* __restrict__ out, int64_t n, int inverse, float alpha,
-                      float beta) {
+spec_transform_kernel(const float2* __restrict__ in, float2* __restrict__ out, int64_t n, int inverse, int transform,
+                      float alpha, float beta) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float2 z = in[i];
     if (inverse) {
         z.x /= beta;
         z.y /= beta;
-        const float mag = sqrtf(z.x * z.x + z.y * z.y);
-        float g = 0.f;
-        if (mag > 0.f) g = (alpha == 0.5f) ? mag : powf(mag, 1.0f / alpha - 1.0f);
-        if (alpha == 1.0f) g = 1.0f;
+        const float g = spec_gain_back(sqrtf(z.x * z.x + z.y * z.y), transform, alpha);
         z.x *= g;
         z.y *= g;
     } else {
-        const float mag = sqrtf(z.x * z.x + z.y * z.y);
-        float g = 0.f;
-        if (mag > 0.f) g = (alpha == 0.5f) ? beta / sqrtf(mag) : beta * powf(mag, alpha - 1.0f);
-        if (alpha == 1.0f) g = beta;
+        const float g = spec_gain_fwd(sqrtf(z.x * z.x + z.y * z.y), transform, alpha, beta);
         z.x *= g;
         z.y *= g;
     }
@@ -460,8 +467,10 @@ int si_sdr_launch(const float* ref, const float* est, const int* len, int B, int
 }
 
 
-int spec_transform_launch(const float2* in, float2* out, int64_t n, int inverse, float alpha, float beta, cudaStream_t s) {
-    spec_transform_kernel<<<(unsigned)cdiv64(n, 256), 256, 0, s>>>(in, out, n, inverse, alpha, beta);
+int spec_transform_launch(const float2* in, float2* out, int64_t n, int inverse, int transform, float alpha, float beta,
+                          cudaStream_t s) {
+    SNRSE_CHECK_ARG(transform == 1 || transform == 2, "spec_transform: transform must be 1 (exponent) or 2 (log)");
+    spec_transform_kernel<<<(unsigned)cdiv64(n, 256), 256, 0, s>>>(in, out, n, inverse, transform, alpha, beta);
     SNRSE_LAUNCH_CHECK();
     return SNRSE_OK;
 }
@@ -469,7 +478,7 @@ int spec_transform_launch(const float2* in, float2* out, int64_t n, int inverse,
 int stft_launch(const float* wave, const int* len, const float* scale, int scale_is_divisor, float* out, int B,
                 int lstride, int tpad, int transform, float alpha, float beta, int planar, cudaStream_t s) {
     SNRSE_CHECK_ARG(B > 0 && tpad > 0 && lstride > HALF, "stft: need B>0, Tpad>0 and more than 255 samples");
-    SNRSE_CHECK_ARG(transform == 0 || transform == 1, "stft: transform must be 0 (none) or 1 (exponent)");
+    SNRSE_CHECK_ARG(transform >= 0 && transform <= 2, "stft: transform must be 0 (none), 1 (exponent) or 2 (log)");
     // one pass of FT frames per block.  (2-4 passes per block, which amortise the per-thread window / twiddle / index
     // constants, measured the same time on 64 x 60 s -- 1.07 ms either way: the kernel is bound by issue slots and by
     // load / barrier latency, not by those constants -- and a longer critical path on small problems.)

@@ -39,6 +39,7 @@ class NCSNppEngine:
         self.device = None
         self._ws = {}       # (B,F,T) -> (workspace tensor, flags)
         self._graphs = {}
+        self.weights_generation = 0    # bumped by every load_state_dict: tag for caches of captured CUDA graphs
 
     def __del__(self):
         try:
@@ -127,6 +128,61 @@ class NCSNppEngine:
         _lib.check(self.lib.snrse_ncsnpp_set_weights(self.h, _lib.ptr(self.blob)), "set_weights")
         self._ws.clear()
         self._graphs.clear()
+        self.weights_generation += 1
+        return self
+
+    # ------------------------------------------------------------------ flat weight file
+    FLAT_MAGIC = b"SNRSEW01"
+
+    def export_flat(self, sd, path):
+        """Write a reference-format state dict as the flat, kernel-ready weight file: 8-byte magic, 8-byte little-endian
+        header length, a JSON header (network config, blob size, sha256 of the blob, the parameter table: name, pack
+        kind, byte offset, row stride, k offset) and the packed blob exactly as the kernels read it (3x3 / 1x1 / NIN
+        weights bf16 K-major with the fused Conv_1|Conv_2 rows concatenated, fp32 biases / GroupNorm affine / Dense_0
+        block).  `load_flat` uploads the blob with one copy and no per-tensor work."""
+        import hashlib
+        import json
+        blob = self.pack_state_dict(sd)
+        raw = blob.numpy().tobytes()
+        header = dict(format="snrse_b200 packed NCSN++ weights", version=1, config={k: list(v) if isinstance(v, tuple) else v
+                                                                                  for k, v in self.cfg.items()},
+                      weight_bytes=len(raw), sha256=hashlib.sha256(raw).hexdigest(), params=self.param_table())
+        hj = json.dumps(header).encode()
+        with open(path, "wb") as f:
+            f.write(self.FLAT_MAGIC)
+            f.write(len(hj).to_bytes(8, "little"))
+            f.write(hj)
+            f.write(raw)
+        return header
+
+    @classmethod
+    def read_flat(cls, path):
+        """-> (header dict, packed blob as a uint8 host tensor); verifies magic, size and checksum."""
+        import hashlib
+        import json
+        with open(path, "rb") as f:
+            if f.read(8) != cls.FLAT_MAGIC:
+                raise ValueError(f"{path}: not a snrse_b200 flat weight file")
+            n = int.from_bytes(f.read(8), "little")
+            header = json.loads(f.read(n).decode())
+            raw = f.read()
+        if len(raw) != header["weight_bytes"] or hashlib.sha256(raw).hexdigest() != header["sha256"]:
+            raise ValueError(f"{path}: weight blob is truncated or corrupt")
+        return header, torch.frombuffer(bytearray(raw), dtype=torch.uint8)
+
+    def load_flat(self, path, device="cuda"):
+        """Upload a file written by `export_flat` (must match this engine's configuration and parameter table)."""
+        header, blob = self.read_flat(path)
+        cfg = {k: list(v) if isinstance(v, tuple) else v for k, v in self.cfg.items()}
+        if header["config"] != cfg or header["weight_bytes"] != self.weight_bytes or header["params"] != self.param_table():
+            raise ValueError(f"{path}: written for another network configuration / library layout")
+        _lib.require_device()
+        self.device = torch.device(device)
+        self.blob = blob.to(self.device)
+        _lib.check(self.lib.snrse_ncsnpp_set_weights(self.h, _lib.ptr(self.blob)), "set_weights")
+        self._ws.clear()
+        self._graphs.clear()
+        self.weights_generation += 1
         return self
 
     # ------------------------------------------------------------------ plans

@@ -46,7 +46,7 @@ def stft(wave, lengths=None, scale=None, scale_is_divisor=True, tpad=None, trans
     else:
         out = torch.empty(B, N_BINS, tpad, dtype=torch.complex64, device=wave.device)
     _lib.check(lib.snrse_stft(_lib.ptr(wave), _lib.ptr(lengths), _lib.ptr(scale), int(scale_is_divisor), _lib.ptr(out),
-                              B, L, tpad, 1 if transform else 0, alpha, beta, int(planar), _lib.stream_ptr()), "stft")
+                              B, L, tpad, int(transform), alpha, beta, int(planar), _lib.stream_ptr()), "stft")
     return out
 
 
@@ -59,7 +59,7 @@ def istft(spec, length, lengths=None, scale=None, transform=True, alpha=0.5, bet
     ws = torch.empty(int(lib.snrse_istft_workspace_bytes(B, tpad)), dtype=torch.uint8, device=spec.device)
     wave = torch.empty(B, length, dtype=torch.float32, device=spec.device)
     _lib.check(lib.snrse_istft(_lib.ptr(spec), _lib.ptr(lengths), _lib.ptr(scale), _lib.ptr(wave), _lib.ptr(ws), B,
-                               length, tpad, 1 if transform else 0, alpha, beta, _lib.stream_ptr()), "istft")
+                               length, tpad, int(transform), alpha, beta, _lib.stream_ptr()), "istft")
     return wave
 
 
@@ -105,15 +105,36 @@ def v3_scalars(ratio, peak, fixed_snr):
 
 
 def lincomb(x=None, y=None, s=None, z=None, a=None, b=None, c=None, d=None, want_mean=True, want_x=True):
-    """out_mean = a x + b y + c s; out_x = out_mean + d z  on complex64 [B, ...] tensors."""
+    """out_mean = a x + b y + c s; out_x = out_mean + d z  on complex64 [B, ...] tensors; a..d are [B] float32
+    coefficient vectors (one per operand present).  Every sampler state update is built on this call, so operands are
+    validated here: all on one CUDA device, complex64, identical shapes (the reference's elementwise ops would raise a
+    broadcast error on a mismatch), made contiguous before their raw pointers are handed to the kernel."""
     lib = _lib_dev()
-    ref = next(v for v in (x, y, s, z) if v is not None)
+    ops_ = {"x": (x, a), "y": (y, b), "s": (s, c), "z": (z, d)}
+    present = [(k, t, co) for k, (t, co) in ops_.items() if t is not None]
+    if not present:
+        raise ValueError("lincomb: no operand given")
+    ref = present[0][1]
     B = ref.shape[0]
+    tensors, coefs = {}, {}
+    for k, t, co in present:
+        if not (torch.is_tensor(t) and t.is_cuda and t.dtype == torch.complex64):
+            raise ValueError(f"lincomb: operand {k} must be a CUDA complex64 tensor (got "
+                             f"{getattr(t, 'dtype', type(t))} on {getattr(t, 'device', 'host')})")
+        if t.shape != ref.shape or t.device != ref.device:
+            raise ValueError(f"lincomb: operand {k} has shape {tuple(t.shape)} on {t.device}, expected "
+                             f"{tuple(ref.shape)} on {ref.device} (operands must match exactly; no broadcasting)")
+        if co is None or not (torch.is_tensor(co) and co.is_cuda and co.dtype == torch.float32 and co.numel() == B):
+            raise ValueError(f"lincomb: coefficient of {k} must be a CUDA float32 vector with {B} elements")
+        tensors[k], coefs[k] = t.contiguous(), co.contiguous()
     n = ref.numel() // B
-    out_mean = torch.empty_like(ref) if want_mean else None
-    out_x = torch.empty_like(ref) if want_x else None
-    _lib.check(lib.snrse_lincomb(_lib.ptr(x), _lib.ptr(y), _lib.ptr(s), _lib.ptr(z), _lib.ptr(a), _lib.ptr(b),
-                                 _lib.ptr(c), _lib.ptr(d), _lib.ptr(out_mean), _lib.ptr(out_x), B, n,
+    shape = ref.shape
+    out_mean = torch.empty(shape, dtype=torch.complex64, device=ref.device) if want_mean else None
+    out_x = torch.empty(shape, dtype=torch.complex64, device=ref.device) if want_x else None
+    g = lambda d_, k: d_.get(k)  # noqa: E731
+    _lib.check(lib.snrse_lincomb(_lib.ptr(g(tensors, "x")), _lib.ptr(g(tensors, "y")), _lib.ptr(g(tensors, "s")),
+                                 _lib.ptr(g(tensors, "z")), _lib.ptr(g(coefs, "x")), _lib.ptr(g(coefs, "y")),
+                                 _lib.ptr(g(coefs, "s")), _lib.ptr(g(coefs, "z")), _lib.ptr(out_mean), _lib.ptr(out_x), B, n,
                                  _lib.stream_ptr()), "lincomb")
     return out_mean, out_x
 

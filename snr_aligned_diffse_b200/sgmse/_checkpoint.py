@@ -13,14 +13,23 @@ from . import install_alias
 
 
 def load_checkpoint_file(path, map_location="cpu"):
-    install_alias()  # pickled `sgmse.*` class references must resolve
-    from . import data_module, sdes, snr_estimator, model  # noqa: F401  (registers sgmse.<sub> in sys.modules)
+    """torch.load of a Lightning checkpoint whose pickled class references (`sgmse.data_module.SpecsDataModule` in
+    `hyper_parameters`, model.py:93) must resolve.  The `sgmse.*` names are pointed at this package only for the duration
+    of the load and only where no other `sgmse` (e.g. the real reference, imported by the golden tooling in the same
+    process) already owns them; whatever was in sys.modules before is restored afterwards.
+    weights_only=False is required by that pickled class reference: load checkpoints from trusted sources only."""
     import sys
-    for sub in ("data_module", "sdes", "snr_estimator", "model", "sampling", "backbones", "util"):
-        mod = sys.modules.get(__package__ + "." + sub)
-        if mod is not None and "sgmse." + sub not in sys.modules:
-            sys.modules["sgmse." + sub] = mod
-    return torch.load(path, map_location=map_location, weights_only=False)
+    before = {k: v for k, v in sys.modules.items() if k == "sgmse" or k.startswith("sgmse.")}
+    foreign = {k: v for k, v in before.items() if not getattr(v, "__name__", "").startswith(__package__)}
+    try:
+        install_alias()
+        return torch.load(path, map_location=map_location, weights_only=False)
+    finally:
+        if foreign:     # another package owns `sgmse`: put its modules back, drop the aliases we added
+            for k in [k for k in sys.modules if k == "sgmse" or k.startswith("sgmse.")]:
+                if k not in before:
+                    del sys.modules[k]
+            sys.modules.update(before)
 
 
 class EMAState:
@@ -109,11 +118,21 @@ class CheckpointedModule:
     def eval(self, no_ema=False):
         return self.train(False, no_ema=no_ema)
 
-    # device management: the compute always happens on the B200; these keep call sites working
+    # device management.  The reference's eval.py calls `model.cpu()` (eval.py:101) and then runs NCSN++ on the host;
+    # this package has no CPU path: weights and compute always live on the B200.  `.cpu()` / `.to("cpu")` are accepted
+    # so that call sites keep working, do NOT move anything, and say so once; `forward` / `enhance` take host or device
+    # tensors and return results on the device the inputs came from.
     def to(self, *args, **kwargs):
+        dev = kwargs.get("device", args[0] if args else None)
+        if isinstance(dev, (str, torch.device)) and torch.device(dev).type == "cpu":
+            return self.cpu()
         return self
 
     def cpu(self):
+        if not getattr(self, "_warned_cpu", False):
+            warnings.warn("snr_aligned_diffse_b200: .cpu() / .to('cpu') is a no-op -- there is no CPU path; the network "
+                          "keeps running on the B200 (the reference would run NCSN++ on the host here, eval.py:101)")
+            self._warned_cpu = True
         return self
 
     def cuda(self, device=None):

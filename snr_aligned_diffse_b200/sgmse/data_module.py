@@ -28,8 +28,9 @@ class SpecsDataModule:
         if n_fft != 510 or hop_length != 128 or window != 'hann':
             raise NotImplementedError("the B200 front end implements the reference geometry only: "
                                       "n_fft=510, hop_length=128, periodic Hann (data_module.py:184-187)")
-        if transform_type not in ("exponent", "none"):
-            raise NotImplementedError(f"transform_type {transform_type!r} is not implemented on the B200 path")
+        if transform_type not in ("exponent", "log", "none"):
+            raise NotImplementedError(f"transform_type {transform_type!r} is not one of the reference's "
+                                      "'exponent' / 'log' / 'none' (data_module.py:241-254)")
         self.base_dir, self.format, self.batch_size = base_dir, format, batch_size
         self.n_fft, self.hop_length, self.num_frames = n_fft, hop_length, num_frames
         self.window = get_window(window, n_fft)
@@ -52,6 +53,11 @@ class SpecsDataModule:
         if self.transform_type == "none":
             return 1.0, 1.0
         return float(self.spec_abs_exponent), float(self.spec_factor)
+
+    @property
+    def transform_code(self):
+        """Kernel-side code of the spectrogram transform: 0 none, 1 exponent, 2 log (include/snrse_b200.h)."""
+        return {"none": 0, "exponent": 1, "log": 2}[self.transform_type]
 
     # ---- transforms
     def stft(self, sig):
@@ -78,8 +84,8 @@ class SpecsDataModule:
         out = torch.empty_like(s)
         lib = _lib.load()
         _lib.require_device()
-        _lib.check(lib.snrse_spec_transform(_lib.ptr(s), _lib.ptr(out), s.numel(), int(inverse), alpha, beta,
-                                            _lib.stream_ptr()), "spec_transform")
+        _lib.check(lib.snrse_spec_transform(_lib.ptr(s), _lib.ptr(out), s.numel(), int(inverse), self.transform_code,
+                                            alpha, beta, _lib.stream_ptr()), "spec_transform")
         return out.to(dev)
 
     def spec_fwd(self, spec):

@@ -96,6 +96,11 @@ class ScoreModel(CheckpointedModule):
     def _dnn_names(self):
         return list(self.dnn.param_shapes().keys())
 
+    def export_flat(self, path):
+        """Write the weights that are live now (EMA after `eval()`, raw after `eval(no_ema=True)` / `train()`) as the flat
+        kernel-ready file of `NCSNppEngine.export_flat`; `NCSNppEngine().load_flat(path)` uploads it."""
+        return self.dnn.engine.export_flat({"dnn." + k: v for k, v in self.dnn.state_dict().items()}, path)
+
     # ------------------------------------------------------------------------------ network call
     def _head_mode(self):
         if self.snr_conditioned == 'false':
@@ -137,11 +142,12 @@ class ScoreModel(CheckpointedModule):
         sde = self.sde.copy()
         sde.N = N
         kwargs = {"eps": self.t_eps, **kwargs}
-        if kwargs.get("graph"):
+        if kwargs.get("graph", None) is not False:
             # captured loops are kept per model across sampler objects; they point into the packed weight blob and the
-            # engine's activation arena, so a weight (re)load -- EMA swap, load_state_dict -- drops them
+            # engine's activation arena, so a weight (re)load -- EMA swap, load_state_dict -- drops them.  The tag is the
+            # engine's monotonically increasing weights generation (an address could be handed out again by the allocator)
             self.dnn._ensure_device_weights()
-            tag = self.dnn.engine.blob.data_ptr()
+            tag = self.dnn.engine.weights_generation
             if self.__dict__.get("_pc_graph_tag") != tag:
                 self.__dict__["_pc_graph_cache"], self.__dict__["_pc_graph_tag"] = {}, tag
             kwargs.setdefault("graph_cache", self.__dict__["_pc_graph_cache"])
@@ -203,10 +209,10 @@ class ScoreModel(CheckpointedModule):
         return (2.040166) * (0.240253 + 0.759747 * fixed_snr ** 2) ** 0.5 / ((1 + (n / s) ** 2) ** 0.5)
 
     def _spec_params(self):
-        dm = self.data_module
+        dm = self.data_module           # (kernel transform code 0 none / 1 exponent / 2 log, alpha, beta)
         if dm.transform_type == "none":
-            return False, 1.0, 1.0
-        return True, float(dm.spec_abs_exponent), float(dm.spec_factor)
+            return 0, 1.0, 1.0
+        return dm.transform_code, float(dm.spec_abs_exponent), float(dm.spec_factor)
 
     # ------------------------------------------------------------------------------ enhancement
     def enhance_batch(self, y, lengths=None, oracle=False, noise_over_clean=None, noise=None, return_aux=False):

@@ -30,14 +30,15 @@ def _time_vector(B, t, device):
 
 
 class GraphedPCLoop:
-    """The reverse loop of `pc_sampler` (sampling/__init__.py:54-75) as one CUDA graph per step.
+    """The whole reverse loop of `pc_sampler` (sampling/__init__.py:54-75) as ONE CUDA graph.
 
     Step i = corrector update(s) + predictor update at t_i: 1 + n_steps network evaluations, the complex noise draws
-    and the fused state updates.  Its scalars (t_i, step size, SDE coefficients) are host constants baked into graph i;
-    the state lives in static buffers, the graphs share one memory pool and are replayed in capture order.  Noise comes
-    from torch's CUDA generator, which advances its Philox offset on every replay."""
+    and the fused state updates; all N steps are recorded back to back into a single graph (N x ~720 kernel nodes).
+    The per-step scalars (t_i, step size, SDE coefficients) are host constants baked into the nodes of step i; the state
+    lives in static buffers.  Noise comes from torch's CUDA generator, which advances its Philox offset on every replay.
+    `per_step=True` keeps the earlier layout (one graph per step, replayed in order) for comparison."""
 
-    def __init__(self, predictor, corrector, timesteps, Y):
+    def __init__(self, predictor, corrector, timesteps, Y, per_step=False):
         dev = Y.device
         self.Y = Y.clone()
         self.x = torch.empty_like(self.Y)
@@ -66,12 +67,19 @@ class GraphedPCLoop:
             self.x.copy_(self.Y)
             one(0)                                   # eager warm-up: plans, workspaces, function attributes
             self.stream.synchronize()
-            pool = None
-            for i in range(n):
+            if per_step:
+                pool = None
+                for i in range(n):
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, pool=pool, stream=self.stream):
+                        one(i)
+                    pool = g.pool()
+                    self.graphs.append(g)
+            else:
                 g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g, pool=pool, stream=self.stream):
-                    one(i)
-                pool = g.pool()
+                with torch.cuda.graph(g, stream=self.stream):
+                    for i in range(n):
+                        one(i)
                 self.graphs.append(g)
         torch.cuda.current_stream(dev).wait_stream(self.stream)
         torch.cuda.set_rng_state(rng, dev)
@@ -89,13 +97,16 @@ class GraphedPCLoop:
 
 
 def get_pc_sampler(predictor_name, corrector_name, sde, score_fn, Y, Y_prior=None, denoise=True, eps=3e-2, snr=0.1,
-                   corrector_steps=1, probability_flow: bool = False, intermediate=False, timestep_type=None, graph=False,
+                   corrector_steps=1, probability_flow: bool = False, intermediate=False, timestep_type=None, graph=None,
                    graph_cache=None, **kwargs):
     """Predictor-corrector sampler; returns a zero-argument callable -> (sample, nfe).
 
-    `graph=True` (extension): every step of the reverse loop (corrector + predictor: network evaluations, noise draws,
-    state updates) is replayed from a CUDA graph captured on first use (`GraphedPCLoop`); `graph_cache` (a dict, e.g.
-    one per model) keeps the captured loops across sampler objects of the same shape and settings."""
+    `graph` (extension): True = the whole reverse loop (every corrector + predictor step: network evaluations, noise
+    draws, state updates) is replayed from ONE CUDA graph captured on first use (`GraphedPCLoop`); False = host loop
+    with eager launches; None (default) = eager the first time a (shape, settings) combination is seen through
+    `graph_cache`, captured and replayed from the second time on, i.e. whenever shapes repeat.  `graph_cache` (a dict,
+    e.g. one per model: `ScoreModel.get_pc_sampler` supplies it) keeps the captured loops across sampler objects;
+    `graph="per_step"` keeps one graph per reverse step."""
     predictor_cls = PredictorRegistry.get_by_name(predictor_name)
     corrector_cls = CorrectorRegistry.get_by_name(corrector_name)
     predictor = predictor_cls(sde, score_fn, probability_flow=probability_flow)
@@ -114,13 +125,25 @@ def get_pc_sampler(predictor_name, corrector_name, sde, score_fn, Y, Y_prior=Non
             # time grid on the host: every step's scalars are known before the first launch
             timesteps = torch.linspace(sde.T, eps, sde.N)
             ns = len(timesteps) * (corrector.n_steps + 1)
-            if graph:
-                key = (predictor_name, corrector_name, tuple(Y.shape), int(sde.N), float(sde.T), float(eps), float(snr),
-                       int(corrector_steps), bool(probability_flow), type(sde).__name__, id(score_fn))
-                cache = graph_cache if graph_cache is not None else _local_graphs
+            use_graph = graph
+            cache = graph_cache if graph_cache is not None else _local_graphs
+            key = (predictor_name, corrector_name, tuple(Y.shape), int(sde.N), float(sde.T), float(eps), float(snr),
+                   int(corrector_steps), bool(probability_flow), type(sde).__name__, graph == "per_step")
+            if use_graph is None:
+                # shapes repeat -> capture: the first call of a combination runs the host loop, later calls replay
+                seen = cache.get(("seen",) + key, 0)
+                cache[("seen",) + key] = seen + 1
+                use_graph = seen >= 1
+            if use_graph:
                 loop = cache.get(key)
                 if loop is None:
-                    loop = cache[key] = GraphedPCLoop(predictor, corrector, timesteps, Y)
+                    # the entry holds score_fn alive, so a cache shared between models cannot hand a loop captured for a
+                    # collected model to a new object that reuses its id()
+                    loop = GraphedPCLoop(predictor, corrector, timesteps, Y, per_step=graph == "per_step")
+                    cache[key] = loop
+                    loop.score_fn = score_fn
+                if getattr(loop, "score_fn", score_fn) is not score_fn:
+                    raise RuntimeError("graph_cache holds a loop captured for another score function; use one cache per model")
                 xt, xt_mean = loop.run(xt, Y)
                 return (xt_mean if denoise else xt), ns
             xt_mean = xt

@@ -358,3 +358,43 @@ def test_enhance_files_matches_per_file_enhance(v3, tmp_path):
         got, _ = wavio.read_wav(str(tmp_path / "out" / os.path.basename(f)))
         want = torch.from_numpy(np.clip(np.rint(alone.double().numpy() * 32767.0), -32768, 32767).astype(np.float32) / 32768.0)
         assert got.shape == want.shape and torch.equal(got, want)
+
+
+def test_flat_weight_file_loads_into_a_fresh_engine(sd, tmp_path):
+    """A file written by export_flat and uploaded with load_flat drives the network to the same bits as load_state_dict."""
+    from snr_aligned_diffse_b200.engine import NCSNppEngine
+    a = NCSNppEngine().load_state_dict(sd, "cuda")
+    path = str(tmp_path / "w.snrse")
+    a.export_flat(sd, path)
+    b = NCSNppEngine().load_flat(path)
+    g = torch.Generator().manual_seed(2)
+    x = torch.view_as_complex(torch.randn(1, 2, 256, 64, 2, generator=g) * 0.3).cuda()
+    t = torch.tensor([0.3], device="cuda")
+    assert torch.equal(torch.view_as_real(a.forward(x[:, 0], x[:, 1], t, mode=1)),
+                       torch.view_as_real(b.forward(x[:, 0], x[:, 1], t, mode=1)))
+
+
+def test_log_transform_variant(sd):
+    """transform_type='log' (data_module.py:249-251,262-264): stand-alone spec_fwd / spec_back and the fused STFT /
+    iSTFT kernels against the oracle restatement; enhance_batch runs end to end with it."""
+    from snr_aligned_diffse_b200 import ops
+    from snr_aligned_diffse_b200.sgmse.data_module import SpecsDataModule
+    dm = SpecsDataModule(transform_type="log", spec_factor=0.15)
+    g = torch.Generator().manual_seed(8)
+    w = torch.randn(2, 6000, generator=g) * 0.2
+    ref = frontend.stft(w)
+    fwd = dm.spec_fwd(ref)
+    want = frontend.spec_fwd(ref, transform_type="log")
+    assert (fwd - want).abs().max() <= 1e-6 * max(1.0, float(want.abs().max()))
+    back = dm.spec_back(want)
+    assert (back - ref).abs().max() <= 1e-4 * ref.abs().max()
+    fused = ops.stft(w.cuda(), transform=2, beta=0.15, tpad=ref.shape[-1]).cpu()
+    assert (fused - want).abs().max() <= 2e-5 * max(1.0, float(want.abs().max()))
+    wave = ops.istft(want.cuda().contiguous(), 6000, transform=2, beta=0.15).cpu()
+    assert (wave - frontend.istft(frontend.spec_back(want, transform_type="log"), 6000)).abs().max() <= 2e-5
+    from snr_aligned_diffse_b200.sgmse.model import ScoreModel
+    m = ScoreModel.from_state_dict(sd, backbone="ncsnpp", sde="ouve", model_type="sebridge_v3", snr_conditioned="true",
+                                   fixed_snr=0.17783, theta=1.5, sigma_min=0.05, sigma_max=1.0, base_dir="",
+                                   transform_type="log").eval(no_ema=True)
+    out = m.enhance(w[:1], w[:1], oracle=True, clean_rms=1.0, noise_rms=0.3)
+    assert out.shape == (6000,) and np.isfinite(out).all()

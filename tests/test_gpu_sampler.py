@@ -77,7 +77,7 @@ def test_bbed_loop_matches_reference_fixture(sd, golden_dir, monkeypatch, graph)
         # captured loop: noise comes from torch's CUDA generator inside the graph, so feed the fixture's draws by
         # patching randn_like during capture with static buffers that are refilled before the replay
         bufs = [torch.empty_like(noises[0], device="cuda") for _ in range(len(noises) - 1)]
-        feed = iter([noises[0].cuda()] + bufs * 2)             # prior draw, warm-up step, captured steps
+        feed = iter([noises[0].cuda()] + bufs[:2] + bufs)      # prior draw, eager warm-up of step 0, the captured steps
         order = []
 
         def fake(x, *a, **k):
@@ -95,3 +95,53 @@ def test_bbed_loop_matches_reference_fixture(sd, golden_dir, monkeypatch, graph)
     torch.cuda.synchronize()
     assert nfe == int(z["nfe"]) == 4 and out.dtype == torch.complex64
     assert rel_l2(out.cpu(), _c(z["out"])) <= 6e-2
+
+
+def test_whole_loop_graph_is_default_when_shapes_repeat(sd):
+    """get_pc_sampler() without a `graph` argument: the first call of a (shape, settings) combination runs the host
+    loop, the second captures the WHOLE N-step loop as one CUDA graph and later calls replay it; with the generator
+    re-seeded the three agree bit for bit, and so does the older one-graph-per-step layout."""
+    m = _model(sd, "ouve", theta=1.5, sigma_min=0.05, sigma_max=0.5)
+    g = torch.Generator().manual_seed(3)
+    Y = torch.view_as_complex(torch.randn(2, 1, 256, 64, 2, generator=g) * 0.05).cuda()
+    outs = []
+    for call in range(3):
+        torch.manual_seed(5)
+        torch.cuda.manual_seed_all(5)
+        out, nfe = m.get_pc_sampler("reverse_diffusion", "ald", Y, N=3, corrector_steps=1, snr=0.5)()
+        assert nfe == 6
+        outs.append(out.clone())
+    loops = [v for k, v in m._pc_graph_cache.items() if k[0] != "seen"]
+    assert len(loops) == 1 and len(loops[0].graphs) == 1            # one graph holds all three steps
+    assert torch.equal(torch.view_as_real(outs[0]), torch.view_as_real(outs[1]))
+    assert torch.equal(torch.view_as_real(outs[1]), torch.view_as_real(outs[2]))
+    torch.manual_seed(5)
+    torch.cuda.manual_seed_all(5)
+    per_step, _ = m.get_pc_sampler("reverse_diffusion", "ald", Y, N=3, corrector_steps=1, snr=0.5, graph="per_step")()
+    assert torch.equal(torch.view_as_real(per_step), torch.view_as_real(outs[2]))
+
+
+def test_lincomb_rejects_mismatched_operands_and_accepts_strided_ones():
+    """ops.lincomb / sdes.axpby (every sampler state update): a Y_prior whose shape differs from Y raises ValueError
+    (the reference's elementwise arithmetic raises a broadcast error there) instead of reading past the end of a buffer;
+    a non-contiguous operand (e.g. a transposed STFT view) gives the same values as its contiguous copy."""
+    from snr_aligned_diffse_b200.sgmse.sdes import OUVESDE, axpby
+    g = torch.Generator().manual_seed(9)
+    Y = torch.view_as_complex(torch.randn(2, 1, 256, 64, 2, generator=g)).cuda()
+    short = Y[..., :32].contiguous()
+    with pytest.raises(ValueError):
+        axpby(x=Y, a=1.0, y=short, b=1.0)
+    with pytest.raises(ValueError):
+        axpby(x=Y, a=1.0, y=Y.to(torch.complex128), b=1.0)
+    with pytest.raises(ValueError):
+        axpby(x=Y, a=torch.ones(3, device="cuda"), y=Y, b=1.0)
+    strided = torch.view_as_complex(torch.randn(2, 1, 64, 256, 2, generator=g)).cuda().transpose(2, 3)
+    assert not strided.is_contiguous()
+    a = axpby(x=Y, a=0.5, y=strided, b=2.0)
+    b = axpby(x=Y, a=0.5, y=strided.contiguous(), b=2.0)
+    assert a.is_contiguous() and torch.equal(torch.view_as_real(a), torch.view_as_real(b))
+    ref = 0.5 * Y + 2.0 * strided
+    assert (a - ref).abs().max() <= 1e-6 * ref.abs().max()
+    sde = OUVESDE(1.5, 0.05, 0.5, N=2)
+    x0, _ = sde.prior_sampling(strided.shape, strided)          # state built from a strided Y is a plain contiguous tensor
+    assert x0.is_contiguous() and x0.shape == strided.shape
