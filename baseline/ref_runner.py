@@ -193,6 +193,17 @@ def task_eager_gpu(a):
         torch.backends.cuda.matmul.allow_tf32 = prec == "tf32"
         torch.backends.cudnn.benchmark = True             # let cuDNN pick its best algorithm per shape
         ac = torch.bfloat16 if prec == "bf16" else None
+        if ac is not None:
+            # the reference's upfirdn2d CUDA op dispatches float / double / half only (upfirdn2d_kernel.cu:311): under
+            # bf16 autocast it raises.  Wrap the call site's symbol so FIR inputs are upcast to fp32 and the result is
+            # cast back -- a monkeypatch in this process, the reference files stay byte-identical.
+            import sgmse.backbones.ncsnpp_utils.up_or_down_sampling as uds
+            if not hasattr(uds, "_orig_upfirdn2d"):
+                uds._orig_upfirdn2d = uds.upfirdn2d
+
+                def _fir_fp32(x, *a_, **k_):
+                    return uds._orig_upfirdn2d(x.float(), *a_, **k_).to(x.dtype)
+                uds.upfirdn2d = _fir_fp32
         try:
             with torch.no_grad():
                 for _ in range(2):

@@ -15,13 +15,15 @@ import torch
 from .shard import HOP, batch_shards
 
 
-def pack_batch(waves, idx, tpad):
+def pack_batch(waves, idx, tpad, pin=False):
     """Zero-padded batch [len(idx), 128*tpad - 1] + int32 lengths for utterances `idx` of one Tpad bucket.
     The buffer length is the longest waveform with `tpad` padded frames (1 + L//128 <= tpad), so it depends on the
     bucket only and every batch of a bucket has the same shape."""
     lbuf = HOP * tpad - 1
-    y = torch.zeros(len(idx), lbuf, dtype=torch.float32)
-    lens = torch.empty(len(idx), dtype=torch.int32)
+    # pinned staging (torch's caching host allocator recycles the blocks): the host -> device copy of this batch is then
+    # truly asynchronous and overlaps the previous batch's kernels
+    y = torch.zeros(len(idx), lbuf, dtype=torch.float32, pin_memory=pin)
+    lens = torch.empty(len(idx), dtype=torch.int32, pin_memory=pin)
     for r, i in enumerate(idx):
         w = waves[i].reshape(-1)
         y[r, :w.numel()] = w
@@ -42,9 +44,13 @@ def enhance_sweep(enhance_fn, waves, rank=0, world=1, max_batch=16, device=None,
     lengths = [int(w.numel()) for w in waves]
     batches = batch_shards(lengths, world, max_batch)[rank]
     ids, samples, checks, sdrs, audio = [], [], [], [], {}
+    on_gpu = device is not None and torch.device(device).type == "cuda"
+    if on_gpu:       # device timing of the whole shard (host packing gaps included), on the stream the work is launched on
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(torch.cuda.current_stream(device))
     t0 = time.perf_counter()
     for tpad, idx in batches:
-        y, lens = pack_batch(waves, idx, tpad)
+        y, lens = pack_batch(waves, idx, tpad, pin=on_gpu)
         if device is not None:
             y, lens = y.to(device, non_blocking=True), lens.to(device, non_blocking=True)
         out = enhance_fn(y, lens)
@@ -67,13 +73,15 @@ def enhance_sweep(enhance_fn, waves, rank=0, world=1, max_batch=16, device=None,
                     audio[i] = a
                 if on_audio is not None:
                     on_audio(i, a)
-    if checks and checks[0].is_cuda:
-        torch.cuda.synchronize(checks[0].device)
-    seconds = time.perf_counter() - t0
+    if on_gpu:
+        ev1.record(torch.cuda.current_stream(device))
+        torch.cuda.synchronize(device)
+    wall = time.perf_counter() - t0
+    seconds = ev0.elapsed_time(ev1) * 1e-3 if on_gpu else wall
     checksum = torch.cat(checks).cpu().tolist() if checks else []
     si_sdr = torch.cat(sdrs).cpu().tolist() if sdrs else [float("nan")] * len(ids)
-    return dict(ids=ids, samples=samples, checksum=checksum, si_sdr=si_sdr, seconds=seconds, batches=len(batches),
-                audio=audio)
+    return dict(ids=ids, samples=samples, checksum=checksum, si_sdr=si_sdr, seconds=seconds, wall_seconds=wall,
+                batches=len(batches), audio=audio)
 
 
 def gather_metrics(local, world=1):

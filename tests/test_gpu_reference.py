@@ -1,0 +1,71 @@
+"""The CUDA path against the UNMODIFIED reference run on the same GPU box (baseline/_ref, a byte copy of
+/root/reference/sgmse-bbed made by baseline/install_ref.py; skipped where it is absent).
+
+`baseline/ref_runner.py --task parity` imports the reference in its own process, loads the same seeded weights and runs
+its own stft / SNRNet / ScoreModel.forward / to_audio on the GPU in strict fp32 (TF32 off) on the bench batch
+(16 x 4 s, `synth_waves(16, 64000, seed=1000)`, estimator in the loop, explicit noise draw).  ALL 16 utterances are then
+compared with `ScoreModel.enhance_batch` of this package: snapped timestep exact, noise/clean ratio 1e-4, norm factor
+1e-6, waveform SI-SDR >= 30 dB and max-abs error <= 4 % of peak (bf16 activations vs the fp32 reference).
+"""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import sampler as o_sampler
+from oracle.topology import NCSNppConfig, param_specs, snrnet_param_specs
+from snr_aligned_diffse_b200.synth import synth_noise, synth_state_dict, synth_waves
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HAVE_REF = os.path.isdir(os.path.join(ROOT, "baseline", "_ref", "sgmse-bbed"))
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="baseline/_ref (copy of the reference) not present")
+@pytest.mark.parametrize("batch,seconds", [(16, 4.0), (2, 10.0)], ids=["config2_16x4s", "2x10s"])
+def test_bench_batch_matches_reference_run_on_this_gpu(tmp_path, batch, seconds):
+    out_npz = str(tmp_path / "ref.npz")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "baseline", "ref_runner.py"), "--task", "parity", "--batch",
+                        str(batch), "--seconds", str(seconds), "--seed", "1000", "--device", "cuda", "--out", out_npz],
+                       capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    ref = np.load(out_npz)
+
+    from snr_aligned_diffse_b200.sgmse import model as sg_model
+    from snr_aligned_diffse_b200.sgmse.model import ScoreModel
+    from snr_aligned_diffse_b200.sgmse.snr_estimator import SNRModel
+    est = SNRModel(base_dir="")
+    est._error_loading_ema = True
+    est.load_state_dict(synth_state_dict(snrnet_param_specs(), seed=1))
+    est.eval(no_ema=True)
+    sg_model.set_snr_model(est)
+    m = ScoreModel.from_state_dict(synth_state_dict(param_specs(NCSNppConfig()), seed=0), backbone="ncsnpp", sde="ouve",
+                                   model_type="sebridge_v3", snr_conditioned="true", fixed_snr=0.17783, theta=1.5,
+                                   sigma_min=0.05, sigma_max=1.0, base_dir="").eval(no_ema=True)
+    L = int(seconds * 16000)
+    tpad = 64 * ((1 + L // 128 + 63) // 64)
+    y = synth_waves(batch, L, seed=1000)
+    Z = synth_noise(batch, tpad, seed=1001)
+    out, aux = m.enhance_batch(y, oracle=False, noise=Z, return_aux=True)
+    got = out.cpu().numpy().astype(np.float64)
+    assert got.shape == ref["x_hat"].shape == (batch, L)
+    rows = []
+    for b in range(batch):
+        assert float(aux["t"][b]) == np.float32(ref["t"][b]) and int(aux["t_index"][b]) == int(ref["idx"][b])
+        assert abs(float(aux["ratio"][b]) / float(ref["ratio"][b]) - 1) <= 1e-4
+        assert abs(float(aux["norm_factor"][b]) / float(ref["norm_factor"][b]) - 1) <= 1e-6
+        want = ref["x_hat"][b].astype(np.float64)
+        sdr = o_sampler.si_sdr(want, got[b])
+        mx = float(np.abs(got[b] - want).max() / np.abs(want).max())
+        rows.append((sdr, mx))
+    d = os.path.join(ROOT, "gpurun_out")
+    os.makedirs(d, exist_ok=True)
+    with open(os.path.join(d, "parity_rows.jsonl"), "a") as f:
+        f.write(json.dumps(dict(case=f"reference_on_gpu_{batch}x{seconds:g}s (all items)", si_sdr_db_min=min(r_[0] for r_ in rows),
+                                si_sdr_db_mean=float(np.mean([r_[0] for r_ in rows])),
+                                maxabs_of_peak_max=max(r_[1] for r_ in rows))) + "\n")
+    assert min(r_[0] for r_ in rows) >= 30.0 and max(r_[1] for r_ in rows) <= 4e-2, rows
