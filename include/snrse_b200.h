@@ -30,6 +30,8 @@ int snrse_version(void);
 const char* snrse_last_error(void);       /* thread-local message of the last failing call */
 int snrse_device_check(void);             /* 0 iff the current device is compute capability 10.x */
 long long snrse_launch_count(void);       /* kernels launched by this library since it was loaded */
+/* Measurement / debug entry points (per-launch-group timing, activation taps, cycle counters) are NOT part of this
+ * ABI: they are declared in snrse_b200_debug.h. */
 
 /* ---------------------------------------------------------------- signal front / back end ------
  * snrse_stft: SpecsDataModule.stft + spec_fwd + pad_spec (data_module.py:241-254,291-293;
@@ -102,8 +104,8 @@ int snrse_ncsnpp_param_info(void* handle, int i, char* name, int name_cap, int* 
 int snrse_ncsnpp_param_shape(void* handle, int i, int64_t* dims, int* ndim); /* shape of the state-dict tensor */
 int snrse_ncsnpp_set_weights(void* handle, const void* device_blob);
 /* Plan for inputs [B][F][T]: returns the workspace size (or -1).  flags bit0: keep all activations
- * (debug taps); bit1: CUDA-core cross-check convolutions instead of tcgen05; bit2: first-generation tcgen05 kernel only;
- * bit3: single-CTA halo kernel instead of the 2-CTA one; bit4: GroupNorm+SiLU as a separate pass (no in-kernel fusion);
+ * (debug taps); bit1: CUDA-core cross-check convolutions instead of tcgen05; bit2: single-CTA tcgen05 GEMM kernel only;
+ * bit3: unused; bit4: GroupNorm+SiLU as a separate pass (no in-kernel fusion);
  * bit5: GroupNorm+SiLU of the up / down blocks inside the FIR kernels. */
 int64_t snrse_ncsnpp_plan_bytes(void* handle, int B, int F, int T, int flags);
 int snrse_ncsnpp_plan_bind(void* handle, int B, int F, int T, void* workspace, int64_t bytes);
@@ -111,26 +113,16 @@ int snrse_ncsnpp_plan_bind(void* handle, int B, int F, int T, void* workspace, i
  * 1: c_skip*x + c_out*dnn (sebridge / sebridge_v3, model.py:537-541); 2: -dnn (bbed, model.py:488-489). */
 int snrse_ncsnpp_forward(void* handle, int B, int F, int T, const void* x, const void* y, const float* t, void* out,
                          int mode, void* stream);
-int snrse_ncsnpp_num_launch_groups(void* handle, int B, int F, int T);
-/* measurement only: eager forward with CUDA events between launch groups (kind 1 = implicit-GEMM conv) */
-int snrse_ncsnpp_profile_forward(void* handle, int B, int F, int T, const void* x, const void* y, const float* t,
-                                 void* out, int mode, void* stream, int cap, int* kinds, double* flops, double* bytes,
-                                 float* ms, int* n_groups);
-int snrse_ncsnpp_read_tap(void* handle, int B, int F, int T, int module_idx, float* out, int64_t cap_elems,
-                          int64_t* dims, void* stream);
 
 /* ---------------------------------------------------------------- single operators (NHWC bf16) --
  * conv: ddpm_conv3x3 / ddpm_conv1x1 / NIN (ncsnpp_utils/layers.py:100-124,537-555) as implicit GEMM:
  *   out[b,h,w,n] = scale*( sum_{tap,c} x0[b,h+dh,w+dw,c]*wt[n][tap*c0+c] + sum_c x1[b,h,w,c]*wt[n][taps0*c0+c]
  *                          + bias[n] + tbias[b*tb_stride+n] + res[b,h,w,n] );
- *   impl 0: tcgen05 (2-CTA halo-reuse persistent kernel when eligible), 1: CUDA cores, 2: first-generation tcgen05
- *   kernel, 3: single-CTA halo kernel. */
+ *   impl 0: tcgen05 (2-CTA halo-reuse persistent kernel when eligible), 1: CUDA cores (cross-check), 2: the
+ *   single-CTA tcgen05 GEMM kernel that also serves 1x1 / NIN / attention. */
 int snrse_conv_nhwc(const void* x0, int c0, int taps0, const void* x1, int c1, const void* wt, int n, const float* bias,
                     const float* tbias, int tb_stride, const void* res, float scale, void* out, int B, int H, int W,
                     int impl, void* stream);
-/* measurement hook for the halo kernel: [grid][8] int64 cycle counters (a/b/acc waits of the MMA warp, total,
- * epilogue wait/body, producer waits); NULL switches it off */
-void snrse_conv_halo_set_debug(long long* dev_counters);
 /* GroupNorm(32, eps) (+SiLU) (ncsnpp_utils/layerspp.py:221,233,245,266) */
 /* GroupNorm(32 groups, eps) + SiLU + conv3x3 (+ optional 1x1 shortcut on x1, bias, per-sample tbias, residual,
  * scale) as ONE pass: statistics kernel + convolution that normalises its operand in shared memory.  Replaces the

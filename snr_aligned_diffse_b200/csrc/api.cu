@@ -120,12 +120,6 @@ int snrse_conv_nhwc(const void* x0, int c0, int taps0, const void* x1, int c1, c
         return conv_simt_launch(&a0, taps0, x1 ? &a1 : nullptr, static_cast<const bf16*>(wt), n, bias, tbias, tb_stride,
                                 res ? &r : nullptr, scale, static_cast<bf16*>(out), n, S(stream));
     }
-    if (impl == 3 && conv_halo_eligible(&a0, taps0, n)) {
-        ConvHaloPlan hp;
-        SNRSE_TRY(conv_halo_make_plan(&hp, &a0, x1 ? &a1 : nullptr, static_cast<const bf16*>(wt), n, bias, tbias,
-                                      tb_stride, res ? &r : nullptr, scale, static_cast<bf16*>(out), n));
-        return conv_halo_launch(&hp, S(stream));
-    }
     if (impl == 0 && conv_halo2_eligible(&a0, taps0, n)) {
         ConvHaloPlan hp;
         SNRSE_TRY(conv_halo2_make_plan(&hp, &a0, x1 ? &a1 : nullptr, static_cast<const bf16*>(wt), n, bias, tbias, tb_stride,
@@ -242,3 +236,9 @@ int snrse_attention_nhwc(const void* q, const void* k, const void* v, void* scor
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// measurement hooks (include/snrse_b200_debug.h): not part of the product ABI
+long long* g_halo_dbg_shared = nullptr;
+// device buffer of [grid][8] cycle counters filled by subsequent conv_halo2 / conv_gemm launches (null: off)
+extern "C" void snrse_conv_halo_set_debug(long long* dev_counters) { g_halo_dbg_shared = dev_counters; }

@@ -377,14 +377,7 @@ int rec_gemm(Plan& P, int a0, int taps0, int a1, int64_t w_off, int n_rows, int6
         const double kt = (double)taps0 * c0 + (a1 >= 0 ? va1.C : 0);
         // algorithmic bytes: each operand / result once (bf16), weights once
         const double by = 2.0 * (px * (c0 + (a1 >= 0 ? va1.C : 0) + n_rows + (res >= 0 ? n_rows : 0)) + kt * n_rows);
-        if ((p.flags & 8) && conv_halo_eligible(&va0, taps0, n_rows)) {   // single-CTA halo kernel (cross-check)
-            ConvHaloPlan hp;
-            SNRSE_TRY(conv_halo_make_plan(&hp, &va0, a1 >= 0 ? &va1 : nullptr, e.wb(w_off), n_rows, bias, tb, tb_stride,
-                                          res >= 0 ? &vres : nullptr, scale, vout.ptr, vout.ld));
-            p.add(LK_GEMM, 2.0 * px * n_rows * kt, by, [hp](cudaStream_t s) { return conv_halo_launch(&hp, s); });
-            return SNRSE_OK;
-        }
-        if (!(p.flags & 12) && conv_halo2_eligible(&va0, taps0, n_rows)) {   // 2-CTA (cta_group::2) halo kernel
+        if (!(p.flags & 4) && conv_halo2_eligible(&va0, taps0, n_rows)) {   // 2-CTA (cta_group::2) halo kernel
             ConvHaloPlan hp;
             SNRSE_TRY(conv_halo2_make_plan(&hp, &va0, a1 >= 0 ? &va1 : nullptr, e.wb(w_off), n_rows, bias, tb, tb_stride,
                                            res >= 0 ? &vres : nullptr, scale, vout.ptr, vout.ld,

@@ -69,11 +69,6 @@ struct ConvHaloPlan {
     float* out4;                  // 2-CTA kernel, thin C -> 4 output convolution only
     const float* addend4;
 };
-bool conv_halo_eligible(const ActView* a0, int taps0, int n_rows);
-int conv_halo_make_plan(ConvHaloPlan* p, const ActView* a0, const ActView* a1, const bf16* wt, int n_rows,
-                        const float* bias, const float* tbias, int tb_stride, const ActView* res, float scale, bf16* out,
-                        int out_ld);
-int conv_halo_launch(const ConvHaloPlan* p, cudaStream_t s);
 // 2-CTA (cta_group::2) single-halo-tile version, same plan structure (conv_halo2.cu): W >= 8, H >= 8
 bool conv_halo2_eligible(const ActView* a0, int taps0, int n_rows);
 // scsh (nullable): GroupNorm scale/shift [B][2][C0] (gn_finalize_launch); when given, operand 0 is replaced by
