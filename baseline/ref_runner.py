@@ -19,7 +19,7 @@ model gets the seeded "de-degenerated" weights of snr_aligned_diffse_b200.synth.
   eager_gpu   : the same reference functions composed for a batch on the GPU (model.to('cuda')): stft ->
                 _forward_transform -> pad_spec -> snr_model -> t snap / normfac -> X_T -> model(X_T, t, Y) -> to_audio.
                 `fp32` = torch defaults (cuDNN convolutions may use TF32, matmul fp32); `tf32` additionally allows TF32
-                matmuls; `bf16` runs the network under torch.autocast(bfloat16).  This is the cuDNN / cuBLAS / cuFFT
+                matmuls; `fp16` / `bf16` run the network under torch.autocast (bf16 needs two upcast wrappers, see code).  This is the cuDNN / cuBLAS / cuFFT
                 kernel set the B200-native path has to beat on the same box.
   parity      : strict fp32 (TF32 off) composed pass with explicit noise Z; writes x_hat / sample / t / norm_factor.
 """
@@ -192,11 +192,12 @@ def task_eager_gpu(a):
         torch.backends.cudnn.allow_tf32 = True            # torch default
         torch.backends.cuda.matmul.allow_tf32 = prec == "tf32"
         torch.backends.cudnn.benchmark = True             # let cuDNN pick its best algorithm per shape
-        ac = torch.bfloat16 if prec == "bf16" else None
-        if ac is not None:
-            # the reference's upfirdn2d CUDA op dispatches float / double / half only (upfirdn2d_kernel.cu:311): under
-            # bf16 autocast it raises.  Wrap the call site's symbol so FIR inputs are upcast to fp32 and the result is
-            # cast back -- a monkeypatch in this process, the reference files stay byte-identical.
+        ac = {"bf16": torch.bfloat16, "fp16": torch.float16}.get(prec)
+        if prec == "bf16":
+            # The unmodified reference cannot run under bf16 autocast: its upfirdn2d CUDA op dispatches float / double /
+            # half only (upfirdn2d_kernel.cu:311) and NCSNpp.forward ends in torch.view_as_complex, which rejects bf16
+            # (ncsnpp.py:401).  Two wrappers in THIS process upcast at those two call sites (the reference files stay
+            # byte-identical); fp16 autocast needs neither and is the reference's own reduced-precision mode.
             import sgmse.backbones.ncsnpp_utils.up_or_down_sampling as uds
             if not hasattr(uds, "_orig_upfirdn2d"):
                 uds._orig_upfirdn2d = uds.upfirdn2d
@@ -204,6 +205,8 @@ def task_eager_gpu(a):
                 def _fir_fp32(x, *a_, **k_):
                     return uds._orig_upfirdn2d(x.float(), *a_, **k_).to(x.dtype)
                 uds.upfirdn2d = _fir_fp32
+                _vac = torch.view_as_complex
+                torch.view_as_complex = lambda t_: _vac(t_.float() if t_.dtype == torch.bfloat16 else t_)
         try:
             with torch.no_grad():
                 for _ in range(2):
@@ -274,7 +277,7 @@ def main():
     ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--seconds", type=float, default=4.0)
     ap.add_argument("--seed", type=int, default=1000)
-    ap.add_argument("--precision", default="fp32,bf16")
+    ap.add_argument("--precision", default="fp32,fp16,bf16")
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--device", default="cuda")
     ap.add_argument("--out", default="ref_parity.npz")

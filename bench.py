@@ -472,7 +472,7 @@ def run_b200(args):
             sweeps = {}
             for fs in (0.17783, 0.31623, 0.56234):
                 model.fixed_snr = fs
-                r = wl.run_sweep824(model, dev, rank, world)
+                r = wl.run_sweep824(model, dev, rank, world, repeat=3)
                 sweeps[str(fs)] = dict(value=round(r["value"], 1), job_seconds=round(r["job_seconds"], 4), finite=r["finite"],
                                        batches_rank0=r["batches_rank0"])
             model.fixed_snr = FIXED_SNR
@@ -502,7 +502,7 @@ def run_b200(args):
         if world == 1 and not args.no_eager_baseline:
             torch.cuda.empty_cache()
             r = _run_ref_runner(["--task", "eager_gpu", "--batch", str(BATCH), "--seconds", str(SECONDS), "--seed", "1000",
-                                 "--precision", "fp32,tf32,bf16", "--reps", "5"], 900)
+                                 "--precision", "fp32,tf32,fp16,bf16", "--reps", "5"], 900)
             if "unavailable" in r:
                 eager = r
             else:
@@ -511,9 +511,10 @@ def run_b200(args):
                              torch=r["torch"], cudnn=r["cudnn"], unit=UNIT, modes=r["results"],
                              mode_notes=dict(fp32="torch defaults: cuDNN convolutions may use TF32, matmuls fp32",
                                              tf32="additionally torch.backends.cuda.matmul.allow_tf32",
-                                             bf16="torch.autocast(bfloat16) around ScoreModel.forward; the reference's upfirdn2d "
-                                                  "CUDA op has no bf16 kernel, so its inputs are upcast by a wrapper in "
-                                                  "baseline/ref_runner.py (reference files untouched)"))
+                                             fp16="torch.autocast(float16) around ScoreModel.forward",
+                                             bf16="torch.autocast(bfloat16) around ScoreModel.forward; the unmodified reference "
+                                                  "cannot run it (upfirdn2d CUDA op and view_as_complex reject bf16), so two "
+                                                  "upcast wrappers in baseline/ref_runner.py are active (reference files untouched)"))
                 best = max((m.get("audio_s_per_s", 0.0) for m in r["results"].values()), default=0.0)
                 eager["best_value"] = best
                 eager["speedup_e2e_over_best_eager"] = round(e2e_value / best, 2) if best else None

@@ -156,8 +156,30 @@ attn_transpose_kernel(const bf16* __restrict__ v, int v_ld, int n, int C, bf16* 
 
 }  // namespace
 
+// The reference materialises the full [B, n, n] score matrix (layerspp.py:84-88).  Here at most ATTN_SCORE_BUDGET bytes
+// of scores (fp32) + probabilities (bf16) are live: when B*n*n*6 exceeds it, the queries are walked in blocks of `qc`
+// rows per utterance (every block is a complete softmax over all n keys, so the result is unchanged); a 60 s utterance
+// (n = 7552) then needs 190 MB instead of 342 MB per attention block, a 64 x 60 s batch 190 MB instead of 22 GB.
+constexpr int64_t ATTN_SCORE_BUDGET = 192ll << 20;
+
+static void attn_blocking(int B, int n, int* pass_b, int* qc) {
+    if ((int64_t)B * n * n * 6 <= ATTN_SCORE_BUDGET || n % 64 != 0) {
+        *pass_b = B;
+        *qc = n;
+        return;
+    }
+    int64_t rows = ATTN_SCORE_BUDGET / (6ll * n);
+    rows = rows / 64 * 64;
+    if (rows < 64) rows = 64;
+    if (rows > n) rows = n;
+    *pass_b = 1;
+    *qc = (int)rows;
+}
+
 int64_t attention_workspace_bytes(int B, int n, int C) {
-    const int64_t nn = (int64_t)B * n * n;
+    int pb, qc;
+    attn_blocking(B, n, &pb, &qc);
+    const int64_t nn = (int64_t)pb * qc * n;
     return nn * 4 + ((nn * 2 + 255) / 256) * 256 + (int64_t)B * C * n * 2 + 512;
 }
 
@@ -167,29 +189,38 @@ int attention_launch(const ActView* q, const ActView* k, const ActView* v, void*
     SNRSE_CHECK_ARG(C % TK == 0, "attention: C must be a multiple of %d", TK);
     float* scores = static_cast<float*>(workspace);
     if (allow_tensor_cores && n % 64 == 0 && C % 64 == 0 && q->ld % 8 == 0 && k->ld % 8 == 0) {
-        const int64_t nn = (int64_t)B * n * n;
+        int pb, qc;
+        attn_blocking(B, n, &pb, &qc);
+        const int64_t nn = (int64_t)pb * qc * n;
         bf16* probs = reinterpret_cast<bf16*>(static_cast<uint8_t*>(workspace) + nn * 4);
         bf16* vt = reinterpret_cast<bf16*>(reinterpret_cast<uint8_t*>(probs) + ((nn * 2 + 255) / 256) * 256);
-        // S[b] = scale * Q[b] K[b]^T : A = Q (tokens x C), B = K (keys x C, row pitch k->ld)
-        ActView qa = *q;
-        qa.H = 1; qa.W = n;
-        ConvGemmPlan g1;
-        SNRSE_TRY(conv_gemm_make_plan_ex(&g1, &qa, 1, nullptr, k->ptr, n, (int64_t)n * k->ld, 1, nullptr, nullptr, 0, nullptr,
-                                         rsqrtf((float)C), scores, n, 1, k->ld));
-        SNRSE_TRY(conv_gemm_launch(&g1, s));
-        const int64_t rows = (int64_t)B * n;
-        attn_softmax_bf16_kernel<<<(unsigned)cdiv64(rows, 8), 256, 0, s>>>(scores, probs, n, rows);
-        SNRSE_LAUNCH_CHECK();
         dim3 gt(cdiv(C, 32), cdiv(n, 32), B);
         attn_transpose_kernel<<<gt, 256, 0, s>>>(v->ptr, v->ld, n, C, vt);
         SNRSE_LAUNCH_CHECK();
-        // O[b] = P[b] V[b] : A = P (tokens x keys), B = V^T (C x keys)
-        ActView pa;
-        pa.ptr = probs; pa.B = B; pa.H = 1; pa.W = n; pa.C = n; pa.ld = n;
-        ConvGemmPlan g2;
-        SNRSE_TRY(conv_gemm_make_plan_ex(&g2, &pa, 1, nullptr, vt, C, (int64_t)C * n, 1, nullptr, nullptr, 0, nullptr, 1.0f,
-                                         o->ptr, o->ld, 0, n));
-        return conv_gemm_launch(&g2, s);
+        for (int b0 = 0; b0 < B; b0 += pb) {
+            for (int q0 = 0; q0 < n; q0 += qc) {
+                const int rows_q = (n - q0 < qc) ? n - q0 : qc;
+                // S = scale * Q K^T : A = Q block (tokens x C), B = K (keys x C, row pitch k->ld)
+                ActView qa = *q;
+                qa.ptr = q->ptr + ((int64_t)b0 * n + q0) * q->ld;
+                qa.B = pb; qa.H = 1; qa.W = rows_q;
+                ConvGemmPlan g1;
+                SNRSE_TRY(conv_gemm_make_plan_ex(&g1, &qa, 1, nullptr, k->ptr + (int64_t)b0 * n * k->ld, n, (int64_t)n * k->ld, 1,
+                                                 nullptr, nullptr, 0, nullptr, rsqrtf((float)C), scores, n, 1, k->ld));
+                SNRSE_TRY(conv_gemm_launch(&g1, s));
+                const int64_t rows = (int64_t)pb * rows_q;
+                attn_softmax_bf16_kernel<<<(unsigned)cdiv64(rows, 8), 256, 0, s>>>(scores, probs, n, rows);
+                SNRSE_LAUNCH_CHECK();
+                // O = P V : A = P (tokens x keys), B = V^T (C x keys)
+                ActView pa;
+                pa.ptr = probs; pa.B = pb; pa.H = 1; pa.W = rows_q; pa.C = n; pa.ld = n;
+                ConvGemmPlan g2;
+                SNRSE_TRY(conv_gemm_make_plan_ex(&g2, &pa, 1, nullptr, vt + (int64_t)b0 * C * n, C, (int64_t)C * n, 1, nullptr,
+                                                 nullptr, 0, nullptr, 1.0f, o->ptr + ((int64_t)b0 * n + q0) * o->ld, o->ld, 0, n));
+                SNRSE_TRY(conv_gemm_launch(&g2, s));
+            }
+        }
+        return SNRSE_OK;
     }
     dim3 g1(cdiv(n, TS), cdiv(n, TS), B);
     attn_scores_kernel<<<g1, 256, 0, s>>>(q->ptr, q->ld, k->ptr, k->ld, n, C, rsqrtf((float)C), scores);

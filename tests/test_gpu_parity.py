@@ -400,6 +400,24 @@ def test_attention(ops, n):
     assert ((got - ref).abs() <= 2 ** -7 * ref.abs() + atol).all()
 
 
+def test_attention_query_blocks_bound_the_score_memory(ops):
+    """n = 6016 tokens (between the 10 s and 60 s shapes): B*n*n*6 bytes exceeds the score budget, so the queries are
+    walked in blocks (5568 + 448 rows) per utterance; every block is a full softmax over all keys -> same result as the
+    single-pass formula, and the workspace stays below the budget + V^T instead of growing with n^2."""
+    from snr_aligned_diffse_b200 import _lib
+    n, C, B = 6016, 256, 2
+    g = torch.Generator().manual_seed(n)
+    q, k, v = (torch.randn(B, n, C, generator=g).to(torch.bfloat16) for _ in range(3))
+    ws = int(_lib.load().snrse_attention_workspace_bytes(B, n, C))
+    assert ws < (192 << 20) + B * C * n * 2 + 4096 < B * n * n * 6
+    got = ops.attention_nhwc(q.to(DEV), k.to(DEV), v.to(DEV)).float().cpu()
+    qd, kd, vd = q.to(DEV).float(), k.to(DEV).float(), v.to(DEV).float()      # fp32 torch reference, on the GPU for speed
+    w = torch.softmax(torch.einsum("bic,bjc->bij", qd, kd) * C ** -0.5, dim=-1)
+    ref = torch.einsum("bij,bjc->bic", w, vd).cpu()
+    atol = 2 ** -9 * float(v.float().abs().max())
+    assert ((got - ref).abs() <= 2 ** -7 * ref.abs() + atol).all()
+
+
 # ----------------------------------------------------------------------------------------------- network
 def _network_report(engine, sd, x, t, flags):
     """Run oracle + engine with activation taps; return (out_ref, out_gpu, per-module rel-L2 list)."""
