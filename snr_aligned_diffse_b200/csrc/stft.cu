@@ -158,7 +158,11 @@ stft_kernel(const float* __restrict__ wave, const int* __restrict__ len, const f
     // split indices + e^{-i pi k/255} = (ec, -es) (thread = output bin k)
     const int m2 = 2 * pfa_input_pos(tid < M255 ? tid : 0);
     const float w0 = hann(m2), w1 = hann(m2 + 1);
-    const int k = tid;
+    // thread <-> output bin: thread t < 255 takes the bin stored at position t after the transform (k = CRT of
+    // (t/85, (t%85)/17, t%17)), so the split reads X[.. + t] without bank conflicts and the partner bin 255-k at a
+    // descending stride of 1 (53 -> 17 and 53 -> 35 wavefronts per 256 threads); every thread writes its own row of
+    // the output, so the permutation costs nothing on the global side.  Thread 255 takes the Nyquist bin.
+    const int k = tid < M255 ? (85 * (tid / 85) + 51 * ((tid % 85) / 17) + 120 * (tid % 17)) % M255 : M255;
     const int ia = pfa_output_index(k == M255 ? 0 : k), ib = pfa_output_index((M255 - k) % M255);
     float es, ec;
     sincospif((float)k / (float)M255, &es, &ec);
@@ -251,15 +255,16 @@ stft_kernel(const float* __restrict__ wave, const int* __restrict__ len, const f
 // them in shared memory in ascending frame order, divides by the window envelope and writes wave[p - 255].
 constexpr int PASSES = 4, HALO = 4, NEWF = PASSES * FT - HALO;      // 28 new frames per block
 constexpr int OLA_SPAN = (PASSES * FT - 1) * HOP + NFFT;             // 4478 samples
-constexpr int ISTFT_SMEM = 2 * FT * FS * 8 + OLA_SPAN * 4 + NFFT * 4 + 64;
+constexpr int TS = 258;                                              // float2 stride between frames of the spectrogram tile
+constexpr int ISTFT_SMEM = (FT * FS + FT * TS) * 8 + OLA_SPAN * 4 + NFFT * 4 + 64;
 
 __global__ void __launch_bounds__(256)
 istft_kernel(const float2* __restrict__ spec, const int* __restrict__ len, const float* __restrict__ scale,
              float* __restrict__ wave, int lstride, int tpad, int transform, float alpha, float beta) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* X = reinterpret_cast<float2*>(smem_raw);                 // transform buffer [FT][FS]
-    float2* T = X + FT * FS;                                          // spectrogram tile [256][FT], later frames [FT][512 floats]
-    float* ola = reinterpret_cast<float*>(T + FT * FS);
+    float2* T = X + FT * FS;                                          // spectrogram tile [FT][TS], later frames [FT][512 floats]
+    float* ola = reinterpret_cast<float*>(T + FT * TS);
     float* hw = ola + OLA_SPAN;                                       // Hann window
     const int b = blockIdx.y, F0 = blockIdx.x * NEWF, tid = threadIdx.x;
     const int L = len ? len[b] : lstride;
@@ -268,14 +273,18 @@ istft_kernel(const float2* __restrict__ spec, const int* __restrict__ len, const
     const float2* sb = spec + (int64_t)b * NBINS * tpad;
     const float inv_beta = 1.0f / beta;
     const bool vec_ok = (tpad & 1) == 0;
-    // merge factors of this thread's bin pair (k, 255-k), k = tid < 128:  e^{+i pi k/255} = (ec, es)
+    // merge: thread t < 255 produces transform input element t, i.e. Z'[k] for k = pfa_input_pos(t), from the bins
+    // k and 255-k (k = 0 pairs with the Nyquist row 255):  e^{+i pi k/255} = (ec, es)
+    const int mk = pfa_input_pos(tid < M255 ? tid : 0), mk2 = M255 - mk;
     float es, ec;
-    sincospif((float)(tid & 127) / (float)M255, &es, &ec);
+    sincospif((float)mk / (float)M255, &es, &ec);
     for (int pass = 0; pass < PASSES; ++pass) {
         const int fb = F0 - HALO + pass * FT;                        // first frame of this pass (even)
         if (fb + FT <= 0 || fb >= tpad) continue;                     // block-uniform: nothing to add
         __syncthreads();                                              // previous pass done with X / T
-        // spectrogram tile -> T as float2 [k][FT], spec_back applied (data_module.py:256-262)
+        // spectrogram tile -> T as float2 [frame][TS] (bin-contiguous: the merge below reads bins at a stride of 15,
+        // conflict-free; the former [bin][FT] layout made it an 8-way bank conflict), spec_back applied
+        // (data_module.py:256-262)
         for (int e = tid; e < NBINS * (FT / 2); e += 256) {
             const int k = e >> 2, c = e & 3, t = fb + 2 * c;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -295,27 +304,19 @@ istft_kernel(const float2* __restrict__ spec, const int* __restrict__ len, const
                 v.x *= g0; v.y *= g0; v.z *= g1; v.w *= g1;
             }
             if (k == 0 || k == NBINS - 1) { v.y = 0.f; v.w = 0.f; }  // one-sided inverse ignores Im of DC / Nyquist
-            reinterpret_cast<float4*>(T)[e] = v;
+            T[(2 * c) * TS + k] = make_float2(v.x, v.y);
+            T[(2 * c + 1) * TS + k] = make_float2(v.z, v.w);
         }
         __syncthreads();
-        // merge: Z'[k] = (S[k] + conj S[255-k]) + i e^{+2 pi i k/510} (S[k] - conj S[255-k]),  k = 0..254, written
-        // straight to the transform's input order.  One thread per pair (k, 255-k): Z'[255-k] uses -conj(E).
-        if (tid < 128) {
-            const int k = tid, k2 = M255 - k;                         // k2 = 255 (Nyquist row) for k = 0
-            const int ja = pfa_input_index(k), jb = pfa_input_index(k2 % M255);
+        // merge: Z'[k] = (S[k] + conj S[255-k]) + i e^{+2 pi i k/510} (S[k] - conj S[255-k]),  k = 0..254, one thread per
+        // element, written in the transform's input order (X[.. + tid]: conflict-free)
+        if (tid < M255) {
 #pragma unroll
             for (int f = 0; f < FT; ++f) {
-                const float2 xa = T[k * FT + f], xb = T[k2 * FT + f];
-                {
-                    const float sr = xa.x + xb.x, si = xa.y - xb.y, dr = xa.x - xb.x, di = xa.y + xb.y;
-                    const float pr = fmaf(ec, dr, -es * di), pi = fmaf(ec, di, es * dr);   // E * d
-                    X[f * FS + ja] = make_float2(sr - pi, si + pr);
-                }
-                if (k != 0) {   // partner bin: roles swapped, E' = -conj(E) = (-ec, es)
-                    const float sr = xb.x + xa.x, si = xb.y - xa.y, dr = xb.x - xa.x, di = xb.y + xa.y;
-                    const float pr = fmaf(-ec, dr, -es * di), pi = fmaf(-ec, di, es * dr);
-                    X[f * FS + jb] = make_float2(sr - pi, si + pr);
-                }
+                const float2 xa = T[f * TS + mk], xb = T[f * TS + mk2];
+                const float sr = xa.x + xb.x, si = xa.y - xb.y, dr = xa.x - xb.x, di = xa.y + xb.y;
+                const float pr = fmaf(ec, dr, -es * di), pi = fmaf(ec, di, es * dr);   // E * d
+                X[f * FS + tid] = make_float2(sr - pi, si + pr);
             }
         }
         __syncthreads();
