@@ -64,6 +64,7 @@ def test_euler_maruyama_step_matches_reference_fixture(sd, golden_dir, monkeypat
     assert rel_l2(x_new.cpu(), _c(z["x_new"])) <= 2e-2 and rel_l2(x_mean.cpu(), _c(z["x_mean"])) <= 2e-2
     # through pc_sampler the reference raises TypeError (the predictor receives a 4th positional argument)
     assert str(z["in_loop"]) == "TypeError"
+    monkeypatch.undo()                                        # the loop draws its own prior noise
     with pytest.raises(TypeError):
         bb.get_pc_sampler("euler_maruyama", "none", _c(z["Y"]).cuda(), N=2)()
 
