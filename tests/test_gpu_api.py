@@ -1,8 +1,9 @@
 """GPU tests of the reference-facing API (`sgmse` mirror) against the golden fixtures / the CPU oracle.
 
 Tolerances: scalars (t, index) exact, norm factor 1e-6 relative; enhanced waveform in bf16 vs the fp32
-reference: SI-SDR >= 28 dB and max-abs error <= 8 % of the waveform peak (SURVEY 7 measured 30.7 dB /
-2-4 % for a bf16 run of the reference itself on such random weights); 4-NFE PC sampler: rel-L2 <= 6e-2.
+reference: rel-L2 <= 2e-2 on the spectrogram, SI-SDR >= 30 dB and max-abs error <= 4 % of the waveform peak (measured
+1.6e-2 / 33.7 dB / 2.6 %, profiles/r01_parity.md; SURVEY 7 measured 30.7 dB / 2-4 % for a bf16 run of the reference
+itself on such random weights); 4-NFE PC sampler: rel-L2 <= 6e-2.
 """
 import os
 
@@ -62,12 +63,12 @@ def test_enhance_v3_matches_reference_fixture(v3, golden_dir):
     x_hat = v3.enhance(y, y, oracle=True, clean_rms=1.0, noise_rms=float(z["ratio"]), noise=Z)
     ref = z["x_hat"]
     assert isinstance(x_hat, np.ndarray) and x_hat.dtype == np.float32 and x_hat.shape == ref.shape   # eval.py:140
-    assert o_sampler.si_sdr(ref.astype(np.float64), x_hat.astype(np.float64)) >= 28.0
-    assert np.abs(x_hat - ref).max() <= 0.08 * np.abs(ref).max()
+    assert o_sampler.si_sdr(ref.astype(np.float64), x_hat.astype(np.float64)) >= 30.0
+    assert np.abs(x_hat - ref).max() <= 0.04 * np.abs(ref).max()
     out, aux = v3.enhance_batch(y, oracle=True, noise_over_clean=[float(z["ratio"])], noise=Z, return_aux=True)
     assert float(aux["t"][0]) == np.float32(z["t"])                                   # snapped timestep: exact
     assert abs(float(aux["norm_factor"][0]) / float(z["norm_factor"]) - 1) <= 1e-6
-    assert rel_l2(aux["sample"].cpu(), _c(z["sample"])[:, 0]) <= 3e-2
+    assert rel_l2(aux["sample"].cpu(), _c(z["sample"])[:, 0]) <= 2e-2
     xh, nfe, rtf = v3.enhance(y, y, oracle=True, clean_rms=1.0, noise_rms=float(z["ratio"]), noise=Z, timeit=True)
     assert nfe == 1 and rtf > 0 and np.array_equal(xh, x_hat)
 
@@ -83,7 +84,7 @@ def test_enhance_batch_ragged_lengths(v3, sd):
     out = v3.enhance_batch(y, lengths=torch.tensor(lens), oracle=True, noise_over_clean=ratios, noise=Z).cpu()
     for b, L in enumerate(lens):
         ref = o_sampler.enhance_v3(sd, y[b:b + 1, :L], Z[b:b + 1], ratios[b], 0.17783, sigma_max=1.0)["x_hat"]
-        assert o_sampler.si_sdr(ref.double().numpy(), out[b, :L].double().numpy()) >= 28.0
+        assert o_sampler.si_sdr(ref.double().numpy(), out[b, :L].double().numpy()) >= 30.0
         assert torch.count_nonzero(out[b, L:]) == 0
 
 

@@ -6,8 +6,9 @@ Tolerances (stated per test):
   * fp32 kernels (STFT, iSTFT, SNRNet, FIR fp32, scalars): 1e-5-level relative to the signal peak
   * bf16-storage kernels: the bf16 rounding of the stored result (2^-8 relative) on top of an fp32 reference
     evaluated on the same bf16-rounded operands
-  * whole network in bf16 vs the fp32 oracle: relative L2 <= 3e-2 on the spectrogram, SI-SDR of the
-    enhanced waveform against the oracle waveform >= 28 dB (bf16 autocast of the reference
+  * whole network in bf16 vs the fp32 oracle: relative L2 <= 2e-2 on the network output (<= 2.5e-2 on every
+    module's activation at the 256 x 64 fixture shape), SI-SDR of the enhanced waveform against the oracle waveform
+    >= 30 dB in tests/test_gpu_api.py / test_gpu_configs.py (bf16 autocast of the reference
     itself sits at 1.5e-2 / 30.7 dB on these random weights)
 """
 import math
@@ -444,8 +445,8 @@ def test_ncsnpp_forward_vs_golden(engine, sd, golden_dir, flags):
     assert (ref - gold).abs().max() <= 1e-4 * gold.abs().max()       # oracle == reference fixture
     worst = max(r for _, r in rep)
     msg = " ".join(f"{i}:{r:.1e}" for i, r in rep)
-    assert worst <= 3e-2, msg                                        # every module output, bf16 vs fp32 oracle
-    assert rel_l2(torch.view_as_real(out), torch.view_as_real(gold)) <= 3e-2, msg
+    assert worst <= 2.5e-2, msg                                      # every module output, bf16 vs fp32 oracle
+    assert rel_l2(torch.view_as_real(out), torch.view_as_real(gold)) <= 2e-2, msg
 
 
 def test_ncsnpp_batch_and_length_independence_tcgen05(engine, sd):
@@ -458,4 +459,4 @@ def test_ncsnpp_batch_and_length_independence_tcgen05(engine, sd):
     assert torch.equal(both[1:], one)                                 # deterministic kernels: bit-exact
     with torch.no_grad():
         ref = o_sampler.score_forward(sd, x[:, :1], t[:, None, None, None], x[:, 1:], "sebridge_v3")
-    assert rel_l2(torch.view_as_real(both.cpu()), torch.view_as_real(ref[:, 0])) <= 3e-2
+    assert rel_l2(torch.view_as_real(both.cpu()), torch.view_as_real(ref[:, 0])) <= 2e-2
