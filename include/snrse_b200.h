@@ -106,7 +106,9 @@ int snrse_ncsnpp_set_weights(void* handle, const void* device_blob);
 /* Plan for inputs [B][F][T]: returns the workspace size (or -1).  flags bit0: keep all activations
  * (debug taps); bit1: CUDA-core cross-check convolutions instead of tcgen05; bit2: single-CTA tcgen05 GEMM kernel only;
  * bit3: unused; bit4: GroupNorm+SiLU as a separate pass (no in-kernel fusion);
- * bit5: GroupNorm+SiLU of the up / down blocks inside the FIR kernels. */
+ * bit5: GroupNorm+SiLU of the up / down blocks inside single-output FIR kernels (two FIR launches per block);
+ * bit6: up / down blocks as GroupNorm pass + two FIR passes (the default is ONE dual-output FIR pass over x that
+ * writes FIR(silu(GroupNorm(x))) and FIR(x)). */
 int64_t snrse_ncsnpp_plan_bytes(void* handle, int B, int F, int T, int flags);
 int snrse_ncsnpp_plan_bind(void* handle, int B, int F, int T, void* workspace, int64_t bytes);
 /* x (state), y (noisy), out: complex64 [B][F][T]; t [B] f32.  mode 0: dnn(cat[x,y], t);

@@ -242,3 +242,6 @@ int snrse_attention_nhwc(const void* q, const void* k, const void* v, void* scor
 long long* g_halo_dbg_shared = nullptr;
 // device buffer of [grid][8] cycle counters filled by subsequent conv_halo2 / conv_gemm launches (null: off)
 extern "C" void snrse_conv_halo_set_debug(long long* dev_counters) { g_halo_dbg_shared = dev_counters; }
+// L2 prefetch of the next tile's boxes in the 2-CTA convolution kernel: 1 (default) on, 0 off (A/B measurements)
+extern int g_halo2_prefetch;
+extern "C" void snrse_conv_halo_set_prefetch(int on) { g_halo2_prefetch = on; }

@@ -56,6 +56,7 @@ struct Halo2Args {
     int acc_bufs;                  // 1 or 2 TMEM accumulator sets
     int stg_bufs;                  // 1 or 2 staging tiles per epilogue warp
     int has_res;
+    int prefetch;                  // L2 prefetch of the next tile's operand / residual boxes (0: off, for A/B measurements)
     float4* out4;                  // N == 16 only: fp32 4-channel output [B,H,W,4] = acc[:, 0:4] + bias (+ addend4)
     const float4* addend4;
     unsigned long long* ustats;    // null, or GroupNorm sums of the result, accumulated: [B][N/4][2] fixed point (gn_fixed.cuh)
@@ -202,13 +203,26 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
             const int tile = 2 * ct + (int)rank;
             const int b = tile / tiles_per_img, rem = tile % tiles_per_img;   // tile == n_tiles -> b == B: zero fill
             const int h0 = (rem / g.tiles_w) * SUB_ROWS * g.sub, w0 = (rem % g.tiles_w) * TW;
+            // the tile this CTA walks next: its boxes are prefetched into L2 one whole tile ahead (one prefetch per stage),
+            // so that the ring's loads -- only two or three stages deep, and the 1x1 shortcut stages are consumed in 512
+            // clk each -- find their data in L2 instead of paying the DRAM latency (measured before: the MMA warp of
+            // the fused-shortcut layers waited on A 41 % of its time, profiles/r02_conv_ncu.md)
+            const int ctn = ct + n_clusters;
+            const int tile_n = 2 * ctn + (int)rank;
+            const int bn = tile_n / tiles_per_img, remn = tile_n % tiles_per_img;
+            const int h0n = (remn / g.tiles_w) * SUB_ROWS * g.sub, w0n = (remn % g.tiles_w) * TW;
+            const bool pf = g.prefetch && ctn < n_ctiles && bn < g.B;
             for (int j = 0; j < n_astage; ++j) {
+                const bool seg0 = !(g.seq[j] & 0x80);
+                const int chunk = g.seq[j] & 0x7f;
+                if (pf && elected) {
+                    if (seg0) ptx::tma_prefetch_4d(&mapA0, chunk * 64, w0n - 1, h0n - 1, bn);
+                    else ptx::tma_prefetch_4d(&mapA1, chunk * 64, w0n, h0n, bn);
+                }
                 if (g.dbg) t0__ = clock64();
                 ptx::mbar_wait(ptx::smem_u32(&a_empty[s]), ph ^ 1u);
                 DBG_ADD(w_a);
                 const uint32_t dst = a_base + s * a_bytes;
-                const bool seg0 = !(g.seq[j] & 0x80);
-                const int chunk = g.seq[j] & 0x7f;
                 if (elected) {
                     // 3x3 operand: halo origin (w0-1, h0-1), rows / columns outside the image are zero-filled == conv padding;
                     // 1x1 shortcut operand: the bare tile (8 x 16*SUB pixels)
@@ -470,6 +484,17 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
                 }
                 __syncwarp();
             }
+            if (g.has_res && g.prefetch && elected) {   // this warp's residual boxes of the NEXT tile -> L2
+                const int ctn = ct + n_clusters;
+                const int tile_n = 2 * ctn + (int)rank;
+                const int bn = tile_n / tiles_per_img, remn = tile_n % tiles_per_img;
+                if (ctn < n_ctiles && bn < g.B) {
+                    const int h0n = (remn / g.tiles_w) * SUB_ROWS * g.sub, w0n = (remn % g.tiles_w) * TW;
+                    for (int u = 0; u < g.sub; ++u)
+                        for (int p = 0; p < n_pass; ++p)
+                            ptx::tma_prefetch_4d(&mapRes, n_off + half * half_cols + 64 * p, w0n, h0n + SUB_ROWS * u + 4 * quarter, bn);
+                }
+            }
             if (g.dbg) t0__ = clock64();
             ptx::mbar_wait(ptx::smem_u32(&acc_full[buf]), use & 1u);
             DBG_ADD(w_full);
@@ -584,6 +609,7 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
 int g_num_sms2 = 0;
 }  // namespace
 extern long long* g_halo_dbg_shared;
+int g_halo2_prefetch = 1;   // measurement switch (snrse_conv_halo_set_prefetch, include/snrse_b200_debug.h)
 
 bool conv_halo2_eligible(const ActView* a0, int taps0, int n_rows) {
     return taps0 == 9 && a0->W >= TW && a0->H >= 8 && (n_rows == 128 || n_rows == 256);
@@ -721,6 +747,7 @@ int conv_halo2_launch(const ConvHaloPlan* p, cudaStream_t s) {
     g.sub = p->sub; g.tiles_h = p->tiles_h; g.tiles_w = p->tiles_w; g.n_tiles = p->n_tiles;
     g.N = p->N; g.nsplit = p->nsplit; g.n_total = p->n_total; g.na = p->na; g.nb = p->nb; g.acc_bufs = p->acc_bufs; g.stg_bufs = p->stg_bufs;
     g.has_res = p->res != nullptr;
+    g.prefetch = g_halo2_prefetch;
     g.bias = p->bias; g.tbias = p->tbias; g.tb_stride = p->tb_stride;
     g.scale = p->scale;
     g.scsh = p->scsh; g.norm_c = p->c0_chunks * 64;

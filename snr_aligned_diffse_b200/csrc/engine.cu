@@ -492,6 +492,24 @@ int rec_fir(Plan& P, int x, int up, int norm = 0) {
     return out;
 }
 
+// a = FIR(silu(GroupNorm(x))) and xs = FIR(x) from ONE pass over x (scale/shift currently in t_scsh)
+void rec_fir_dual(Plan& P, int x, int up, int* a, int* xs) {
+    const LT tx = P.tens[x];
+    const int on = up ? P.new_t(tx.B, tx.H * 2, tx.W * 2, tx.C, 2) : P.new_t(tx.B, tx.H / 2, tx.W / 2, tx.C, 2);
+    const int orw = up ? P.new_t(tx.B, tx.H * 2, tx.W * 2, tx.C, 2) : P.new_t(tx.B, tx.H / 2, tx.W / 2, tx.C, 2);
+    P.use(x); P.use(on); P.use(orw); P.use(P.t_scsh);
+    P.step++;
+    P.builders.push_back([=](Plan& p) -> int {
+        const ActView vx = p.view(x), vn = p.view(on), vr = p.view(orw);
+        const float* scsh = p.fptr(p.t_scsh);
+        const double el = (double)vx.B * vx.H * vx.W * vx.C + 2.0 * vn.B * vn.H * vn.W * vn.C;
+        p.add(LK_FIR, 0.0, 2.0 * el, [=](cudaStream_t s) { return fir_dual_launch(&vx, &vn, &vr, up, scsh, s); });
+        return SNRSE_OK;
+    });
+    *a = on;
+    *xs = orw;
+}
+
 int rec_resblock(Plan& P, const Mod& m, int x) {
     // GroupNorm_0 + SiLU (+ FIR resampling of both branches) + Conv_0 + Dense_0(temb)
     int a, xs = x, fuse0 = 0;
@@ -507,6 +525,10 @@ int rec_resblock(Plan& P, const Mod& m, int x) {
             rec_gn_finalize(P, x, m.o[0], m.o[1]);
             a = rec_fir(P, x, m.up ? 1 : 0, 1);
             xs = rec_fir(P, x, m.up ? 1 : 0, 0);
+        } else if ((m.up || m.down) && !(P.flags & (16 | 64))) {
+            // default: one dual-output FIR pass over x produces both branches (x is read once instead of four times)
+            rec_gn_finalize(P, x, m.o[0], m.o[1]);
+            rec_fir_dual(P, x, m.up ? 1 : 0, &a, &xs);
         } else {
             a = rec_gn(P, x, m.o[0], m.o[1], 1);
             if (m.up) { a = rec_fir(P, a, 1); xs = rec_fir(P, x, 1); }

@@ -95,9 +95,8 @@ __device__ __forceinline__ void load_row_down_fast(const bf16* __restrict__ p, i
 }
 
 template <bool NORM>
-__global__ void __launch_bounds__(256)
-fir_down2_kernel(const bf16* __restrict__ x, int ld, int C, int H, int W, bf16* __restrict__ out, int out_ld, int band,
-                 const float* __restrict__ scsh) {
+__device__ __forceinline__ void fir_down2_body(const bf16* __restrict__ x, int ld, int C, int H, int W, bf16* __restrict__ out,
+                                               int out_ld, int band, const float* __restrict__ scsh) {
     const int tpp = C >> 3, cols = blockDim.x / tpp;
     const int c0 = (threadIdx.x % tpp) * 8;
     const int Ho = H >> 1, Wo = W >> 1;
@@ -172,9 +171,8 @@ __device__ __forceinline__ void hfilt_up(const bf16* __restrict__ img, int ld, i
 }
 
 template <bool NORM>
-__global__ void __launch_bounds__(256)
-fir_up2_kernel(const bf16* __restrict__ x, int ld, int C, int H, int W, bf16* __restrict__ out, int out_ld, int band,
-               const float* __restrict__ scsh) {
+__device__ __forceinline__ void fir_up2_body(const bf16* __restrict__ x, int ld, int C, int H, int W, bf16* __restrict__ out,
+                                             int out_ld, int band, const float* __restrict__ scsh) {
     const int tpp = C >> 3, cols = blockDim.x / tpp;
     const int c0 = (threadIdx.x % tpp) * 8;
     const int wi = blockIdx.x * cols + threadIdx.x / tpp;
@@ -209,6 +207,39 @@ fir_up2_kernel(const bf16* __restrict__ x, int ld, int C, int H, int W, bf16* __
 #pragma unroll
         for (int j = 0; j < 8; ++j) { pa[j] = ca[j]; pb[j] = cb[j]; ca[j] = na[j]; cb[j] = nb[j]; }
     }
+}
+
+template <bool NORM>
+__global__ void __launch_bounds__(256)
+fir_down2_kernel(const bf16* __restrict__ x, int ld, int C, int H, int W, bf16* __restrict__ out, int out_ld, int band,
+                 const float* __restrict__ scsh) {
+    fir_down2_body<NORM>(x, ld, C, H, W, out, out_ld, band, scsh);
+}
+template <bool NORM>
+__global__ void __launch_bounds__(256)
+fir_up2_kernel(const bf16* __restrict__ x, int ld, int C, int H, int W, bf16* __restrict__ out, int out_ld, int band,
+               const float* __restrict__ scsh) {
+    fir_up2_body<NORM>(x, ld, C, H, W, out, out_ld, band, scsh);
+}
+
+// ---- dual-output variants for the up / down residual blocks (layerspp.py:245-257): the block filters BOTH
+// h = silu(GroupNorm(x)) and the raw x with the same FIR.  One launch produces FIR(h) and FIR(x): every thread runs the
+// normalising filter over its band and then the plain filter over the SAME band, whose rows are then still in L1 / L2,
+// so x comes from DRAM once.  Against the three-pass form (gn_apply: read x, write h; FIR: read h; FIR: read x) the
+// DRAM traffic per element of x drops from 3 reads + 1 write (+ outputs) to 1 read (+ outputs), and the register
+// footprint stays that of the single-output kernels (a one-pass version holding both windows needed 156 / 242).
+// Same arithmetic and rounding points as the separate passes: bit-identical results.
+__global__ void __launch_bounds__(256)
+fir_down2_dual_kernel(const bf16* __restrict__ x, int ld, int C, int H, int W, bf16* __restrict__ out_n, int out_n_ld,
+                      bf16* __restrict__ out_r, int out_r_ld, int band, const float* __restrict__ scsh) {
+    fir_down2_body<true>(x, ld, C, H, W, out_n, out_n_ld, band, scsh);
+    fir_down2_body<false>(x, ld, C, H, W, out_r, out_r_ld, band, nullptr);
+}
+__global__ void __launch_bounds__(256)
+fir_up2_dual_kernel(const bf16* __restrict__ x, int ld, int C, int H, int W, bf16* __restrict__ out_n, int out_n_ld,
+                    bf16* __restrict__ out_r, int out_r_ld, int band, const float* __restrict__ scsh) {
+    fir_up2_body<true>(x, ld, C, H, W, out_n, out_n_ld, band, scsh);
+    fir_up2_body<false>(x, ld, C, H, W, out_r, out_r_ld, band, nullptr);
 }
 
 __global__ void __launch_bounds__(256)
@@ -361,6 +392,21 @@ int fir_up2_launch(const ActView* x, const ActView* out, cudaStream_t s, const f
     dim3 grid((unsigned)cdiv(x->W, cols), (unsigned)cdiv(x->H, band), (unsigned)x->B);
     if (scsh) fir_up2_kernel<true><<<grid, nthr, 0, s>>>(x->ptr, x->ld, x->C, x->H, x->W, out->ptr, out->ld, band, scsh);
     else fir_up2_kernel<false><<<grid, nthr, 0, s>>>(x->ptr, x->ld, x->C, x->H, x->W, out->ptr, out->ld, band, scsh);
+    SNRSE_LAUNCH_CHECK();
+    return SNRSE_OK;
+}
+
+int fir_dual_launch(const ActView* x, const ActView* out_n, const ActView* out_r, int up, const float* scsh, cudaStream_t s) {
+    SNRSE_CHECK_ARG(scsh != nullptr, "fir_dual: GroupNorm scale / shift required");
+    SNRSE_CHECK_ARG(x->C % 8 == 0 && x->C <= 2048 && x->B <= 65535, "fir_dual: C %% 8 == 0, C <= 2048, B <= 65535");
+    SNRSE_CHECK_ARG(up || (x->H % 2 == 0 && x->W % 2 == 0), "fir_dual (down): H, W must be even");
+    const int tpp = x->C / 8, nthr = tpp * (256 / tpp > 0 ? 256 / tpp : 1), cols = nthr / tpp;
+    const int wcols = up ? x->W : x->W / 2, hrows = up ? x->H : x->H / 2;
+    int band = FIR_BAND;
+    while (band > 1 && (int64_t)cdiv(wcols, cols) * cdiv(hrows, band) * x->B < 592) band >>= 1;
+    dim3 grid((unsigned)cdiv(wcols, cols), (unsigned)cdiv(hrows, band), (unsigned)x->B);
+    if (up) fir_up2_dual_kernel<<<grid, nthr, 0, s>>>(x->ptr, x->ld, x->C, x->H, x->W, out_n->ptr, out_n->ld, out_r->ptr, out_r->ld, band, scsh);
+    else fir_down2_dual_kernel<<<grid, nthr, 0, s>>>(x->ptr, x->ld, x->C, x->H, x->W, out_n->ptr, out_n->ld, out_r->ptr, out_r->ld, band, scsh);
     SNRSE_LAUNCH_CHECK();
     return SNRSE_OK;
 }

@@ -29,9 +29,13 @@ class GuardedAllocator:
             size = tuple(size[0])
         dev = torch.device(device) if device is not None else None
         if dev is None or dev.type != "cuda" or kw.get("pin_memory"):
-            return self._empty(*size, dtype=dtype, device=device, **kw)
+            if dtype is not None:
+                kw["dtype"] = dtype
+            if device is not None:
+                kw["device"] = device
+            return self._empty(*size, **kw)
         dtype = dtype or torch.get_default_dtype()
-        item = torch.empty((), dtype=dtype).element_size()
+        item = self._empty((), dtype=dtype).element_size()
         n = int(np.prod(size)) * item if len(size) else item
         raw = self._empty(n + 2 * PAD, dtype=torch.uint8, device=dev)
         raw.fill_(0xA5)

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Per-kind time of one NCSN++ forward for a (B, T) bucket, measured with CUDA events between launch groups
-(snrse_ncsnpp_profile_forward).  Usage: python tools/profile_shape.py B T [flags]"""
+(snrse_ncsnpp_profile_forward).  Usage: python tools/profile_shape.py B T [flags] [prefetch 0|1]"""
 import os
 import sys
 
@@ -13,6 +13,9 @@ from snr_aligned_diffse_b200.synth import synth_state_dict  # noqa: E402
 
 B, T = int(sys.argv[1]), int(sys.argv[2])
 flags = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+prefetch = int(sys.argv[4]) if len(sys.argv) > 4 else 1
+from snr_aligned_diffse_b200 import _lib  # noqa: E402
+_lib.load().snrse_conv_halo_set_prefetch(prefetch)
 eng = NCSNppEngine()
 eng.load_state_dict(synth_state_dict(eng.param_shapes(), seed=0), "cuda")
 g = torch.Generator().manual_seed(0)
@@ -20,8 +23,12 @@ x = torch.view_as_complex(torch.randn(B, 256, T, 2, generator=g)).cuda()
 y = torch.view_as_complex(torch.randn(B, 256, T, 2, generator=g)).cuda()
 t = torch.full((B,), 0.5, device="cuda")
 names = {0: "other", 1: "conv_tcgen05", 2: "groupnorm", 3: "fir", 4: "attention", 5: "thin_conv", 6: "pack_temb_head"}
-for _ in range(2):
+for _ in range(3):
     prof = eng.profile_forward(x, y, t, mode=1, flags=flags)
+runs = [eng.profile_forward(x, y, t, mode=1, flags=flags) for _ in range(5)]
+runs.sort(key=lambda pr: sum(q["ms"] for q in pr))
+prof = runs[2]                      # median of five back-to-back passes
+print(f"flags={flags} prefetch={prefetch}")
 tot = sum(p["ms"] for p in prof)
 by = {}
 for p in prof:
