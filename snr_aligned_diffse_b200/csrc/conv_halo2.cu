@@ -374,12 +374,14 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
                     const uint32_t addr0 = a_base + s * a_bytes + (uint32_t)rg * ROW_B + ((q ^ ((uint32_t)rg & 7u)) << 4);
                     if (live) {
                         const bool interior = h0 >= 1 && h0 + SUB_ROWS * g.sub + 1 <= g.H && w0 >= 1 && w0 + TW + 1 <= g.W;
-                        // two rows per trip (independent dependency chains hide the LDS / MUFU latency)
-                        for (int r = rg; r < rows_total; r += 64) {
-                            bool ok[2];
-                            uint4 raw[2];
+                        // NR rows per trip: independent dependency chains hide the LDS / MUFU latency (only two normalising
+                        // warps share a scheduler, so instruction-level parallelism has to come from within the thread)
+                        constexpr int NR = 4;
+                        for (int r = rg; r < rows_total; r += 32 * NR) {
+                            bool ok[NR];
+                            uint4 raw[NR];
 #pragma unroll
-                            for (int k = 0; k < 2; ++k) {
+                            for (int k = 0; k < NR; ++k) {
                                 const int rr = r + 32 * k;
                                 ok[k] = rr < rows_total;
                                 if (!interior) {   // border tile: padding pixels stay zero
@@ -390,7 +392,7 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
                                 if (ok[k]) raw[k] = ptx::lds128(addr0 + (uint32_t)(rr - rg) * ROW_B);
                             }
 #pragma unroll
-                            for (int k = 0; k < 2; ++k) {
+                            for (int k = 0; k < NR; ++k) {
                                 if (ok[k]) {
                                     const uint32_t w[4] = {raw[k].x, raw[k].y, raw[k].z, raw[k].w};
                                     uint4 o;
