@@ -49,8 +49,27 @@ def enhance_sweep(enhance_fn, waves, rank=0, world=1, max_batch=16, device=None,
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record(torch.cuda.current_stream(device))
     t0 = time.perf_counter()
+    # host packing runs a few batches ahead of the launches on two worker threads (the copies release the GIL), so the
+    # GPU never waits for the host to zero-pad the next batch; intra-op threading is switched off meanwhile (a 16-thread
+    # OpenMP pool spinning between 100 us copies slowed the packing 4x on a box whose cores were shared by two ranks)
+    import collections
+    import concurrent.futures
+    prev_threads = torch.get_num_threads()
+    torch.set_num_threads(1)
+    pool = concurrent.futures.ThreadPoolExecutor(max_workers=2)
+    ahead, nxt = collections.deque(), 0
+    depth = 6
+
+    def refill():
+        nonlocal nxt
+        while nxt < len(batches) and len(ahead) < depth:
+            tp, ix = batches[nxt]
+            ahead.append(pool.submit(pack_batch, waves, ix, tp, on_gpu))
+            nxt += 1
+    refill()
     for tpad, idx in batches:
-        y, lens = pack_batch(waves, idx, tpad, pin=on_gpu)
+        y, lens = ahead.popleft().result()
+        refill()
         if device is not None:
             y, lens = y.to(device, non_blocking=True), lens.to(device, non_blocking=True)
         out = enhance_fn(y, lens)
@@ -77,6 +96,8 @@ def enhance_sweep(enhance_fn, waves, rank=0, world=1, max_batch=16, device=None,
         ev1.record(torch.cuda.current_stream(device))
         torch.cuda.synchronize(device)
     wall = time.perf_counter() - t0
+    pool.shutdown(wait=True)
+    torch.set_num_threads(prev_threads)
     seconds = ev0.elapsed_time(ev1) * 1e-3 if on_gpu else wall
     checksum = torch.cat(checks).cpu().tolist() if checks else []
     si_sdr = torch.cat(sdrs).cpu().tolist() if sdrs else [float("nan")] * len(ids)
