@@ -108,7 +108,8 @@ int snrse_ncsnpp_set_weights(void* handle, const void* device_blob);
  * bit3: unused; bit4: GroupNorm+SiLU as a separate pass (no in-kernel fusion);
  * bit5: GroupNorm+SiLU of the up / down blocks inside single-output FIR kernels (two FIR launches per block);
  * bit6: up / down blocks as GroupNorm pass + two FIR passes (the default is ONE dual-output FIR pass over x that
- * writes FIR(silu(GroupNorm(x))) and FIR(x)). */
+ * writes FIR(silu(GroupNorm(x))) and FIR(x)); bit7: GroupNorm scale/shift of the normalising convolutions from gn_finalize
+ * launches (the default derives them inside the convolution kernel from the statistics). */
 int64_t snrse_ncsnpp_plan_bytes(void* handle, int B, int F, int T, int flags);
 int snrse_ncsnpp_plan_bind(void* handle, int B, int F, int T, void* workspace, int64_t bytes);
 /* x (state), y (noisy), out: complex64 [B][F][T]; t [B] f32.  mode 0: dnn(cat[x,y], t);

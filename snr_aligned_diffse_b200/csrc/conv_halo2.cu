@@ -32,6 +32,8 @@
 #include "ptx.cuh"
 #include "tma_host.h"
 
+int g_halo2_prefetch = 1;   // bit0: L2 prefetch of the next tile (snrse_conv_halo_set_prefetch, include/snrse_b200_debug.h)
+
 namespace {
 
 constexpr int HALO_THREADS = 384;        // + 256 (warps 12..19) when GroupNorm+SiLU is applied to the operand in flight
@@ -62,6 +64,8 @@ struct Halo2Args {
     unsigned long long* ustats;    // null, or GroupNorm sums of the result, accumulated: [B][N/4][2] fixed point (gn_fixed.cuh)
     const float* scsh;             // null, or GroupNorm scale/shift [B][2][norm_c] applied (+SiLU) to operand 0 in shared memory
     int norm_c;
+    GnSrc gn;                      // has_gn: scale/shift derived in the kernel from these statistics instead of read from scsh
+    int has_gn;
     const float* bias;
     const float* tbias;
     int tb_stride;
@@ -152,6 +156,8 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
     const int n_astage = g.c0_chunks + g.c1_chunks;   // halo tiles consumed per super-tile
     const uint32_t acc_cols = (uint32_t)(g.sub * g.N);
     const uint32_t tmem_cols = acc_cols * (uint32_t)g.acc_bufs;  // 128/256/512: power of two
+    const bool norm_on = g.scsh != nullptr || g.has_gn;          // GroupNorm + SiLU applied to operand 0 in flight
+    const uint32_t gn_tab = stg_base + (uint32_t)(EPI_WARPS * g.stg_bufs) * 4096u;   // has_gn: scale[512] | shift[512] floats
 
     if (warp == W_MMA1) {
         if (lane == 0) {
@@ -226,7 +232,7 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
                 if (elected) {
                     // 3x3 operand: halo origin (w0-1, h0-1), rows / columns outside the image are zero-filled == conv padding;
                     // 1x1 shortcut operand: the bare tile (8 x 16*SUB pixels)
-                    if (g.scsh) {
+                    if (norm_on) {
                         // tile -> this CTA's own barrier; the normalising warps publish it to the leader afterwards
                         // (shortcut tiles take the same route untouched, so every ring slot follows one protocol)
                         ptx::mbar_arrive_expect_tx(ptx::smem_u32(&a_land[s]), seg0 ? a_tx : a1_tx);
@@ -242,7 +248,7 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
                 if (++s == (uint32_t)g.na) { s = 0; ph ^= 1u; }
             }
         }
-        if (g.dbg && elected && !g.scsh) g.dbg[blockIdx.x * 8 + 6] = w_a;
+        if (g.dbg && elected && !norm_on) g.dbg[blockIdx.x * 8 + 6] = w_a;
     } else if (warp == W_PROD_B) {
         // =========================== B producer: weight tiles ===========================
         const bool elected = ptx::elect_one();
@@ -270,7 +276,7 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
                 }
             }
         }
-        if (g.dbg && elected && !g.scsh) g.dbg[blockIdx.x * 8 + 7] = w_b;
+        if (g.dbg && elected && !norm_on) g.dbg[blockIdx.x * 8 + 7] = w_b;
     } else if (warp == W_MMA0 || warp == W_MMA1) {
         // =========================== MMA issuers (leader CTA only) ===========================
         // One issuing warp per sub-tile (accumulator): measured (profiles/r01_mma_probe.md), the issuing thread's
@@ -331,7 +337,7 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
             if (g.dbg && elected && u == 0) {
                 g.dbg[blockIdx.x * 8 + 0] = w_a;
                 g.dbg[blockIdx.x * 8 + 1] = w_b;
-                if (!g.scsh) g.dbg[blockIdx.x * 8 + 2] = w_acc;
+                if (!norm_on) g.dbg[blockIdx.x * 8 + 2] = w_acc;
                 g.dbg[blockIdx.x * 8 + 3] = clock64() - t_start;
             }
         }
@@ -340,8 +346,10 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
         // y = silu(x * scale[b,c] + shift[b,c]) (ncsnpp_utils/layerspp.py:245,266) applied in place to every raw halo
         // tile: 256 threads, thread = (16-byte chunk q of 8 channels, row group), rows strided by 32.  Pixels outside
         // the image stay zero (the convolution pads the NORMALISED activation).  Same arithmetic as gn_apply_kernel.
-        if (g.scsh) {
+        if (norm_on) {
             const int tid = (warp - NORM_WARP0) * 32 + lane;
+            float* tab = reinterpret_cast<float*>(smem_raw + (gn_tab - ptx::smem_u32(smem_raw)));
+            int tab_b = -1;                                       // image whose scale / shift the table holds
             const uint32_t q = (uint32_t)(tid & 7);
             const int rg = tid >> 3;
             const int rows_total = (SUB_ROWS * g.sub + 2) * HALO_W;
@@ -353,15 +361,50 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
                 const int tile = 2 * ct + (int)rank;
                 const int b = tile / tiles_per_img, rem = tile % tiles_per_img;
                 const int h0 = (rem / g.tiles_w) * SUB_ROWS * g.sub, w0 = (rem % g.tiles_w) * TW;
+                if (g.has_gn && b < g.B && b != tab_b) {
+                    // In-kernel finalize (replaces a gn_finalize launch per normalised convolution): per-channel scale /
+                    // shift of image b from the fixed-point unit sums, same arithmetic as gn_finalize_kernel.  A cluster
+                    // walks consecutive tiles, so this runs once or twice per CTA.
+                    asm volatile("bar.sync 1, 256;" ::: "memory");   // everyone holds the previous image's values in registers
+                    const int C = g.norm_c, cpg = C >> 5, upg = cpg >> 2;
+                    for (int c = tid; c < C; c += NORM_THREADS) {
+                        const int grp = c / cpg;
+                        long long sm = 0;
+                        double q = 0.0;
+                        for (int k = 0; k < upg; ++k) {
+                            const int u = grp * upg + k;
+                            const unsigned long long* p = u < g.gn.U0 ? g.gn.st0 + ((int64_t)b * g.gn.U0 + u) * 2
+                                                                       : g.gn.st1 + ((int64_t)b * g.gn.U1 + (u - g.gn.U0)) * 2;
+                            sm += (long long)__ldg(p);
+                            q += gn_unfix_sq(__ldg(p + 1));
+                        }
+                        const double mean = gn_unfix_sum(sm) * g.gn.inv_count;
+                        double var = q * g.gn.inv_count - mean * mean;
+                        if (var < 0.0) var = 0.0;
+                        const float mean_f = (float)mean, rstd = (float)(1.0 / sqrt(var + (double)g.gn.eps));
+                        const float scv = rstd * __ldg(g.gn.gamma + c);
+                        tab[c] = scv;
+                        tab[512 + c] = __ldg(g.gn.beta + c) - mean_f * scv;
+                    }
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                    tab_b = b;
+                }
                 for (int j = 0; j < n_astage; ++j) {
                     const bool live = (b < g.B) && !(g.seq[j] & 0x80);   // the 1x1 shortcut operand is used raw
                     const int chunk = g.seq[j] & 0x7f;
                     // h = x * (scale/2) + shift/2  ==  (x*scale + shift)/2 exactly;  silu(t) = h + h*tanh(h)  (silu_f)
                     float sc[8], sh[8];
                     if (live) {
-                        const float4* pa = reinterpret_cast<const float4*>(g.scsh + ((int64_t)b * 2) * g.norm_c + chunk * 64 + q * 8);
-                        const float4* pc = reinterpret_cast<const float4*>(g.scsh + ((int64_t)b * 2 + 1) * g.norm_c + chunk * 64 + q * 8);
-                        const float4 a0 = __ldg(pa), a1 = __ldg(pa + 1), c0 = __ldg(pc), c1 = __ldg(pc + 1);
+                        float4 a0, a1, c0, c1;
+                        if (g.has_gn) {
+                            const float4* pa = reinterpret_cast<const float4*>(tab + chunk * 64 + q * 8);
+                            const float4* pc = reinterpret_cast<const float4*>(tab + 512 + chunk * 64 + q * 8);
+                            a0 = pa[0]; a1 = pa[1]; c0 = pc[0]; c1 = pc[1];
+                        } else {
+                            const float4* pa = reinterpret_cast<const float4*>(g.scsh + ((int64_t)b * 2) * g.norm_c + chunk * 64 + q * 8);
+                            const float4* pc = reinterpret_cast<const float4*>(g.scsh + ((int64_t)b * 2 + 1) * g.norm_c + chunk * 64 + q * 8);
+                            a0 = __ldg(pa); a1 = __ldg(pa + 1); c0 = __ldg(pc); c1 = __ldg(pc + 1);
+                        }
                         sc[0] = a0.x; sc[1] = a0.y; sc[2] = a0.z; sc[3] = a0.w; sc[4] = a1.x; sc[5] = a1.y; sc[6] = a1.z; sc[7] = a1.w;
                         sh[0] = c0.x; sh[1] = c0.y; sh[2] = c0.z; sh[3] = c0.w; sh[4] = c1.x; sh[5] = c1.y; sh[6] = c1.z; sh[7] = c1.w;
 #pragma unroll
@@ -611,7 +654,7 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
 int g_num_sms2 = 0;
 }  // namespace
 extern long long* g_halo_dbg_shared;
-int g_halo2_prefetch = 1;   // measurement switch (snrse_conv_halo_set_prefetch, include/snrse_b200_debug.h)
+extern int g_halo2_prefetch;   // measurement switch (snrse_conv_halo_set_prefetch, include/snrse_b200_debug.h)
 
 bool conv_halo2_eligible(const ActView* a0, int taps0, int n_rows) {
     return taps0 == 9 && a0->W >= TW && a0->H >= 8 && (n_rows == 128 || n_rows == 256);
@@ -619,8 +662,12 @@ bool conv_halo2_eligible(const ActView* a0, int taps0, int n_rows) {
 
 int conv_halo2_make_plan(ConvHaloPlan* p, const ActView* a0, const ActView* a1, const bf16* wt, int n_rows,
                          const float* bias, const float* tbias, int tb_stride, const ActView* res, float scale, bf16* out,
-                         int out_ld, const float* scsh, unsigned long long* ustats) {
+                         int out_ld, const float* scsh, unsigned long long* ustats, const GnSrc* gn) {
     SNRSE_CHECK_ARG(conv_halo2_eligible(a0, 9, n_rows), "conv_halo2: shape not eligible");
+    SNRSE_CHECK_ARG(!(scsh && gn), "conv_halo2: give either a scale/shift table or the statistics, not both");
+    SNRSE_CHECK_ARG(!gn || (a0->C <= 512 && gn->st0 && gn->gamma && gn->beta && 4 * (gn->U0 + gn->U1) == a0->C),
+                    "conv_halo2: bad GroupNorm statistics source");
+    const bool norm = scsh || gn;
     SNRSE_CHECK_ARG(a0->C % 64 == 0 && a0->ld % 8 == 0, "conv_halo2: Cin must be a multiple of 64");
     SNRSE_CHECK_ARG(!a1 || (a1->C % 64 == 0 && a1->ld % 8 == 0 && a1->H == a0->H && a1->W == a0->W && a1->B == a0->B),
                     "conv_halo2: bad shortcut operand");
@@ -652,12 +699,13 @@ int conv_halo2_make_plan(ConvHaloPlan* p, const ActView* a0, const ActView* a1, 
     p->N = n_loc;
     p->acc_bufs = (sub * n_loc <= 256) ? 2 : 1;
     const int a_bytes = (int)halo_stage_bytes(sub), b_bytes = (n_loc / 2) * 128;
-    const int budget = 220 * 1024;   // dynamic shared memory (static: barriers + per-warp bias slices, ~4.3 KB)
+    // dynamic shared memory (static: barriers + per-warp bias slices, ~4.3 KB); the in-kernel GroupNorm table takes 4 KB
+    const int budget = 220 * 1024 - (gn ? 4096 : 0);
     // One A slot feeds 9 taps x SUB x 4 MMAs (>= 2300 clk): two slots hide the next tile's load.  With in-flight
     // normalisation the slot also waits for the normalising warps (load + ~2500 clk); at N=128 (64-clock MMAs) that
     // needs a third slot, paid for with single-buffered epilogue staging.
     int na = 2, stg = 2;
-    if (scsh && n_loc == 128 && sub == 2) { na = 3; stg = 1; }
+    if (norm && n_loc == 128 && sub == 2 && !(g_halo2_prefetch & 2)) { na = 3; stg = 1; }   // bit1: A/B measurement of na=2 / stg=2
     int nb = (budget - na * a_bytes - stg * EPI_WARPS * 4096) / b_bytes;
     if (nb < 6 && stg == 2) {
         stg = 1;
@@ -667,13 +715,14 @@ int conv_halo2_make_plan(ConvHaloPlan* p, const ActView* a0, const ActView* a1, 
     SNRSE_CHECK_ARG(nb >= 4, "conv_halo2: shared memory budget");
     if (na < MAX_A && (budget - (na + 1) * a_bytes - stg * EPI_WARPS * 4096 - nb * b_bytes) >= 0) ++na;
     p->na = na; p->nb = nb; p->stg_bufs = stg;
-    p->smem_bytes = na * a_bytes + nb * b_bytes + stg * EPI_WARPS * 4096 + 1024;
+    p->smem_bytes = na * a_bytes + nb * b_bytes + stg * EPI_WARPS * 4096 + (gn ? 4096 : 0) + 1024;
     const int n_ctiles = (p->n_tiles + 1) / 2, max_clusters = g_num_sms2 / 2;
     p->grid = nsplit == 2 ? 4 * n_ctiles : 2 * (n_ctiles < max_clusters ? n_ctiles : max_clusters);
     p->bias = bias; p->tbias = tbias; p->tb_stride = tb_stride;
     p->res = res ? res->ptr : nullptr; p->res_ld = res ? res->ld : 0;
     p->scale = scale; p->out = out; p->out_ld = out_ld;
     p->scsh = scsh;
+    if (gn) { p->gn = *gn; p->has_gn = 1; }
     p->ustats = ustats;
     const int box_h = SUB_ROWS * sub + 2;
     SNRSE_TRY(tma_make_act_map(&p->mapA0, a0->ptr, a0->C, a0->W, a0->H, a0->B, a0->ld, 64, HALO_W, box_h));
@@ -691,8 +740,11 @@ int conv_halo2_make_plan(ConvHaloPlan* p, const ActView* a0, const ActView* a1, 
 // Thin output convolution on the same kernel: 3x3, C -> 4 (weights packed as 16 rows, rows 4..15 zero), optional
 // GroupNorm+SiLU of the operand in flight, fp32 output [B,H,W,4] = conv + bias (+ addend4).
 int conv_halo2_make_plan_out4(ConvHaloPlan* p, const ActView* a0, const bf16* wt16, const float* bias4, const float* addend4,
-                              float* out4, const float* scsh) {
+                              float* out4, const float* scsh, const GnSrc* gn) {
     SNRSE_CHECK_ARG(a0->W >= TW && a0->H >= 8 && a0->C % 64 == 0 && a0->ld % 8 == 0, "conv_halo2 out4: shape not eligible");
+    SNRSE_CHECK_ARG(!(scsh && gn), "conv_halo2 out4: give either a scale/shift table or the statistics, not both");
+    SNRSE_CHECK_ARG(!gn || (a0->C <= 512 && gn->st0 && gn->gamma && gn->beta && 4 * (gn->U0 + gn->U1) == a0->C),
+                    "conv_halo2 out4: bad GroupNorm statistics source");
     SNRSE_CHECK_ARG(bias4 && out4, "conv_halo2 out4: null pointer");
     if (g_num_sms2 == 0) {
         int dev = 0;
@@ -715,12 +767,13 @@ int conv_halo2_make_plan_out4(ConvHaloPlan* p, const ActView* a0, const bf16* wt
     p->n_total = 16;
     p->acc_bufs = 2;
     const int a_bytes = (int)halo_stage_bytes(sub);
-    p->na = 3; p->nb = MAX_B; p->stg_bufs = 1;
-    p->smem_bytes = p->na * a_bytes + p->nb * 1024 + 1024;
+    p->na = 3; p->nb = MAX_B; p->stg_bufs = 0;   // no epilogue staging: the result leaves from registers
+    p->smem_bytes = p->na * a_bytes + p->nb * 1024 + (gn ? 4096 : 0) + 1024;
     const int n_ctiles = (p->n_tiles + 1) / 2, max_clusters = g_num_sms2 / 2;
     p->grid = 2 * (n_ctiles < max_clusters ? n_ctiles : max_clusters);
     p->bias = bias4; p->scale = 1.0f;
     p->scsh = scsh;
+    if (gn) { p->gn = *gn; p->has_gn = 1; }
     p->out4 = out4; p->addend4 = addend4;
     SNRSE_TRY(tma_make_act_map(&p->mapA0, a0->ptr, a0->C, a0->W, a0->H, a0->B, a0->ld, 64, HALO_W, SUB_ROWS * sub + 2));
     p->mapA1 = p->mapA0; p->mapOut = p->mapA0; p->mapRes = p->mapA0;
@@ -749,14 +802,15 @@ int conv_halo2_launch(const ConvHaloPlan* p, cudaStream_t s) {
     g.sub = p->sub; g.tiles_h = p->tiles_h; g.tiles_w = p->tiles_w; g.n_tiles = p->n_tiles;
     g.N = p->N; g.nsplit = p->nsplit; g.n_total = p->n_total; g.na = p->na; g.nb = p->nb; g.acc_bufs = p->acc_bufs; g.stg_bufs = p->stg_bufs;
     g.has_res = p->res != nullptr;
-    g.prefetch = g_halo2_prefetch;
+    g.prefetch = g_halo2_prefetch & 1;
     g.bias = p->bias; g.tbias = p->tbias; g.tb_stride = p->tb_stride;
     g.scale = p->scale;
     g.scsh = p->scsh; g.norm_c = p->c0_chunks * 64;
+    g.gn = p->gn; g.has_gn = p->has_gn;
     g.ustats = p->ustats;
     g.out4 = reinterpret_cast<float4*>(p->out4); g.addend4 = reinterpret_cast<const float4*>(p->addend4);
     g.dbg = g_halo_dbg_shared;
-    conv_halo2_kernel<<<p->grid, HALO_THREADS + (p->scsh ? NORM_THREADS : 0), p->smem_bytes, s>>>(p->mapA0, p->mapA1, p->mapB, p->mapOut, p->mapRes, g);
+    conv_halo2_kernel<<<p->grid, HALO_THREADS + ((p->scsh || p->has_gn) ? NORM_THREADS : 0), p->smem_bytes, s>>>(p->mapA0, p->mapA1, p->mapB, p->mapOut, p->mapRes, g);
     SNRSE_LAUNCH_CHECK();
     return SNRSE_OK;
 }

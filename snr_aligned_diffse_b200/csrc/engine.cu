@@ -332,12 +332,22 @@ const float INV_SQRT2 = 0.70710678118654752440f;
 constexpr int MAX_STAT_ENTRIES = 192;   // tensors with GroupNorm statistics per forward (NCSN++ default: ~110)
 enum { LK_OTHER = 0, LK_GEMM = 1, LK_GN = 2, LK_FIR = 3, LK_ATTN = 4, LK_THIN = 5, LK_HEAD = 6 };
 
+// GroupNorm of a convolution operand, resolved inside the 2-CTA kernel (no gn_finalize launch): statistics entries of the
+// tensor (or of the two halves of a concatenation), units per source, elements per group, affine parameters
+struct GnRef {
+    int s0 = -1, s1 = -1, u0 = 0, u1 = 0;
+    int64_t cnt = 0, g_off = 0, b_off = 0;
+};
+
 int rec_gemm(Plan& P, int a0, int taps0, int a1, int64_t w_off, int n_rows, int64_t bias_off, int tb_row, int res,
-             float scale, int out, int norm = 0, int want_stats = 0, int algo_cin = 0) {
+             float scale, int out, int norm = 0, int want_stats = 0, int algo_cin = 0, const GnRef* gnref = nullptr) {
+    const bool has_gn = gnref != nullptr;
+    GnRef gr;
+    if (has_gn) gr = *gnref;
     // algo_cin > 0: channel count the ALGORITHM contracts over when the operand is a zero-padded copy (the 4-channel
     // network input enters as a 64-channel hi/lo tile): FLOPs and bytes are booked at algo_cin, not at the padded width
     P.use(a0);
-    if (norm) P.use(P.t_scsh);
+    if (norm && !has_gn) P.use(P.t_scsh);
     int st = -1;
     if (want_stats) {   // the epilogue also accumulates the GroupNorm sums of `out`
         st = P.n_stat_entries++;
@@ -379,9 +389,19 @@ int rec_gemm(Plan& P, int a0, int taps0, int a1, int64_t w_off, int n_rows, int6
         const double by = 2.0 * (px * (c0 + (a1 >= 0 ? va1.C : 0) + n_rows + (res >= 0 ? n_rows : 0)) + kt * n_rows);
         if (!(p.flags & 4) && conv_halo2_eligible(&va0, taps0, n_rows)) {   // 2-CTA (cta_group::2) halo kernel
             ConvHaloPlan hp;
+            GnSrc src{};
+            if (has_gn) {
+                src.st0 = p.stat_ptr(gr.s0);
+                src.st1 = gr.s1 >= 0 ? p.stat_ptr(gr.s1) : nullptr;
+                src.U0 = gr.u0; src.U1 = gr.u1;
+                src.inv_count = 1.0 / (double)gr.cnt;
+                src.gamma = e.wf(gr.g_off); src.beta = e.wf(gr.b_off);
+                src.eps = 1e-6f;
+            }
             SNRSE_TRY(conv_halo2_make_plan(&hp, &va0, a1 >= 0 ? &va1 : nullptr, e.wb(w_off), n_rows, bias, tb, tb_stride,
                                            res >= 0 ? &vres : nullptr, scale, vout.ptr, vout.ld,
-                                           norm ? p.fptr(p.t_scsh) : nullptr, st >= 0 ? p.stat_ptr(st) : nullptr));
+                                           (norm && !has_gn) ? p.fptr(p.t_scsh) : nullptr, st >= 0 ? p.stat_ptr(st) : nullptr,
+                                           (norm && has_gn) ? &src : nullptr));
             p.add(LK_GEMM, 2.0 * px * n_rows * kt, by, [hp](cudaStream_t s) { return conv_halo2_launch(&hp, s); });
             return SNRSE_OK;
         }
@@ -449,6 +469,33 @@ void rec_gn_finalize(Plan& P, int x, int64_t g_off, int64_t b_off) {
     });
 }
 
+// GroupNorm feeding a convolution on the 2-CTA kernel: by default the kernel derives scale / shift from the statistics itself
+// (returns true and fills `ref`; nothing is launched here beyond a stand-alone statistics pass where the tensor's writer
+// did not emit them); with flag bit7 a gn_finalize launch writes the table into t_scsh as in r01 (returns false).
+bool rec_gn_for_conv(Plan& P, int x, int64_t g_off, int64_t b_off, GnRef* ref) {
+    if (P.flags & 128) {
+        rec_gn_finalize(P, x, g_off, b_off);
+        return false;
+    }
+    GnRef r;
+    auto cc = P.cat_children.find(x);
+    if (cc != P.cat_children.end()) {
+        r.s0 = get_stats(P, cc->second.first);
+        r.s1 = get_stats(P, cc->second.second);
+        r.u0 = P.tens[cc->second.first].C / 4;
+        r.u1 = P.tens[cc->second.second].C / 4;
+    } else {
+        r.s0 = get_stats(P, x);
+        r.u0 = P.tens[x].C / 4;
+    }
+    const LT tx = P.tens[x];
+    r.cnt = (int64_t)tx.H * tx.W * (tx.C / 32);
+    r.g_off = g_off;
+    r.b_off = b_off;
+    *ref = r;
+    return true;
+}
+
 // GroupNorm (+SiLU) as its own pass -> new dense tensor
 int rec_gn(Plan& P, int x, int64_t g_off, int64_t b_off, int silu) {
     rec_gn_finalize(P, x, g_off, b_off);
@@ -513,8 +560,10 @@ void rec_fir_dual(Plan& P, int x, int up, int* a, int* xs) {
 int rec_resblock(Plan& P, const Mod& m, int x) {
     // GroupNorm_0 + SiLU (+ FIR resampling of both branches) + Conv_0 + Dense_0(temb)
     int a, xs = x, fuse0 = 0;
+    GnRef gn0, gn1;
+    bool has_gn0 = false, has_gn1 = false;
     if (!m.up && !m.down && fusable(P, x, m.cout)) {
-        rec_gn_finalize(P, x, m.o[0], m.o[1]);  // normalisation itself happens inside Conv_0
+        has_gn0 = rec_gn_for_conv(P, x, m.o[0], m.o[1], &gn0);  // normalisation itself happens inside Conv_0
         a = x;
         fuse0 = 1;
     } else {
@@ -539,19 +588,20 @@ int rec_resblock(Plan& P, const Mod& m, int x) {
     const int h = P.new_t(ta.B, ta.H, ta.W, m.cout, 2);
     // the 2-CTA kernel's epilogue also emits the GroupNorm partial sums of what it writes
     const int stats0 = fusable(P, a, m.cout);
-    rec_gemm(P, a, 9, -1, m.o[2], m.cout, m.o[3], m.tb_row, -1, 1.0f, h, fuse0, stats0);
+    rec_gemm(P, a, 9, -1, m.o[2], m.cout, m.o[3], m.tb_row, -1, 1.0f, h, fuse0, stats0, 0, has_gn0 ? &gn0 : nullptr);
     // GroupNorm_1 + SiLU + Conv_1 (+ Conv_2 shortcut or identity residual), / sqrt(2)
     int a2 = h, fuse1 = 0;
     if (fusable(P, h, m.cout)) {
-        rec_gn_finalize(P, h, m.o[4], m.o[5]);
+        has_gn1 = rec_gn_for_conv(P, h, m.o[4], m.o[5], &gn1);
         fuse1 = 1;
     } else {
         a2 = rec_gn(P, h, m.o[4], m.o[5], 1);
     }
     const int out = P.new_t(ta.B, ta.H, ta.W, m.cout, 2);
     const int stats1 = fusable(P, a2, m.cout);
-    if (m.has_c2) rec_gemm(P, a2, 9, xs, m.o[6], m.cout, m.o[7], -1, -1, INV_SQRT2, out, fuse1, stats1);
-    else rec_gemm(P, a2, 9, -1, m.o[6], m.cout, m.o[7], -1, xs, INV_SQRT2, out, fuse1, stats1);
+    const GnRef* g1 = has_gn1 ? &gn1 : nullptr;
+    if (m.has_c2) rec_gemm(P, a2, 9, xs, m.o[6], m.cout, m.o[7], -1, -1, INV_SQRT2, out, fuse1, stats1, 0, g1);
+    else rec_gemm(P, a2, 9, -1, m.o[6], m.cout, m.o[7], -1, xs, INV_SQRT2, out, fuse1, stats1, 0, g1);
     return out;
 }
 
@@ -703,7 +753,9 @@ int record_plan(Plan& P) {
             // tensor-core kernel with the normalisation in flight when the map is large enough, CUDA cores otherwise
             const bool tc = fusable(P, h, 128);
             int a = h;
-            if (tc) rec_gn_finalize(P, h, mg.o[0], mg.o[1]);
+            GnRef gnh;
+            bool has_gnh = false;
+            if (tc) has_gnh = rec_gn_for_conv(P, h, mg.o[0], mg.o[1], &gnh);
             else a = rec_gn(P, h, mg.o[0], mg.o[1], 1);
             const LT th = P.tens[h];
             const int np = P.new_t(th.B, th.H, th.W, 4, 4);
@@ -711,7 +763,7 @@ int record_plan(Plan& P) {
             if (pyr >= 0) up = P.new_t(th.B, th.H, th.W, 4, 4);
             const int prev = pyr;
             P.use(a); P.use(np);
-            if (tc) P.use(P.t_scsh);
+            if (tc && !has_gnh) P.use(P.t_scsh);
             if (prev >= 0) { P.use(prev); P.use(up); }
             P.step++;
             P.builders.push_back([=](Plan& p) -> int {
@@ -723,7 +775,17 @@ int record_plan(Plan& P) {
                 const double px = (double)va.B * va.H * va.W;
                 if (tc) {
                     ConvHaloPlan hp;
-                    SNRSE_TRY(conv_halo2_make_plan_out4(&hp, &va, e.wb(mc.o[2]), e.wf(mc.o[1]), upp, dst, p.fptr(p.t_scsh)));
+                    GnSrc src{};
+                    if (has_gnh) {
+                        src.st0 = p.stat_ptr(gnh.s0);
+                        src.st1 = gnh.s1 >= 0 ? p.stat_ptr(gnh.s1) : nullptr;
+                        src.U0 = gnh.u0; src.U1 = gnh.u1;
+                        src.inv_count = 1.0 / (double)gnh.cnt;
+                        src.gamma = e.wf(gnh.g_off); src.beta = e.wf(gnh.b_off);
+                        src.eps = 1e-6f;
+                    }
+                    SNRSE_TRY(conv_halo2_make_plan_out4(&hp, &va, e.wb(mc.o[2]), e.wf(mc.o[1]), upp, dst,
+                                                        has_gnh ? nullptr : p.fptr(p.t_scsh), has_gnh ? &src : nullptr));
                     p.add(LK_THIN, 2.0 * px * 36 * va.C, px * (2.0 * va.C + 16 + (pv ? 20 : 0)), [=](cudaStream_t s) {
                         if (pv) SNRSE_TRY(fir_up2_f4_launch(pv, upp, va.B, va.H / 2, va.W / 2, s));
                         return conv_halo2_launch(&hp, s);

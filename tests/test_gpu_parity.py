@@ -435,8 +435,8 @@ def _network_report(engine, sd, x, t, flags):
     return ref[:, 0], out.cpu(), rep
 
 
-@pytest.mark.parametrize("flags", [2, 4, 16, 32, 0], ids=["cuda-core-conv", "tcgen05gemm-conv", "tcgen05-gn-in-fir",
-                                                    "tcgen05-unfused-gn", "tcgen05-conv"])
+@pytest.mark.parametrize("flags", [2, 4, 16, 32, 192, 0], ids=["cuda-core-conv", "tcgen05gemm-conv", "tcgen05-unfused-gn",
+                                                         "tcgen05-gn-in-single-fir", "tcgen05-r01-gn-passes", "tcgen05-conv"])
 def test_ncsnpp_forward_vs_golden(engine, sd, golden_dir, flags):
     z = np.load(os.path.join(golden_dir, "ncsnpp_forward.npz"))
     x, t = _c(z["x"]), _c(z["t"])
@@ -447,6 +447,21 @@ def test_ncsnpp_forward_vs_golden(engine, sd, golden_dir, flags):
     msg = " ".join(f"{i}:{r:.1e}" for i, r in rep)
     assert worst <= 2.5e-2, msg                                      # every module output, bf16 vs fp32 oracle
     assert rel_l2(torch.view_as_real(out), torch.view_as_real(gold)) <= 2e-2, msg
+
+
+@pytest.mark.parametrize("B,T", [(2, 64), (3, 192), (5, 128)])
+def test_in_kernel_groupnorm_finalize_equals_finalize_launches(engine, B, T):
+    """Default: the normalising convolutions derive GroupNorm scale / shift from the fixed-point statistics inside the
+    kernel (one or two sources for concatenated inputs, recomputed when a CTA moves to the next image).  Flag bit7
+    restores a gn_finalize launch per normalisation (r01).  Same arithmetic -> the network output is bit-identical;
+    so is the dual-output FIR pass of the up / down blocks against GroupNorm pass + two FIR passes (bit6)."""
+    g = torch.Generator().manual_seed(B * 1000 + T)
+    x = torch.view_as_complex(torch.randn(B, 2, 256, T, 2, generator=g) * 0.3)
+    t = torch.linspace(0.05, 0.9, B)
+    outs = [engine.forward(x[:, 0].to(DEV), x[:, 1].to(DEV), t.to(DEV), mode=1, flags=f).clone() for f in (0, 128, 64, 192)]
+    for o in outs[1:]:
+        assert torch.equal(torch.view_as_real(outs[0]), torch.view_as_real(o))
+    assert torch.isfinite(torch.view_as_real(outs[0])).all()
 
 
 def test_ncsnpp_batch_and_length_independence_tcgen05(engine, sd):
