@@ -700,7 +700,7 @@ int conv_halo2_make_plan(ConvHaloPlan* p, const ActView* a0, const ActView* a1, 
     p->acc_bufs = (sub * n_loc <= 256) ? 2 : 1;
     const int a_bytes = (int)halo_stage_bytes(sub), b_bytes = (n_loc / 2) * 128;
     // dynamic shared memory (static: barriers + per-warp bias slices, ~4.3 KB); the in-kernel GroupNorm table takes 4 KB
-    const int budget = 220 * 1024 - (gn ? 4096 : 0);
+    const int budget = 220 * 1024 - ((gn || (g_halo2_prefetch & 4)) ? 4096 : 0);   // bit2: A/B measurement of the smaller budget alone
     // One A slot feeds 9 taps x SUB x 4 MMAs (>= 2300 clk): two slots hide the next tile's load.  With in-flight
     // normalisation the slot also waits for the normalising warps (load + ~2500 clk); at N=128 (64-clock MMAs) that
     // needs a third slot, paid for with single-buffered epilogue staging.

@@ -469,11 +469,14 @@ void rec_gn_finalize(Plan& P, int x, int64_t g_off, int64_t b_off) {
     });
 }
 
-// GroupNorm feeding a convolution on the 2-CTA kernel: by default the kernel derives scale / shift from the statistics itself
-// (returns true and fills `ref`; nothing is launched here beyond a stand-alone statistics pass where the tensor's writer
-// did not emit them); with flag bit7 a gn_finalize launch writes the table into t_scsh as in r01 (returns false).
+// GroupNorm feeding a convolution on the 2-CTA kernel.  Default: a gn_finalize launch writes the scale / shift table into
+// t_scsh (returns false).  Flag bit7: the kernel derives scale / shift from the statistics itself (returns true and fills
+// `ref`; nothing is launched here beyond a stand-alone statistics pass where the tensor's writer did not emit them).
+// Measured on the graphed 16 x 4 s step, variants interleaved (tools/step_ab.py, profiles/r02_step_ab.md): 77 launches
+// fewer but +0.2 ms per step -- the table costs the weight ring a slot and stalls the normalising warps at every image
+// change, and under the power cap the saved launch gaps buy nothing -- so the launches stay the default.
 bool rec_gn_for_conv(Plan& P, int x, int64_t g_off, int64_t b_off, GnRef* ref) {
-    if (P.flags & 128) {
+    if (!(P.flags & 128)) {
         rec_gn_finalize(P, x, g_off, b_off);
         return false;
     }
@@ -574,8 +577,10 @@ int rec_resblock(Plan& P, const Mod& m, int x) {
             rec_gn_finalize(P, x, m.o[0], m.o[1]);
             a = rec_fir(P, x, m.up ? 1 : 0, 1);
             xs = rec_fir(P, x, m.up ? 1 : 0, 0);
-        } else if ((m.up || m.down) && !(P.flags & (16 | 64))) {
-            // default: one dual-output FIR pass over x produces both branches (x is read once instead of four times)
+        } else if ((m.up || m.down) && (P.flags & 64) && !(P.flags & 16)) {
+            // bit6: one dual-output FIR launch over x produces both branches (x comes from DRAM once instead of three
+            // times).  Measured neutral on the graphed step (19.92 vs 19.90 ms, profiles/r02_step_ab.md): the FIR kernels are
+            // issue-bound on the redundant SiLU evaluations, so the three-pass form stays the default.
             rec_gn_finalize(P, x, m.o[0], m.o[1]);
             rec_fir_dual(P, x, m.up ? 1 : 0, &a, &xs);
         } else {
