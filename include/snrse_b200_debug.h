@@ -27,7 +27,9 @@ int snrse_ncsnpp_read_tap(void* handle, int B, int F, int T, int module_idx, flo
 /* cycle counters of the convolution kernels: [grid][8] int64 (a / b / accumulator waits of the MMA warp, total,
  * epilogue wait / body, producer waits), filled by every later launch; NULL switches them off */
 void snrse_conv_halo_set_debug(long long* dev_counters);
-/* A/B switch of the L2 prefetch (next tile's operand and residual boxes) in the 2-CTA convolution kernel: default 1 */
+/* measurement switches of the 2-CTA convolution kernel.  bit0: L2 prefetch of the next tile's operand and residual boxes
+ * (default 0: measured +0.1 ms per step); bit1: two A slots + double-buffered staging on the GroupNorm-in-flight layers;
+ * bit2: 4 KB smaller shared-memory budget.  See profiles/r02_step_ab.md. */
 void snrse_conv_halo_set_prefetch(int on);
 
 #ifdef __cplusplus

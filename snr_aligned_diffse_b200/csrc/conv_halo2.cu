@@ -32,7 +32,9 @@
 #include "ptx.cuh"
 #include "tma_host.h"
 
-int g_halo2_prefetch = 1;   // bit0: L2 prefetch of the next tile (snrse_conv_halo_set_prefetch, include/snrse_b200_debug.h)
+// Measurement switches (snrse_conv_halo_set_prefetch, include/snrse_b200_debug.h).  bit0: L2 prefetch of the next tile's
+// boxes -- measured on the graphed step, interleaved: 20.05 ms with, 19.95 ms without (profiles/r02_step_ab.md), so OFF.
+int g_halo2_prefetch = 0;
 
 namespace {
 
@@ -209,10 +211,10 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
             const int tile = 2 * ct + (int)rank;
             const int b = tile / tiles_per_img, rem = tile % tiles_per_img;   // tile == n_tiles -> b == B: zero fill
             const int h0 = (rem / g.tiles_w) * SUB_ROWS * g.sub, w0 = (rem % g.tiles_w) * TW;
-            // the tile this CTA walks next: its boxes are prefetched into L2 one whole tile ahead (one prefetch per stage),
-            // so that the ring's loads -- only two or three stages deep, and the 1x1 shortcut stages are consumed in 512
-            // clk each -- find their data in L2 instead of paying the DRAM latency (measured before: the MMA warp of
-            // the fused-shortcut layers waited on A 41 % of its time, profiles/r02_conv_ncu.md)
+            // optional (off by default, see g_halo2_prefetch): the boxes of the tile this CTA walks next are prefetched into
+            // L2 one whole tile ahead.  The MMA warp of the fused-shortcut layers waits on A 41 % of its time
+            // (profiles/r02_conv_ncu.md), but the prefetch does not change that: the limit is the bytes the two- or
+            // three-stage ring can keep in flight against 512-clk shortcut stages, not the DRAM latency.
             const int ctn = ct + n_clusters;
             const int tile_n = 2 * ctn + (int)rank;
             const int bn = tile_n / tiles_per_img, remn = tile_n % tiles_per_img;

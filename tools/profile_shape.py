@@ -13,7 +13,7 @@ from snr_aligned_diffse_b200.synth import synth_state_dict  # noqa: E402
 
 B, T = int(sys.argv[1]), int(sys.argv[2])
 flags = int(sys.argv[3]) if len(sys.argv) > 3 else 0
-prefetch = int(sys.argv[4]) if len(sys.argv) > 4 else 1
+prefetch = int(sys.argv[4]) if len(sys.argv) > 4 else 0
 from snr_aligned_diffse_b200 import _lib  # noqa: E402
 _lib.load().snrse_conv_halo_set_prefetch(prefetch)
 eng = NCSNppEngine()

@@ -15,19 +15,21 @@ sys.path.insert(0, ROOT)
 import bench  # noqa: E402
 from snr_aligned_diffse_b200.pipeline import GraphedEnhancer  # noqa: E402
 
-flags = [int(a) for a in sys.argv[1:]] or [0, 128, 64, 192]
-prefetch = int(os.environ.get("SNRSE_PREFETCH", "1"))
 from snr_aligned_diffse_b200 import _lib  # noqa: E402
-_lib.load().snrse_conv_halo_set_prefetch(prefetch)
+# a variant is FLAGS or FLAGS:PREFETCH (L2 prefetch switch of the 2-CTA convolution kernel, read when the graph is captured)
+variants = sys.argv[1:] or ["0", "128", "64", "192"]
+flags = variants
 dev = torch.device("cuda", 0)
 torch.cuda.set_device(0)
 L = int(bench.SECONDS * bench.SR)
 y = bench.synth_waves(bench.BATCH, L, seed=1000).to(dev)
 pipes = []
-for i, f in enumerate(flags):
+for i, v in enumerate(variants):
+    f, pf = (v.split(":") + ["0"])[:2]
+    _lib.load().snrse_conv_halo_set_prefetch(int(pf))
     model, _ = bench.build_models(dev, with_estimator=(i == 0))
     model.dnn._ensure_device_weights()
-    model.dnn.engine.default_flags = f
+    model.dnn.engine.default_flags = int(f)
     p = GraphedEnhancer(model, bench.BATCH, L, dev, oracle=False)
     p.y_dev.copy_(y)
     p.capture(warmup=2)
