@@ -276,7 +276,7 @@ def profile_roofline(model, pipe, y_dev, peaks):
         d["frac_of_hbm"] = round(d["algo_GBps"] / hbm, 3) if d["algo_GBps"] else None
     traffic, traffic_note = None, None
     try:   # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture (profiles/)
-        cap = json.load(open(os.path.join(ROOT, "profiles", "r01_conv_halo2_ncu.json")))
+        cap = json.load(open(os.path.join(ROOT, "profiles", "r02_conv_halo2_ncu.json")))
         c = cap["gn_silu_in_flight"]
         traffic = int(c["dram_bytes_read"] + c["dram_bytes_write"])
         traffic_note = (f"bytes per launch of {cap['shape']}; algorithmic bytes of that launch "
