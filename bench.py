@@ -481,7 +481,7 @@ def run_b200(args):
                                       utterances=r["utterances"], audio_seconds=round(r["audio_seconds"], 1),
                                       value=sweeps["0.17783"]["value"], by_fixed_snr=sweeps, mode=r["mode"],
                                       sharding="equal-Tpad batches of <= 16 assigned to ranks by LPT on a fitted per-batch cost")
-            r = wl.run_longform60(model, dev, rank, world, count=2)
+            r = wl.run_longform60(model, dev, rank, world, count=2, repeat=3)
             extras["longform60"] = dict(metric="enhanced audio-sec/sec, 60 s utterances (Tpad 7552), batch 1", unit=UNIT,
                                         scaling="weak", n_gpus=world, utterances=r["utterances"], value=round(r["value"], 1),
                                         ms_per_utterance=round(1e3 * r["job_seconds"] / 2, 2), finite=r["finite"])

@@ -32,17 +32,18 @@ def pack_batch(waves, idx, tpad, pin=False):
 
 
 def enhance_sweep(enhance_fn, waves, rank=0, world=1, max_batch=16, device=None, keep_audio=False, references=None,
-                  on_audio=None):
+                  on_audio=None, target_frames=None):
     """Enhance the utterances `waves` (list of 1-D float tensors) this rank owns.
 
     enhance_fn(y [B, L] , lengths [B] int32) -> enhanced [B, L] (e.g. `lambda y, n: model.enhance_batch(y, lengths=n)`).
     references: optional list of clean waveforms (same lengths): adds the per-utterance SI-SDR in dB, computed on the
     device (`ops.si_sdr`; the reference computes it on host numpy arrays per file, B/eval.py:140-144).
+    target_frames: batches of about that many padded frames instead of at most `max_batch` utterances (`shard.bucket_batches`).
     on_audio(i, waveform): optional sink called with every enhanced utterance (host tensor) right after its batch, while
     the following batches are still being enqueued (used by `wavio.enhance_files` to write wavs off the critical path).
     Returns dict(ids, samples, checksum, si_sdr, seconds, batches, audio) for this rank's shard."""
     lengths = [int(w.numel()) for w in waves]
-    batches = batch_shards(lengths, world, max_batch)[rank]
+    batches = batch_shards(lengths, world, max_batch, target_frames=target_frames)[rank]
     ids, samples, checks, sdrs, audio = [], [], [], [], {}
     on_gpu = device is not None and torch.device(device).type == "cuda"
     if on_gpu:       # device timing of the whole shard (host packing gaps included), on the stream the work is launched on

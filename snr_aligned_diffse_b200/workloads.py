@@ -18,6 +18,7 @@ from .sweep import enhance_sweep, gather_metrics
 from .synth import synth_waves
 
 SR = 16000
+SWEEP_TARGET_FRAMES = 16384     # padded frames per batch of the 824-utterance sweep (two bench-shape batches' worth)
 
 
 def synth_wave(length, seed):
@@ -51,13 +52,13 @@ def _max_over_ranks(ms, dev):
     return float(v.item())
 
 
-def run_utterance_sweep(model, waves, dev, rank, world, max_batch=16, graphs=True, repeat=2):
+def run_utterance_sweep(model, waves, dev, rank, world, max_batch=16, graphs=True, repeat=2, target_frames=None):
     """Enhance the list `waves` (sharded over the ranks) `repeat` times; the LAST pass is timed.  Pass 1 builds the
     plans and, with graphs=True, captures one CUDA graph per batch shape (all Tpad buckets are therefore captured before
     the clock of the timed pass starts).  Returns dict(job_seconds, audio_seconds, utterances, batches_rank0, finite)."""
     from .pipeline import GraphedEnhancerCache
     lengths = [int(w.numel()) for w in waves]
-    mine = batch_shards(lengths, world, max_batch)[rank]
+    mine = batch_shards(lengths, world, max_batch, target_frames=target_frames)[rank]
     model.dnn._ensure_device_weights()
     if mine:
         need = max(model.dnn.engine.workspace_bytes(len(idx), 256, tpad) for tpad, idx in mine)
@@ -67,7 +68,7 @@ def run_utterance_sweep(model, waves, dev, rank, world, max_batch=16, graphs=Tru
     res = None
     for _ in range(max(1, repeat)):
         _barrier(dev)
-        res = enhance_sweep(fn, waves, rank=rank, world=world, max_batch=max_batch, device=dev)
+        res = enhance_sweep(fn, waves, rank=rank, world=world, max_batch=max_batch, device=dev, target_frames=target_frames)
     allm = gather_metrics(res, world)
     audio_s = sum(allm["samples"]) / SR
     return dict(job_seconds=allm["job_seconds"], audio_seconds=audio_s, utterances=len(allm["ids"]),
@@ -75,11 +76,11 @@ def run_utterance_sweep(model, waves, dev, rank, world, max_batch=16, graphs=Tru
                 value=audio_s / allm["job_seconds"])
 
 
-def run_sweep824(model, dev, rank, world, count=824, max_batch=16, graphs=True, repeat=2):
+def run_sweep824(model, dev, rank, world, count=824, max_batch=16, graphs=True, repeat=2, target_frames=SWEEP_TARGET_FRAMES):
     lengths = synthetic_lengths(count, seed=0)
     waves = [synth_wave(int(l), seed=i) for i, l in enumerate(lengths)]
-    out = run_utterance_sweep(model, waves, dev, rank, world, max_batch, graphs, repeat)
-    out.update(scaling="strong", fixed_snr=float(model.fixed_snr), max_batch=max_batch,
+    out = run_utterance_sweep(model, waves, dev, rank, world, max_batch, graphs, repeat, target_frames or None)
+    out.update(scaling="strong", fixed_snr=float(model.fixed_snr), max_batch=max_batch, target_frames=target_frames,
                mode=("one CUDA graph per batch shape, all captured in the untimed first pass" if graphs
                      else "eager launches"))
     return out

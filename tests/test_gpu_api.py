@@ -175,10 +175,10 @@ def test_sweep_matches_single_utterance_calls(v3, sd):
         return v3.enhance_batch(y, lengths=n, oracle=True, noise_over_clean=[0.3] * y.shape[0], noise=Z)
 
     merged = {}
-    for world in (1, 2):
+    for world, tf in ((1, None), (2, None), (1, 300), (2, 160)):      # tf: frame-budget batching (larger batches of short utterances)
         for rank in range(world):
-            r = enhance_sweep(fn, waves, rank=rank, world=world, max_batch=3, device="cuda", keep_audio=True,
-                              references=waves)
+            r = enhance_sweep(fn, waves, rank=rank, world=world, max_batch=3 if tf is None else 1, device="cuda", keep_audio=True,
+                              references=waves, target_frames=tf)
             for i, a in r["audio"].items():
                 if i in merged:
                     assert torch.equal(merged[i], a), i          # same bits whatever the sharding

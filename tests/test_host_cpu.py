@@ -201,6 +201,12 @@ def test_sharding_lpt():
     assert sorted(i for _, idx in batches for i in idx) == list(range(824))
     for tpad, idx in batches:
         assert len(idx) <= 16 and all(64 * (-(-(1 + L[i] // 128) // 64)) == tpad for i in idx)
+    # frame-budget batching: still a partition into equal-Tpad batches, short utterances in larger batches (<= 64),
+    # long ones never below max_batch, fewer batches overall
+    big = bucket_batches(L, list(range(824)), max_batch=16, target_frames=16384)
+    assert sorted(i for _, idx in big for i in idx) == list(range(824)) and len(big) < len(batches)
+    for tpad, idx in big:
+        assert len(idx) <= max(16, min(64, 16384 // tpad)) and all(64 * (-(-(1 + L[i] // 128) // 64)) == tpad for i in idx)
     # batch-level sharding (what the sweep uses): a partition into the SAME global batches, full batches stay full,
     # and the modelled job time (slowest rank) beats utterance-level sharding + per-rank batching
     from snr_aligned_diffse_b200.shard import batch_cost, batch_shards

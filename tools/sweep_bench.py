@@ -27,6 +27,8 @@ def main():
     ap.add_argument("--count", type=int, default=0, help="utterances (vbd: total, default 824; long: per rank, default 2)")
     ap.add_argument("--fixed-snr", type=float, default=bench.FIXED_SNR)
     ap.add_argument("--max-batch", type=int, default=16)
+    ap.add_argument("--target-frames", type=int, default=wl.SWEEP_TARGET_FRAMES,
+                    help="vbd: padded frames per batch (0: at most --max-batch utterances per batch)")
     ap.add_argument("--repeat", type=int, default=2, help="passes over the list; the last one is timed")
     ap.add_argument("--enhancers", type=int, default=2, help="pc workload: independent batches in flight per GPU (graph mode)")
     ap.add_argument("--graphs", default="1", help="1: CUDA graphs (default), 0: eager launches, per_step (pc only)")
@@ -47,7 +49,7 @@ def main():
         model, _ = bench.build_models(dev, fixed_snr=args.fixed_snr)
         if args.workload == "vbd":
             out = wl.run_sweep824(model, dev, rank, world, count=args.count or 824, max_batch=args.max_batch,
-                                  graphs=bool(graphs), repeat=args.repeat)
+                                  graphs=bool(graphs), repeat=args.repeat, target_frames=args.target_frames)
         else:
             out = wl.run_longform60(model, dev, rank, world, count=args.count or 2, graphs=bool(graphs), repeat=args.repeat)
     if rank == 0:
