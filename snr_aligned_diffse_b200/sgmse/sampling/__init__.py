@@ -130,10 +130,13 @@ def get_pc_sampler(predictor_name, corrector_name, sde, score_fn, Y, Y_prior=Non
             key = (predictor_name, corrector_name, tuple(Y.shape), int(sde.N), float(sde.T), float(eps), float(snr),
                    int(corrector_steps), bool(probability_flow), type(sde).__name__, graph == "per_step")
             if use_graph is None:
-                # shapes repeat -> capture: the first call of a combination runs the host loop, later calls replay
+                # shapes repeat -> capture: the first call of a combination runs the host loop, later calls replay.
+                # Only with a caller-supplied cache, i.e. through ScoreModel.get_pc_sampler, whose score function is known
+                # to be capturable (no host synchronisation); an arbitrary `score_fn` handed to this module-level factory
+                # keeps the reference's eager loop unless graph=True is asked for.
                 seen = cache.get(("seen",) + key, 0)
                 cache[("seen",) + key] = seen + 1
-                use_graph = seen >= 1
+                use_graph = graph_cache is not None and seen >= 1
             if use_graph:
                 loop = cache.get(key)
                 if loop is None:

@@ -67,38 +67,40 @@ def enhance_sweep(enhance_fn, waves, rank=0, world=1, max_batch=16, device=None,
             tp, ix = batches[nxt]
             ahead.append(pool.submit(pack_batch, waves, ix, tp, on_gpu))
             nxt += 1
-    refill()
-    for tpad, idx in batches:
-        y, lens = ahead.popleft().result()
+    try:
         refill()
-        if device is not None:
-            y, lens = y.to(device, non_blocking=True), lens.to(device, non_blocking=True)
-        out = enhance_fn(y, lens)
-        pos = torch.arange(out.shape[1], device=out.device)[None, :]
-        valid = pos < lens.to(out.device)[:, None].to(pos.dtype)
-        cs = (out.double() * valid).sum(1)            # per-utterance checksum over the valid samples only
-        for r, i in enumerate(idx):
-            ids.append(i)
-            samples.append(lengths[i])
-        checks.append(cs)
-        if references is not None:
-            from . import ops
-            x, _ = pack_batch(references, idx, tpad)
-            sdrs.append(ops.si_sdr(x.to(out.device, non_blocking=True), out, lens.to(out.device)))
-        if keep_audio or on_audio is not None:
-            host = out.detach().to("cpu", non_blocking=False)     # one copy per batch
+        for tpad, idx in batches:
+            y, lens = ahead.popleft().result()
+            refill()
+            if device is not None:
+                y, lens = y.to(device, non_blocking=True), lens.to(device, non_blocking=True)
+            out = enhance_fn(y, lens)
+            pos = torch.arange(out.shape[1], device=out.device)[None, :]
+            valid = pos < lens.to(out.device)[:, None].to(pos.dtype)
+            cs = (out.double() * valid).sum(1)            # per-utterance checksum over the valid samples only
             for r, i in enumerate(idx):
-                a = host[r, :lengths[i]].clone()
-                if keep_audio:
-                    audio[i] = a
-                if on_audio is not None:
-                    on_audio(i, a)
+                ids.append(i)
+                samples.append(lengths[i])
+            checks.append(cs)
+            if references is not None:
+                from . import ops
+                x, _ = pack_batch(references, idx, tpad)
+                sdrs.append(ops.si_sdr(x.to(out.device, non_blocking=True), out, lens.to(out.device)))
+            if keep_audio or on_audio is not None:
+                host = out.detach().to("cpu", non_blocking=False)     # one copy per batch
+                for r, i in enumerate(idx):
+                    a = host[r, :lengths[i]].clone()
+                    if keep_audio:
+                        audio[i] = a
+                    if on_audio is not None:
+                        on_audio(i, a)
+    finally:
+        pool.shutdown(wait=True)
+        torch.set_num_threads(prev_threads)
     if on_gpu:
         ev1.record(torch.cuda.current_stream(device))
         torch.cuda.synchronize(device)
     wall = time.perf_counter() - t0
-    pool.shutdown(wait=True)
-    torch.set_num_threads(prev_threads)
     seconds = ev0.elapsed_time(ev1) * 1e-3 if on_gpu else wall
     checksum = torch.cat(checks).cpu().tolist() if checks else []
     si_sdr = torch.cat(sdrs).cpu().tolist() if sdrs else [float("nan")] * len(ids)
