@@ -33,11 +33,11 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, out_path):
+def _worker(rank, world, port, out_path, target_frames=None):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     waves = _waves()
-    local = enhance_sweep(_fake_enhance, waves, rank=rank, world=world, max_batch=4)
+    local = enhance_sweep(_fake_enhance, waves, rank=rank, world=world, max_batch=4, target_frames=target_frames)
     allm = gather_metrics(local, world)
     if rank == 0:
         torch.save(dict(all=allm, local_ids=local["ids"]), out_path)
@@ -58,12 +58,16 @@ def test_pack_batch_shapes():
         assert torch.equal(y[r, :L[i]], waves[i]) and torch.count_nonzero(y[r, L[i]:]) == 0
 
 
-def test_sweep_world2_gloo_matches_single_rank(tmp_path):
+import pytest  # noqa: E402
+
+
+@pytest.mark.parametrize("target_frames", [None, 640], ids=["max-batch", "frame-budget"])
+def test_sweep_world2_gloo_matches_single_rank(tmp_path, target_frames):
     waves = _waves()
     single = gather_metrics(enhance_sweep(_fake_enhance, waves, rank=0, world=1, max_batch=4), 1)
     assert single["ids"] == list(range(len(waves)))
     out = str(tmp_path / "m.pt")
-    mp.spawn(_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, _free_port(), out, target_frames), nprocs=2, join=True)
     got = torch.load(out)
     other = torch.load(out + ".1")
     # a partition of the utterances over the two ranks
