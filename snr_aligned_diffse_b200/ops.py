@@ -218,7 +218,7 @@ def conv3x3_nhwc_stats(x0, wt, x1=None, bias=None, tbias=None, res=None, scale=1
                                             _lib.ptr(wt), N, _lib.ptr(bias), _lib.ptr(tbias),
                                             0 if tbias is None else tbias.shape[-1], _lib.ptr(res), scale, _lib.ptr(out),
                                             B, H, W, _lib.ptr(ust), _lib.stream_ptr()), "conv3x3_stats")
-    dec = ust.double() * torch.tensor([2.0 ** -30, 2.0 ** -16], dtype=torch.float64, device=x0.device)   # gn_fixed.cuh scales
+    dec = ust.double() * torch.tensor([2.0 ** -30, 2.0 ** -20], dtype=torch.float64, device=x0.device)   # gn_fixed.cuh scales
     return out, dec, ust
 
 
