@@ -326,6 +326,30 @@ def test_groupnorm(ops, C, H, W, silu):
     assert ((got - ref).abs() <= 2 ** -7 * ref.abs() + 2e-3).all()
 
 
+@pytest.mark.parametrize("mag", [2e-3, 1.0, 400.0], ids=["tiny", "unit", "large"])
+def test_groupnorm_statistics_hold_over_the_activation_range(ops, mag):
+    """The 64-bit fixed-point GroupNorm sums (gn_fixed.cuh: 2^-30 / 2^-20) neither lose small activations to rounding
+    nor wrap on large ones: rms 2e-3 (squares ~ eps) .. 400 on a 2 x 128 x 256 x 128 map, both the stand-alone statistics
+    pass and the convolution epilogue's sums, against fp32 group_norm / exact fp64 sums of the stored tensor."""
+    g = torch.Generator().manual_seed(3)
+    C, H, W = 128, 128, 256
+    x = (torch.randn(2, C, H, W, generator=g) * mag + 0.3 * mag).to(torch.bfloat16)
+    gamma, beta = 1 + 0.1 * torch.randn(C, generator=g), 0.1 * torch.randn(C, generator=g)
+    ref = torch.nn.functional.silu(torch.nn.functional.group_norm(x.float(), 32, gamma, beta, eps=1e-6))
+    got = ops.groupnorm_nhwc(_nhwc(x).to(DEV), gamma.to(DEV), beta.to(DEV), silu=True).float().cpu().permute(0, 3, 1, 2)
+    assert ((got - ref).abs() <= 2 ** -7 * ref.abs() + 4e-3).all()
+    # epilogue sums of a convolution whose output has that magnitude (identity-like weights: centre tap only)
+    wt = torch.zeros(C, 9 * C)
+    wt[torch.arange(C), 4 * C + torch.arange(C)] = 1.0
+    out, st, _ = ops.conv3x3_nhwc_stats(_nhwc(x).to(DEV), wt.to(torch.bfloat16).to(DEV))
+    o = out.double().cpu()                                    # [B,H,W,C] as stored
+    want_s = o.reshape(2, H * W, C // 4, 4).sum((1, 3))
+    want_q = (o ** 2).reshape(2, H * W, C // 4, 4).sum((1, 3))
+    st = st.cpu()
+    assert ((st[..., 0] - want_s).abs() <= 1e-5 * want_s.abs() + 1e-3 * mag).all()
+    assert ((st[..., 1] - want_q).abs() <= 1e-5 * want_q).all()
+
+
 def test_fir(ops, golden_dir):
     z = np.load(os.path.join(golden_dir, "fir.npz"))   # reference upfirdn2d_native outputs, fp32
     x = _c(z["x"])                                      # [2,3,6,10] -> use 4-channel fp32 path with a zero channel
