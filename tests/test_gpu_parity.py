@@ -347,7 +347,8 @@ def test_groupnorm_statistics_hold_over_the_activation_range(ops, mag):
     want_q = (o ** 2).reshape(2, H * W, C // 4, 4).sum((1, 3))
     st = st.cpu()
     assert ((st[..., 0] - want_s).abs() <= 1e-5 * want_s.abs() + 1e-3 * mag).all()
-    assert ((st[..., 1] - want_q).abs() <= 1e-5 * want_q).all()
+    # 1024 partials per unit, each rounded to 2^-20: ~1e-5 absolute on the unit total, i.e. 7e-11 on a per-element variance
+    assert ((st[..., 1] - want_q).abs() <= 1e-5 * want_q + 4e-5).all()
 
 
 def test_fir(ops, golden_dir):
