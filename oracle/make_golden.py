@@ -309,6 +309,46 @@ def main():
                         Z=Zp.numpy().astype(np.complex64), ratio=ratio_p, clean_rms=clean_rms, noise_rms=noise_rms,
                         t_index=idx_p, t=float(t_), norm_factor=float(nf), x_hat=xh_p.numpy())
 
+    # ---- (5c) the reference's two training-folder wavs through the ESTIMATOR path (enhance(oracle=False), model.py:713-721):
+    # SNR-branch STFT of y / max|y| -> pad_spec_16 -> the import-time snr_model -> n/s -> t snap -> composed pass as (5).
+    # The noise draw is snr_aligned_diffse_b200.synth.synth_noise(1, Tpad, seed) (stored as the seed, not the tensor).
+    from snr_aligned_diffse_b200.synth import synth_noise
+    extra = {}
+    for tag, path, seed in (("p226_001", "/root/reference/dataset/VBD_SNR-5/train/noisy/p226_001.wav", 226),
+                            ("p286_001", "/root/reference/dataset/VBD_SNR-5/train2/noisy/p286_001.wav", 286)):
+        wf = _wave.open(path, "rb")
+        assert wf.getframerate() == 16000 and wf.getnchannels() == 1 and wf.getsampwidth() == 2
+        pcm_e = np.frombuffer(wf.readframes(wf.getnframes()), dtype="<i2")
+        wf.close()
+        y_e = torch.from_numpy(pcm_e.astype(np.float32) / 32768.0)[None]
+        Le = y_e.shape[1]
+        tpe = 64 * ((1 + Le // 128 + 63) // 64)
+        Ze = synth_noise(1, tpe, seed)
+        y_chk = y_e / y_e.abs().max().item()
+        feat_e = pad_spec_16(torch.view_as_real(torch.stft(y_chk, n_fft=510, hop_length=128, center='True',
+                                                           window=torch.hann_window(510, periodic=True),
+                                                           return_complex=True)).permute(0, 3, 1, 2))
+        with torch.no_grad():
+            est_gt = ref_model.snr_model(feat_e)
+        est_snr_e = est_gt / (1 - est_gt)
+        nf_e = y_e.abs().max().item()
+        t_e = v3.calculate_snr_direct(1, est_snr_e, v3.fixed_snr).detach().cpu().numpy()
+        idx_e = int(np.abs(ref_model.t_30 - t_e).argmin())
+        t_e = ref_model.t_30[idx_e]
+        nf_e = nf_e * v3.calculate_normfac_direct(1, torch.FloatTensor([10 ** 0.25 * v3.fixed_snr * t_e]), v3.fixed_snr)
+        Ye = pad_spec(torch.unsqueeze(v3._forward_transform(v3._stft(y_e / nf_e)), 0))
+        with torch.no_grad():
+            samp_e = v3(Ye + Ze * v3.sigma_max * t_e, (torch.ones(1) * t_e)[:, None, None, None], Ye)
+        xh_e = (v3.to_audio(samp_e.squeeze(), Le) * nf_e).squeeze()
+        ratio_o = float(o_snrnet.estimate_noise_over_clean(snr_sd, y_e)[0, 0])
+        o_e = o_sampler.enhance_v3(sd, y_e, Ze, ratio_o, 0.17783, sigma_max=1.0)
+        report[tag + "_ratio"] = abs(ratio_o - float(est_snr_e))
+        report[tag + "_wave"] = maxabs(o_e["x_hat"], xh_e)
+        assert o_e["t_index"] == idx_e and report[tag + "_wave"] <= 1e-4 * float(xh_e.abs().max()), (tag, report)
+        extra.update({tag + "_y": pcm_e, tag + "_seed": seed, tag + "_ratio": float(est_snr_e), tag + "_t_index": idx_e,
+                      tag + "_t": float(t_e), tag + "_norm_factor": float(nf_e), tag + "_x_hat": xh_e.numpy()})
+    np.savez_compressed(os.path.join(GOLD, "train_wavs.npz"), **extra)
+
     # ---- (6b) BBED scalar functions (sdes.py:275-293) under the reference's pinned-numpy semantics
     from sgmse.sdes import BBED as RefBBED
     rb = RefBBED(0.999, 2.6, 0.52, N=30)

@@ -186,3 +186,26 @@ def test_reference_wav_fixture_p232(v3, golden_dir):
     _row(case="p232_001.wav (reference fixture)", item=0, t_index=int(z["t_index"]), t=float(z["t"]), rel_l2=None,
          si_sdr_db=sdr, maxabs_of_peak=mx)
     assert sdr >= SI_SDR_DB and mx <= MAXABS, (sdr, mx)
+
+
+@pytest.mark.parametrize("tag", ["p226_001", "p286_001"])
+def test_reference_training_wavs_through_the_estimator_path(v3, golden_dir, tag):
+    """The reference's other two wav fixtures (dataset/VBD_SNR-5/train/noisy/p226_001.wav, train2/noisy/p286_001.wav)
+    through `enhance(oracle=False)`: SNR-branch STFT -> SNRNet -> n/s -> t snap -> network, against the unmodified
+    reference's output (tests/golden/train_wavs.npz, oracle/make_golden.py section 5c)."""
+    z = np.load(os.path.join(golden_dir, "train_wavs.npz"))
+    y = torch.from_numpy(z[tag + "_y"].astype(np.float32) / 32768.0)[None]
+    L = y.shape[1]
+    tpad = 64 * ((1 + L // 128 + 63) // 64)
+    Z = synth_noise(1, tpad, int(z[tag + "_seed"]))
+    out, aux = v3.enhance_batch(y, oracle=False, noise=Z, return_aux=True)
+    assert abs(float(aux["ratio"][0]) / float(z[tag + "_ratio"]) - 1) <= 1e-4
+    assert int(aux["t_index"][0]) == int(z[tag + "_t_index"]) and float(aux["t"][0]) == np.float32(z[tag + "_t"])
+    assert abs(float(aux["norm_factor"][0]) / float(z[tag + "_norm_factor"]) - 1) <= 1e-6
+    ref = z[tag + "_x_hat"].astype(np.float64)
+    got = out[0].cpu().numpy().astype(np.float64)
+    sdr = o_sampler.si_sdr(ref, got)
+    mx = float(np.abs(got - ref).max() / np.abs(ref).max())
+    _row(case=f"{tag}.wav (reference fixture, estimator path)", item=0, t_index=int(z[tag + "_t_index"]), t=float(z[tag + "_t"]),
+         rel_l2=None, si_sdr_db=sdr, maxabs_of_peak=mx)
+    assert sdr >= SI_SDR_DB and mx <= MAXABS, (sdr, mx)

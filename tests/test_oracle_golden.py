@@ -143,3 +143,52 @@ def test_upfirdn2d_general_oracle_matches_reference_vectors(golden_dir):
     fz = np.load(os.path.join(golden_dir, "fir.npz"))
     assert (o_ncsnpp.upfirdn2d_general(x, k * 4, 2, 2, 1, 1, 2, 1, 2, 1) - _c(fz["up"])).abs().max() < 1e-6
     assert (o_ncsnpp.upfirdn2d_general(x, k, 1, 1, 2, 2, 1, 1, 1, 1) - _c(fz["down"])).abs().max() < 1e-6
+
+
+# ----------------------------------------------------------------------------------------------- r02 fixtures
+import pytest  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def sd():
+    return synth_state_dict(param_specs(NCSNppConfig()), seed=0)
+
+
+def test_oracle_sampler_variants_match_reference_fixtures(sd, golden_dir):
+    """Langevin corrector loop, Euler-Maruyama step and the BBED loop (T_sampling 0.5) against the unmodified reference's
+    outputs (oracle/make_golden.py sections 6c-6e)."""
+    z = np.load(os.path.join(golden_dir, "pc_langevin.npz"))
+    out, nfe = o_sampler.pc_sample(sd, _c(z["Y"]), o_sampler.OUVE(1.5, 0.05, 0.5, N=2), [n for n in _c(z["noises"])], N=2,
+                                   eps=0.03, snr=0.5, corrector="langevin")
+    assert nfe == int(z["nfe"]) == 4 and (out - _c(z["out"])).abs().max() <= 1e-4 * _c(z["out"]).abs().max()
+    z = np.load(os.path.join(golden_dir, "em_step.npz"))
+    x_new, x_mean = o_sampler.em_step(sd, _c(z["x"]), _c(z["t"]), _c(z["Y"]), o_sampler.OUVE(1.5, 0.05, 0.5, N=30), _c(z["z"]), 30)
+    assert (x_new - _c(z["x_new"])).abs().max() <= 1e-4 * _c(z["x_new"]).abs().max()
+    assert (x_mean - _c(z["x_mean"])).abs().max() <= 1e-4 * _c(z["x_mean"]).abs().max()
+    assert str(z["in_loop"]) == "TypeError"          # what the reference does with this predictor inside pc_sampler
+    z = np.load(os.path.join(golden_dir, "pc_bbed.npz"))
+    out, nfe = o_sampler.pc_sample(sd, _c(z["Y"]), o_sampler.BBED(0.5, 2.6, 0.52, N=2), [n for n in _c(z["noises"])], N=2,
+                                   eps=0.03, snr=0.5)
+    assert nfe == int(z["nfe"]) == 4 and (out - _c(z["out"])).abs().max() <= 1e-4 * _c(z["out"]).abs().max()
+
+
+def test_oracle_matches_reference_on_its_own_wav_fixtures(sd, golden_dir):
+    """dataset/VBD_SNR-5 valid/p232_001.wav with the active_rms.txt oracle ratio, and train/p226_001.wav,
+    train2/p286_001.wav through the estimator path (make_golden.py sections 5b, 5c)."""
+    from oracle.topology import snrnet_param_specs
+    from snr_aligned_diffse_b200.synth import synth_noise, synth_state_dict
+    z = np.load(os.path.join(golden_dir, "p232_001.npz"))
+    y = torch.from_numpy(z["y"].astype(np.float32) / 32768.0)[None]
+    o = o_sampler.enhance_v3(sd, y, _c(z["Z"]), float(z["ratio"]), 0.17783, sigma_max=1.0)
+    assert o["t_index"] == int(z["t_index"]) and abs(o["norm_factor"] - float(z["norm_factor"])) < 1e-7
+    assert (o["x_hat"] - _c(z["x_hat"])).abs().max() <= 1e-4 * np.abs(z["x_hat"]).max()
+    snr_sd = synth_state_dict(snrnet_param_specs(), seed=1)
+    w = np.load(os.path.join(golden_dir, "train_wavs.npz"))
+    for tag in ("p226_001", "p286_001"):
+        y = torch.from_numpy(w[tag + "_y"].astype(np.float32) / 32768.0)[None]
+        ratio = float(o_snrnet.estimate_noise_over_clean(snr_sd, y)[0, 0])
+        assert abs(ratio / float(w[tag + "_ratio"]) - 1) <= 1e-5
+        tpad = 64 * ((1 + y.shape[1] // 128 + 63) // 64)
+        o = o_sampler.enhance_v3(sd, y, synth_noise(1, tpad, int(w[tag + "_seed"])), ratio, 0.17783, sigma_max=1.0)
+        assert o["t_index"] == int(w[tag + "_t_index"])
+        assert (o["x_hat"] - _c(w[tag + "_x_hat"])).abs().max() <= 1e-4 * np.abs(w[tag + "_x_hat"]).max()
