@@ -30,6 +30,13 @@ int snrse_version(void);
 const char* snrse_last_error(void);       /* thread-local message of the last failing call */
 int snrse_device_check(void);             /* 0 iff the current device is compute capability 10.x */
 long long snrse_launch_count(void);       /* kernels launched by this library since it was loaded */
+/* Programmatic dependent launch (griddepcontrol.launch_dependents / .wait in every kernel): `mask` selects the launches that
+ * carry the programmatic-stream-serialization attribute, i.e. may become resident while their predecessor in the stream /
+ * captured graph drains (prologue, TMEM allocation and the weight ring's first loads overlap the predecessor's tail; results
+ * are unchanged).  bit0: the memory-bound / small kernels, bit1: the two tcgen05 convolution kernels.  Read at launch
+ * (== graph capture) time.  Returns the previous mask; mask < 0 only queries.  Default: environment variable SNRSE_PDL when
+ * set, else 2 (measured on the graphed 16 x 4 s step: 0 -> 20.13 ms, 2 -> 20.00 ms, 1 and 3 -> +0.1 ms; profiles/r02_step_ab.md). */
+int snrse_set_pdl(int mask);
 /* Measurement / debug entry points (per-launch-group timing, activation taps, cycle counters) are NOT part of this
  * ABI: they are declared in snrse_b200_debug.h. */
 

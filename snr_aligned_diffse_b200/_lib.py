@@ -21,6 +21,7 @@ PROTOTYPES = {
     "snrse_last_error": (c_char_p, []),
     "snrse_device_check": (i32, []),
     "snrse_launch_count": (ctypes.c_longlong, []),
+    "snrse_set_pdl": (i32, [i32]),
     "snrse_stft": (i32, [vp, vp, vp, i32, vp, i32, i32, i32, i32, f32, f32, i32, vp]),
     "snrse_istft_workspace_bytes": (i64, [i32, i32]),
     "snrse_istft": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, f32, vp]),

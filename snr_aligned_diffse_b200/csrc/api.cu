@@ -1,6 +1,7 @@
 // C-ABI entry points for the stand-alone operators (declared in include/snrse_b200.h).
 // The NCSN++ executor entry points live in engine.cu, the SNR estimator's in snrnet.cu.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <vector>
 
@@ -8,6 +9,11 @@
 
 static thread_local char g_err[512] = "";
 long long g_snrse_launches = 0;
+static int pdl_default() {
+    const char* e = getenv("SNRSE_PDL");
+    return e ? (atoi(e) & 3) : 2;
+}
+int g_snrse_pdl = pdl_default();
 
 void snrse_set_error(const char* fmt, ...) {
     va_list ap;
@@ -29,6 +35,11 @@ extern "C" {
 
 int snrse_version(void) { return 100; }
 long long snrse_launch_count(void) { return g_snrse_launches; }
+int snrse_set_pdl(int on) {
+    const int prev = g_snrse_pdl;
+    if (on >= 0) g_snrse_pdl = on & 3;
+    return prev;
+}
 const char* snrse_last_error(void) { return g_err; }
 
 // 0 when the current device is a Blackwell B200-class GPU (compute capability 10.x); the kernels are sm_100a-only.

@@ -17,6 +17,7 @@ constexpr int TS = 64, TK = 32;
 __global__ void __launch_bounds__(256)
 attn_scores_kernel(const bf16* __restrict__ q, int q_ld, const bf16* __restrict__ k, int k_ld, int n, int C, float scale,
                    float* __restrict__ S) {
+    pdl_sync();
     __shared__ float qs[TS][TK + 1], ks[TS][TK + 1];
     const int b = blockIdx.z, i0 = blockIdx.y * TS, j0 = blockIdx.x * TS;
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
@@ -60,6 +61,7 @@ attn_scores_kernel(const bf16* __restrict__ q, int q_ld, const bf16* __restrict_
 
 __global__ void __launch_bounds__(256)
 attn_softmax_kernel(float* __restrict__ S, int n, int64_t rows) {
+    pdl_sync();
     const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= rows) return;
@@ -81,6 +83,7 @@ attn_softmax_kernel(float* __restrict__ S, int n, int64_t rows) {
 __global__ void __launch_bounds__(256)
 attn_mix_kernel(const float* __restrict__ S, const bf16* __restrict__ v, int v_ld, int n, int C, bf16* __restrict__ o,
                 int o_ld) {
+    pdl_sync();
     __shared__ float ps[TS][TK + 1], vs[TK][TS + 1];
     const int b = blockIdx.z, i0 = blockIdx.y * TS, c0 = blockIdx.x * TS;
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
@@ -126,6 +129,7 @@ attn_mix_kernel(const float* __restrict__ S, const bf16* __restrict__ v, int v_l
 // row softmax of fp32 scores -> bf16 probabilities (one warp per row)
 __global__ void __launch_bounds__(256)
 attn_softmax_bf16_kernel(const float* __restrict__ S, bf16* __restrict__ P, int n, int64_t rows) {
+    pdl_sync();
     const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= rows) return;
@@ -144,6 +148,7 @@ attn_softmax_bf16_kernel(const float* __restrict__ S, bf16* __restrict__ P, int 
 // V [B][n][ld] (C channels) -> V^T [B][C][n], 32x32 tiles through shared memory
 __global__ void __launch_bounds__(256)
 attn_transpose_kernel(const bf16* __restrict__ v, int v_ld, int n, int C, bf16* __restrict__ vt) {
+    pdl_sync();
     __shared__ bf16 t[32][33];
     const int b = blockIdx.z, j0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -195,7 +200,7 @@ int attention_launch(const ActView* q, const ActView* k, const ActView* v, void*
         bf16* probs = reinterpret_cast<bf16*>(static_cast<uint8_t*>(workspace) + nn * 4);
         bf16* vt = reinterpret_cast<bf16*>(reinterpret_cast<uint8_t*>(probs) + ((nn * 2 + 255) / 256) * 256);
         dim3 gt(cdiv(C, 32), cdiv(n, 32), B);
-        attn_transpose_kernel<<<gt, 256, 0, s>>>(v->ptr, v->ld, n, C, vt);
+        snrse_launch(attn_transpose_kernel, dim3(gt), dim3(256), 0, s, v->ptr, v->ld, n, C, vt);
         SNRSE_LAUNCH_CHECK();
         for (int b0 = 0; b0 < B; b0 += pb) {
             for (int q0 = 0; q0 < n; q0 += qc) {
@@ -209,7 +214,7 @@ int attention_launch(const ActView* q, const ActView* k, const ActView* v, void*
                                                  nullptr, nullptr, 0, nullptr, rsqrtf((float)C), scores, n, 1, k->ld));
                 SNRSE_TRY(conv_gemm_launch(&g1, s));
                 const int64_t rows = (int64_t)pb * rows_q;
-                attn_softmax_bf16_kernel<<<(unsigned)cdiv64(rows, 8), 256, 0, s>>>(scores, probs, n, rows);
+                snrse_launch(attn_softmax_bf16_kernel, dim3((unsigned)cdiv64(rows, 8)), dim3(256), 0, s, scores, probs, n, rows);
                 SNRSE_LAUNCH_CHECK();
                 // O = P V : A = P (tokens x keys), B = V^T (C x keys)
                 ActView pa;
@@ -223,13 +228,13 @@ int attention_launch(const ActView* q, const ActView* k, const ActView* v, void*
         return SNRSE_OK;
     }
     dim3 g1(cdiv(n, TS), cdiv(n, TS), B);
-    attn_scores_kernel<<<g1, 256, 0, s>>>(q->ptr, q->ld, k->ptr, k->ld, n, C, rsqrtf((float)C), scores);
+    snrse_launch(attn_scores_kernel, dim3(g1), dim3(256), 0, s, q->ptr, q->ld, k->ptr, k->ld, n, C, rsqrtf((float)C), scores);
     SNRSE_LAUNCH_CHECK();
     const int64_t rows = (int64_t)B * n;
-    attn_softmax_kernel<<<(unsigned)cdiv64(rows, 8), 256, 0, s>>>(scores, n, rows);
+    snrse_launch(attn_softmax_kernel, dim3((unsigned)cdiv64(rows, 8)), dim3(256), 0, s, scores, n, rows);
     SNRSE_LAUNCH_CHECK();
     dim3 g3(cdiv(C, TS), cdiv(n, TS), B);
-    attn_mix_kernel<<<g3, 256, 0, s>>>(scores, v->ptr, v->ld, n, C, o->ptr, o->ld);
+    snrse_launch(attn_mix_kernel, dim3(g3), dim3(256), 0, s, scores, v->ptr, v->ld, n, C, o->ptr, o->ld);
     SNRSE_LAUNCH_CHECK();
     return SNRSE_OK;
 }

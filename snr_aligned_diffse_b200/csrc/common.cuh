@@ -41,6 +41,34 @@ extern long long g_snrse_launches;
         SNRSE_CUDA(cudaGetLastError()); \
     } while (0)
 
+// Launch helper of every kernel in the library.  With g_snrse_pdl != 0 the launch carries the programmatic-stream-
+// serialization attribute (programmatic dependent launch): the grid may become resident while its predecessor in the
+// stream (or captured graph) is still draining, runs its prologue, and blocks in pdl_sync() / griddepcontrol.wait until
+// the predecessor has completed and flushed.  EVERY kernel of the library executes griddepcontrol.wait before its first
+// access to memory another kernel may have written and before its own first global write, so completion stays transitive.
+extern int g_snrse_pdl;
+#ifdef __CUDACC__
+// g_snrse_pdl is a mask: bit0 = the memory-bound / small kernels, bit1 = the two tcgen05 convolution kernels
+template <typename... KArgs, typename... Args>
+static inline void snrse_launch_m(int mask, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = (g_snrse_pdl & mask) ? 1 : 0;
+    (void)cudaLaunchKernelEx(&cfg, kern, static_cast<Args&&>(args)...);   // errors surface in SNRSE_LAUNCH_CHECK (cudaGetLastError)
+}
+template <typename... KArgs, typename... Args>
+static inline void snrse_launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+    snrse_launch_m(1, kern, grid, block, smem, s, static_cast<Args&&>(args)...);
+}
+#endif
+
 #define SNRSE_TRY(call)              \
     do {                             \
         int rc__ = (call);           \
@@ -51,6 +79,13 @@ static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 static inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 #ifdef __CUDACC__
+// Programmatic dependent launch, device side.  pdl_trigger(): the next kernel of the stream may start becoming resident
+// (it still blocks in its own pdl_wait()).  pdl_wait(): the predecessor grid has completed and its writes are visible;
+// a no-op when the launch did not carry the attribute.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_sync() { pdl_trigger(); pdl_wait(); }
+
 // SiLU through ONE special-function op: x*sigmoid(x) = h + h*tanh(h), h = x/2 (tanh.approx.f32, rel. error
 // ~2^-11, below the bf16 rounding of the stored result).  The exp+rcp form needs two SFU ops per element and
 // made the GroupNorm+SiLU pass SFU-bound instead of HBM-bound (16 SFU lanes/clk/SM).

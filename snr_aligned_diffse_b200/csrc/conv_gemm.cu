@@ -54,6 +54,7 @@ struct GemmArgs {
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                  const __grid_constant__ CUtensorMap mapB, const GemmArgs g) {
+    pdl_trigger();   // the next kernel may become resident; it blocks in its own pdl_wait()
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[MAX_STAGES];
     __shared__ __align__(8) uint64_t empty_bar[MAX_STAGES];
@@ -101,6 +102,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_base_smem, 0);
+    // Programmatic dependent launch: barrier init, TMEM allocation and descriptor prefetch above overlap the predecessor's
+    // tail; the weight producer streams its (constant) tiles right away, everyone else waits for the predecessor's data
+    if (!(warp == 6 && !g.b_batched)) pdl_wait();
 
     if (warp == 0) {
         // =========================== TMA producer ===========================
@@ -385,7 +389,7 @@ int conv_gemm_launch(const ConvGemmPlan* p, cudaStream_t s) {
     g.a_box_bytes = p->a_box_bytes;
     g.dbg = g_halo_dbg_shared;
     dim3 grid((unsigned)(p->B * p->tiles_h * p->tiles_w), (unsigned)cdiv(p->N, p->n_tile));
-    conv_gemm_kernel<<<grid, NUM_THREADS, p->smem_bytes, s>>>(p->mapA0, p->mapA1, p->mapB, g);
+    snrse_launch_m(2, conv_gemm_kernel, dim3(grid), dim3(NUM_THREADS), p->smem_bytes, s, p->mapA0, p->mapA1, p->mapB, g);
     SNRSE_LAUNCH_CHECK();
     return SNRSE_OK;
 }

@@ -44,7 +44,7 @@ constexpr int EPI_WARPS = 8;
 // The warp scheduler favours the highest warp id of a sub-partition: the single-lane issue warps sit above the
 // epilogue warps so that their (few) instructions never queue behind epilogue arithmetic.
 constexpr int W_PROD_A = 8, W_PROD_B = 9, W_MMA0 = 10, W_MMA1 = 11;
-constexpr int MAX_A = 3, MAX_B = 8;
+constexpr int MAX_A = 3, MAX_B = 8, MAX_SC = 2;
 constexpr int TW = 8, SUB_ROWS = 16, HALO_W = TW + 2;
 constexpr uint32_t ROW_B = 128;                       // one pixel = 64 bf16 channels = one swizzle row
 
@@ -57,6 +57,7 @@ struct Halo2Args {
     int N;                         // columns per accumulator (128 or 256) == output channels / nsplit
     int nsplit, n_total;           // small maps: the clusters of the upper half of the grid take output channels N..2N-1
     int na, nb;                    // ring depths
+    int nsc;                       // > 0: the 1x1 shortcut operand tiles travel through their own ring of nsc slots
     int acc_bufs;                  // 1 or 2 TMEM accumulator sets
     int stg_bufs;                  // 1 or 2 staging tiles per epilogue warp
     int has_res;
@@ -80,6 +81,10 @@ struct Halo2Args {
 
 __host__ __device__ inline uint32_t halo_stage_bytes(int sub) {   // halo tile rounded up to the 1 KB swizzle atom
     return (((uint32_t)(SUB_ROWS * sub + 2) * HALO_W * ROW_B) + 1023u) & ~1023u;
+}
+
+__host__ __device__ inline uint32_t halo_bsum_bytes(int n_cols) {   // EPI_WARPS slices of max(N/2, 32) floats
+    return (uint32_t)(8 * (n_cols / 2 < 32 ? 32 : n_cols / 2) * 4);
 }
 
 // K-major SWIZZLE_128B descriptor with an explicit 8-row-group stride (bytes); start may be any 128-byte row
@@ -133,10 +138,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(HALO_THREADS + NORM_
 conv_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                   const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapOut,
                   const __grid_constant__ CUtensorMap mapRes, const Halo2Args g) {
+    pdl_trigger();   // the next kernel may become resident; it blocks in its own pdl_wait()
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t a_full[MAX_A], a_empty[MAX_A], a_land[MAX_A], b_full[MAX_B], b_empty[MAX_B];
-    __shared__ __align__(8) uint64_t acc_full[2], acc_empty[2], res_bar[EPI_WARPS];
-    __shared__ __align__(16) float bsum[EPI_WARPS][128];   // per epilogue warp: (bias + time-embedding bias) * scale
+    __shared__ __align__(8) uint64_t acc_full[2], acc_empty[2], res_bar[EPI_WARPS], sc_full[MAX_SC], sc_empty[MAX_SC];
     __shared__ uint32_t tmem_base_smem;
 
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // provably warp-uniform
@@ -153,13 +158,18 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
     const uint32_t a_tx = (uint32_t)(SUB_ROWS * g.sub + 2) * HALO_W * ROW_B;            // bytes one halo TMA box delivers
     const uint32_t a1_tx = (uint32_t)(SUB_ROWS * g.sub) * TW * ROW_B;                   // shortcut operand: no halo
     const uint32_t b_bytes = (uint32_t)(g.N / 2) * ROW_B;   // this CTA's half of the weight tile
-    const uint32_t a_base = smem_base, b_base = smem_base + (uint32_t)g.na * a_bytes;
+    // shared-memory map: halo ring | shortcut ring | weight ring | epilogue staging | per-warp additive terms | GroupNorm table
+    const uint32_t a_base = smem_base, sc_base = a_base + (uint32_t)g.na * a_bytes;
+    const uint32_t sc_bytes = a1_tx;                        // 16 KB per sub-tile: a multiple of the 1 KB swizzle atom
+    const uint32_t b_base = sc_base + (uint32_t)g.nsc * sc_bytes;
     const uint32_t stg_base = b_base + (uint32_t)g.nb * b_bytes;
     const int n_astage = g.c0_chunks + g.c1_chunks;   // halo tiles consumed per super-tile
     const uint32_t acc_cols = (uint32_t)(g.sub * g.N);
     const uint32_t tmem_cols = acc_cols * (uint32_t)g.acc_bufs;  // 128/256/512: power of two
     const bool norm_on = g.scsh != nullptr || g.has_gn;          // GroupNorm + SiLU applied to operand 0 in flight
-    const uint32_t gn_tab = stg_base + (uint32_t)(EPI_WARPS * g.stg_bufs) * 4096u;   // has_gn: scale[512] | shift[512] floats
+    // per epilogue warp: (bias + time-embedding bias) * scale for its N/2 columns
+    const uint32_t bs_base = stg_base + (uint32_t)(EPI_WARPS * g.stg_bufs) * 4096u;
+    const uint32_t gn_tab = bs_base + halo_bsum_bytes(g.N);   // has_gn: scale[512] | shift[512] floats
 
     if (warp == W_MMA1) {
         if (lane == 0) {
@@ -177,6 +187,10 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
                 ptx::mbar_init(ptx::smem_u32(&acc_empty[i]), 2 * EPI_WARPS);   // one arrive per epilogue warp of BOTH CTAs
             }
             for (int i = 0; i < EPI_WARPS; ++i) ptx::mbar_init(ptx::smem_u32(&res_bar[i]), 1);
+            for (int i = 0; i < g.nsc; ++i) {
+                ptx::mbar_init(ptx::smem_u32(&sc_full[i]), 2);                 // one expect-tx arrival per CTA's producer
+                ptx::mbar_init(ptx::smem_u32(&sc_empty[i]), (uint32_t)g.sub);
+            }
             ptx::fence_barrier_init();
         }
         __syncwarp();
@@ -197,6 +211,10 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
     ptx::tc_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_base_smem, 0);
     const int tiles_per_img = g.tiles_h * g.tiles_w;
+    // Programmatic dependent launch: everything above (barriers, TMEM, descriptor prefetch, cluster handshake) overlaps the
+    // predecessor's tail.  The weight producer starts filling its ring at once (weights are constants of the graph); every
+    // other role first waits until the predecessor's activations / statistics / time-embedding biases are visible.
+    if (warp != W_PROD_B) pdl_wait();
 
     if (warp == W_PROD_A) {
         // =========================== A producer: one halo tile per channel chunk ===========================
@@ -207,6 +225,52 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
         long long w_a = 0;
         DBG_T0();
         const uint32_t fb0 = ptx::mapa_rank0(ptx::smem_u32(&a_full[0]));   // leader's barriers (8 B apart)
+        if (g.nsc > 0) {
+            // Two rings, one warp: a cursor per ring walks (tile, chunk) on its own and issues whenever ITS slot is free, so
+            // a full shortcut ring never holds back the next halo tile (and vice versa).  Shortcut tiles go straight to
+            // the leader's barrier (never normalised); halo tiles take the route of the shared ring below.
+            const uint32_t sfb0 = ptx::mapa_rank0(ptx::smem_u32(&sc_full[0]));
+            uint32_t s2 = 0, ph2 = 0;
+            int ct_h = cluster_id, i_h = 0, ct_s = cluster_id, i_s = 0;
+            uint32_t spins = 0;
+            while (ct_h < n_ctiles || ct_s < n_ctiles) {
+                bool progress = false;
+                if (ct_h < n_ctiles && __shfl_sync(0xffffffffu, ptx::mbar_test_wait(ptx::smem_u32(&a_empty[s]), ph ^ 1u), 0)) {
+                    const int tile = 2 * ct_h + (int)rank;
+                    const int b = tile / tiles_per_img, rem = tile % tiles_per_img;   // tile == n_tiles -> b == B: zero fill
+                    const int h0 = (rem / g.tiles_w) * SUB_ROWS * g.sub, w0 = (rem % g.tiles_w) * TW;
+                    const uint32_t dst = a_base + s * a_bytes;
+                    if (elected) {
+                        if (norm_on) {
+                            ptx::mbar_arrive_expect_tx(ptx::smem_u32(&a_land[s]), a_tx);
+                            ptx::tma_load_4d(dst, &mapA0, ptx::smem_u32(&a_land[s]), i_h * 64, w0 - 1, h0 - 1, b);
+                        } else {
+                            ptx::mbar_arrive_expect_tx_remote(fb0 + 8u * s, a_tx);
+                            ptx::tma_load_4d_2sm(dst, &mapA0, fb0 + 8u * s, i_h * 64, w0 - 1, h0 - 1, b);
+                        }
+                    }
+                    __syncwarp();
+                    if (++s == (uint32_t)g.na) { s = 0; ph ^= 1u; }
+                    if (++i_h == g.c0_chunks) { i_h = 0; ct_h += n_clusters; }
+                    progress = true;
+                }
+                if (ct_s < n_ctiles && __shfl_sync(0xffffffffu, ptx::mbar_test_wait(ptx::smem_u32(&sc_empty[s2]), ph2 ^ 1u), 0)) {
+                    const int tile = 2 * ct_s + (int)rank;
+                    const int b = tile / tiles_per_img, rem = tile % tiles_per_img;
+                    const int h0 = (rem / g.tiles_w) * SUB_ROWS * g.sub, w0 = (rem % g.tiles_w) * TW;
+                    if (elected) {
+                        ptx::mbar_arrive_expect_tx_remote(sfb0 + 8u * s2, a1_tx);
+                        ptx::tma_load_4d_2sm(sc_base + s2 * sc_bytes, &mapA1, sfb0 + 8u * s2, i_s * 64, w0, h0, b);
+                    }
+                    __syncwarp();
+                    if (++s2 == (uint32_t)g.nsc) { s2 = 0; ph2 ^= 1u; }
+                    if (++i_s == g.c1_chunks) { i_s = 0; ct_s += n_clusters; }
+                    progress = true;
+                }
+                if (progress) spins = 0;
+                else if (++spins > (1u << 26)) asm volatile("trap;");   // a protocol bug must fault, never hang
+            }
+        } else
         for (int ct = cluster_id; ct < n_ctiles; ct += n_clusters) {
             const int tile = 2 * ct + (int)rank;
             const int b = tile / tiles_per_img, rem = tile % tiles_per_img;   // tile == n_tiles -> b == B: zero fill
@@ -291,7 +355,7 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
         if (rank == 0 && u < g.sub) {
             const uint32_t idesc = ptx::umma_idesc_bf16(256, (uint32_t)g.N);
             const bool elected = ptx::elect_one();
-            uint32_t sa = 0, pha = 0, sb = 0, phb = 0, itt = 0;
+            uint32_t sa = 0, pha = 0, sb = 0, phb = 0, ssc = 0, phsc = 0, itt = 0;
             long long w_a = 0, w_b = 0, w_acc = 0;
             const long long t_start = g.dbg ? clock64() : 0;
             DBG_T0();
@@ -303,10 +367,13 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
                 DBG_ADD(w_acc);
                 const uint32_t d = tmem_base + buf * acc_cols + (uint32_t)(u * g.N);
                 for (int j = 0; j < n_astage; ++j) {
-                    if (g.dbg) t0__ = clock64();
-                    ptx::mbar_wait(ptx::smem_u32(&a_full[sa]), pha);
-                    DBG_ADD(w_a);
                     const bool seg0 = !(g.seq[j] & 0x80);
+                    const bool own_ring = !seg0 && g.nsc > 0;      // shortcut tile from the shortcut ring
+                    if (g.dbg) t0__ = clock64();
+                    if (own_ring) ptx::mbar_wait(ptx::smem_u32(&sc_full[ssc]), phsc);
+                    else ptx::mbar_wait(ptx::smem_u32(&a_full[sa]), pha);
+                    DBG_ADD(w_a);
+                    const uint32_t tile_base = own_ring ? sc_base + ssc * sc_bytes : a_base + sa * a_bytes;
                     const int ntap = seg0 ? 9 : 1;
                     for (int t = 0; t < ntap; ++t) {
                         const uint32_t r = (uint32_t)t / 3u, sft = (uint32_t)t - 3u * r;
@@ -315,7 +382,7 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
                         // 3x3: first pixel row of this sub-tile's tap window in the halo tile, 8-row groups 10 rows apart;
                         // 1x1 shortcut: the bare tile, sub-tile u starts at row 16*8*u, groups 8 rows apart
                         const uint32_t row0 = seg0 ? (r + (uint32_t)(SUB_ROWS * u)) * HALO_W + sft : (uint32_t)(SUB_ROWS * TW * u);
-                        const uint64_t da = umma_desc_rows(a_base + sa * a_bytes + row0 * ROW_B, (seg0 ? HALO_W : TW) * ROW_B);
+                        const uint64_t da = umma_desc_rows(tile_base + row0 * ROW_B, (seg0 ? HALO_W : TW) * ROW_B);
                         if (g.dbg) t0__ = clock64();
                         ptx::mbar_wait(ptx::smem_u32(&b_full[sb]), phb);
                         DBG_ADD(w_b);
@@ -330,8 +397,13 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
                         __syncwarp();
                         if (++sb == (uint32_t)g.nb) { sb = 0; phb ^= 1u; }
                     }
-                    if (elected) ptx::mma_commit_2sm(ptx::smem_u32(&a_empty[sa]));
-                    if (++sa == (uint32_t)g.na) { sa = 0; pha ^= 1u; }
+                    if (own_ring) {
+                        if (elected) ptx::mma_commit_2sm(ptx::smem_u32(&sc_empty[ssc]));
+                        if (++ssc == (uint32_t)g.nsc) { ssc = 0; phsc ^= 1u; }
+                    } else {
+                        if (elected) ptx::mma_commit_2sm(ptx::smem_u32(&a_empty[sa]));
+                        if (++sa == (uint32_t)g.na) { sa = 0; pha ^= 1u; }
+                    }
                 }
                 if (elected) ptx::mma_commit_2sm(ptx::smem_u32(&acc_full[buf]));
                 __syncwarp();
@@ -392,6 +464,7 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
                     tab_b = b;
                 }
                 for (int j = 0; j < n_astage; ++j) {
+                    if ((g.seq[j] & 0x80) && g.nsc > 0) continue;        // shortcut tiles bypass the halo ring
                     const bool live = (b < g.B) && !(g.seq[j] & 0x80);   // the 1x1 shortcut operand is used raw
                     const int chunk = g.seq[j] & 0x7f;
                     // h = x * (scale/2) + shift/2  ==  (x*scale + shift)/2 exactly;  silu(t) = h + h*tanh(h)  (silu_f)
@@ -480,7 +553,7 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
         const uint32_t my_stg = stg_base + (uint32_t)(e * g.stg_bufs) * 4096u;
         const uint32_t my_rbar = ptx::smem_u32(&res_bar[e]);
         const uint32_t row_off = (uint32_t)lane * ROW_B, sw = (uint32_t)(lane & 7);
-        float* bs = bsum[e];
+        float* bs = reinterpret_cast<float*>(smem_raw + (bs_base - ptx::smem_u32(smem_raw))) + e * (half_cols < 32 ? 32 : half_cols);
         uint32_t itt = 0, cnt = 0, rphase = 0;
         int last_b = -1;
         long long w_full = 0, t_body = 0;
@@ -706,7 +779,7 @@ int conv_halo2_make_plan(ConvHaloPlan* p, const ActView* a0, const ActView* a1, 
     // One A slot feeds 9 taps x SUB x 4 MMAs (>= 2300 clk): two slots hide the next tile's load.  With in-flight
     // normalisation the slot also waits for the normalising warps (load + ~2500 clk); at N=128 (64-clock MMAs) that
     // needs a third slot, paid for with single-buffered epilogue staging.
-    int na = 2, stg = 2;
+    int na = 2, stg = 2, nsc = 0;
     if (norm && n_loc == 128 && sub == 2 && !(g_halo2_prefetch & 2)) { na = 3; stg = 1; }   // bit1: A/B measurement of na=2 / stg=2
     int nb = (budget - na * a_bytes - stg * EPI_WARPS * 4096) / b_bytes;
     if (nb < 6 && stg == 2) {
@@ -716,8 +789,22 @@ int conv_halo2_make_plan(ConvHaloPlan* p, const ActView* a0, const ActView* a1, 
     if (nb > MAX_B) nb = MAX_B;
     SNRSE_CHECK_ARG(nb >= 4, "conv_halo2: shared memory budget");
     if (na < MAX_A && (budget - (na + 1) * a_bytes - stg * EPI_WARPS * 4096 - nb * b_bytes) >= 0) ++na;
-    p->na = na; p->nb = nb; p->stg_bufs = stg;
-    p->smem_bytes = na * a_bytes + nb * b_bytes + stg * EPI_WARPS * 4096 + (gn ? 4096 : 0) + 1024;
+    // Fused 1x1 shortcut: its operand tiles (16 KB per sub-tile, one 4-MMA group each) go through a ring of their own and
+    // are interleaved with the 3x3 chunks in the K loop (conv_halo2_launch).  In the shared ring every shortcut stage
+    // (512 clk of MMA work at N = 128) waited a full load latency for its slot: 40-45 % of the MMA warp's time
+    // (profiles/r02_conv_ncu.md).  Two halo slots + two shortcut slots + a shorter weight ring need the whole 227 KB.
+    // Only for the 128-output-channel layers (where N = 128 whatever the batch): the K order then depends on the layer alone,
+    // never on the batch-dependent tiling, so results stay batch-invariant bit for bit.  The 256-channel layers keep the
+    // shared ring: at N = 256 / SUB = 2 two extra slots leave room for only two weight slots.
+    if (a1 && n_rows == 128 && !(g_halo2_prefetch & 8)) {   // bit3: A/B measurement of the shared ring
+        const int sc_bytes = SUB_ROWS * sub * TW * 128;
+        const int limit = 227 * 1024 - 1024 /*alignment*/ - 768 /*static: barriers*/ - (int)halo_bsum_bytes(n_loc) - (gn ? 4096 : 0);
+        const int nb2 = (limit - 2 * a_bytes - MAX_SC * sc_bytes - EPI_WARPS * 4096) / b_bytes;
+        if (nb2 >= 4) { na = 2; nsc = MAX_SC; stg = 1; nb = nb2 > MAX_B ? MAX_B : nb2; }
+    }
+    p->na = na; p->nb = nb; p->stg_bufs = stg; p->nsc = nsc;
+    p->smem_bytes = na * a_bytes + nsc * SUB_ROWS * sub * TW * 128 + nb * b_bytes + stg * EPI_WARPS * 4096 +
+                    (int)halo_bsum_bytes(n_loc) + (gn ? 4096 : 0) + 1024;
     const int n_ctiles = (p->n_tiles + 1) / 2, max_clusters = g_num_sms2 / 2;
     p->grid = nsplit == 2 ? 4 * n_ctiles : 2 * (n_ctiles < max_clusters ? n_ctiles : max_clusters);
     p->bias = bias; p->tbias = tbias; p->tb_stride = tb_stride;
@@ -770,7 +857,7 @@ int conv_halo2_make_plan_out4(ConvHaloPlan* p, const ActView* a0, const bf16* wt
     p->acc_bufs = 2;
     const int a_bytes = (int)halo_stage_bytes(sub);
     p->na = 3; p->nb = MAX_B; p->stg_bufs = 0;   // no epilogue staging: the result leaves from registers
-    p->smem_bytes = p->na * a_bytes + p->nb * 1024 + (gn ? 4096 : 0) + 1024;
+    p->smem_bytes = p->na * a_bytes + p->nb * 1024 + (int)halo_bsum_bytes(16) + (gn ? 4096 : 0) + 1024;
     const int n_ctiles = (p->n_tiles + 1) / 2, max_clusters = g_num_sms2 / 2;
     p->grid = 2 * (n_ctiles < max_clusters ? n_ctiles : max_clusters);
     p->bias = bias4; p->scale = 1.0f;
@@ -787,22 +874,37 @@ int conv_halo2_make_plan_out4(ConvHaloPlan* p, const ActView* a0, const bf16* wt
 int conv_halo2_launch(const ConvHaloPlan* p, cudaStream_t s) {
     static bool attr_set = false;
     if (!attr_set) {
-        SNRSE_CUDA(cudaFuncSetAttribute(conv_halo2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024));
+        cudaFuncAttributes fa;
+        SNRSE_CUDA(cudaFuncGetAttributes(&fa, conv_halo2_kernel));
+        SNRSE_CHECK_ARG(fa.sharedSizeBytes <= 768, "conv_halo2: static shared memory grew past the plan's allowance");
+        SNRSE_CUDA(cudaFuncSetAttribute(conv_halo2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        227 * 1024 - (int)fa.sharedSizeBytes));
         attr_set = true;
     }
     Halo2Args g;
     g.c0_chunks = p->c0_chunks; g.c1_chunks = p->c1_chunks;
-    {   // K-loop order: 3x3 chunks, then the 1x1 shortcut chunks.  (Interleaving the short shortcut chunks between the
-        // long 3x3 chunks was measured and did not help: with two or three A slots the 3x3 tile that follows two
-        // shortcut tiles has only 1024 clk of MMA work to hide its load behind.)
+    {   // K-loop order.  Shared ring: the 3x3 chunks, then the 1x1 shortcut chunks (interleaving them there was measured
+        // and did not help: the 3x3 tile that follows two shortcut tiles has only 1024 clk of MMA work to hide its load
+        // behind).  Separate shortcut ring: the shortcut chunks are spread evenly behind the 3x3 chunks (c s s c s s for
+        // 128 + 256 channels), so a shortcut slot has a whole 3x3 stage to reload.  The packed weights keep their
+        // [taps x 3x3 channels | shortcut channels] K layout either way; the first stage is always a 3x3 chunk.
         int n = 0;
-        for (int i = 0; i < p->c0_chunks; ++i) g.seq[n++] = (unsigned char)i;
-        for (int i = 0; i < p->c1_chunks; ++i) g.seq[n++] = (unsigned char)(0x80 | i);
+        if (p->nsc > 0) {
+            int done = 0;
+            for (int i = 0; i < p->c0_chunks; ++i) {
+                g.seq[n++] = (unsigned char)i;
+                const int upto = (int)((int64_t)(i + 1) * p->c1_chunks / p->c0_chunks);
+                for (; done < upto; ++done) g.seq[n++] = (unsigned char)(0x80 | done);
+            }
+        } else {
+            for (int i = 0; i < p->c0_chunks; ++i) g.seq[n++] = (unsigned char)i;
+            for (int i = 0; i < p->c1_chunks; ++i) g.seq[n++] = (unsigned char)(0x80 | i);
+        }
         for (; n < 16; ++n) g.seq[n] = 0;
     }
     g.H = p->H; g.W = p->W; g.B = p->B;
     g.sub = p->sub; g.tiles_h = p->tiles_h; g.tiles_w = p->tiles_w; g.n_tiles = p->n_tiles;
-    g.N = p->N; g.nsplit = p->nsplit; g.n_total = p->n_total; g.na = p->na; g.nb = p->nb; g.acc_bufs = p->acc_bufs; g.stg_bufs = p->stg_bufs;
+    g.N = p->N; g.nsplit = p->nsplit; g.n_total = p->n_total; g.na = p->na; g.nb = p->nb; g.nsc = p->nsc; g.acc_bufs = p->acc_bufs; g.stg_bufs = p->stg_bufs;
     g.has_res = p->res != nullptr;
     g.prefetch = g_halo2_prefetch & 1;
     g.bias = p->bias; g.tbias = p->tbias; g.tb_stride = p->tb_stride;
@@ -812,7 +914,7 @@ int conv_halo2_launch(const ConvHaloPlan* p, cudaStream_t s) {
     g.ustats = p->ustats;
     g.out4 = reinterpret_cast<float4*>(p->out4); g.addend4 = reinterpret_cast<const float4*>(p->addend4);
     g.dbg = g_halo_dbg_shared;
-    conv_halo2_kernel<<<p->grid, HALO_THREADS + ((p->scsh || p->has_gn) ? NORM_THREADS : 0), p->smem_bytes, s>>>(p->mapA0, p->mapA1, p->mapB, p->mapOut, p->mapRes, g);
+    snrse_launch_m(2, conv_halo2_kernel, dim3(p->grid), dim3(HALO_THREADS + ((p->scsh || p->has_gn) ? NORM_THREADS : 0)), p->smem_bytes, s, p->mapA0, p->mapA1, p->mapB, p->mapOut, p->mapRes, g);
     SNRSE_LAUNCH_CHECK();
     return SNRSE_OK;
 }

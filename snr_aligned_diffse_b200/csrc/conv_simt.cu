@@ -18,6 +18,7 @@ template <int COUT>
 __global__ void __launch_bounds__(128)
 conv_in4_kernel(const float4* __restrict__ x4, const float* __restrict__ w, const float* __restrict__ bias, bf16* out,
                 int H, int W, int ld) {
+    pdl_sync();
     __shared__ __align__(16) float s_w[36][COUT];  // [tap*4 + cin][cout]
     __shared__ float s_b[COUT];
     const int b = blockIdx.z, h0 = blockIdx.y * 8, w0 = blockIdx.x * 32;
@@ -85,6 +86,7 @@ constexpr int CO_TH = 8, CO_TW = 32, CO_CH = 32;
 __global__ void __launch_bounds__(128)
 conv_out4_kernel(const bf16* __restrict__ a, int ld, int C, const float* __restrict__ w, const float* __restrict__ bias,
                  const float4* __restrict__ addend, float4* __restrict__ out, int H, int W) {
+    pdl_sync();
     __shared__ uint32_t s_x[CO_CH / 2][CO_TH + 2][CO_TW + 2];   // bf16 pairs, [c2][row][col]   21.8 KB
     __shared__ __align__(16) float s_w[9][CO_CH][4];             // [tap][c][out]                4.6 KB
     const int b = blockIdx.z, h0 = blockIdx.y * CO_TH, w0 = blockIdx.x * CO_TW;
@@ -157,6 +159,7 @@ constexpr int CB_PIX = 32;   // pixels per thread
 __global__ void __launch_bounds__(256)
 combine4_kernel(const float4* __restrict__ p4, const bf16* __restrict__ h, int h_ld, const float4* __restrict__ w,
                 const float* __restrict__ bias, bf16* out, int out_ld, int C, int64_t npix) {
+    pdl_sync();
     const int tpp = C / 8, slots = blockDim.x / tpp;
     const int c0 = (threadIdx.x % tpp) * 8, slot = threadIdx.x / tpp;
     float wr[8][4], bs[8];
@@ -188,6 +191,7 @@ conv_simt_kernel(const bf16* __restrict__ a0, int ld0, int C0, int taps0, const 
                  const bf16* __restrict__ wt, int N, const float* __restrict__ bias, const float* __restrict__ tbias,
                  int tb_stride, const bf16* __restrict__ res, int res_ld, float scale, bf16* out, int out_ld, int H,
                  int W) {
+    pdl_sync();
     __shared__ float s_a[8][512];
     const int b = blockIdx.z, h = blockIdx.y, w0 = blockIdx.x * 8;
     const int ktot = taps0 * C0 + C1;
@@ -251,7 +255,7 @@ conv_simt_kernel(const bf16* __restrict__ a0, int ld0, int C0, int taps0, const 
 int conv_in4_launch(const float* x4, const float* w, const float* bias, const ActView* out, cudaStream_t s) {
     SNRSE_CHECK_ARG(out->C == 128, "conv_in4: nf must be 128 (got %d)", out->C);
     dim3 grid(cdiv(out->W, 32), cdiv(out->H, 8), out->B);
-    conv_in4_kernel<128><<<grid, 128, 0, s>>>(reinterpret_cast<const float4*>(x4), w, bias, out->ptr, out->H, out->W,
+    snrse_launch(conv_in4_kernel<128>, dim3(grid), dim3(128), 0, s, reinterpret_cast<const float4*>(x4), w, bias, out->ptr, out->H, out->W,
                                               out->ld);
     SNRSE_LAUNCH_CHECK();
     return SNRSE_OK;
@@ -261,7 +265,7 @@ int conv_out4_launch(const ActView* a, const float* w, const float* bias, const 
                      cudaStream_t s) {
     SNRSE_CHECK_ARG(a->C % CO_CH == 0 && a->ld % 8 == 0, "conv_out4: C must be a multiple of %d (got %d)", CO_CH, a->C);
     dim3 grid(cdiv(a->W, CO_TW), cdiv(a->H, CO_TH), a->B);
-    conv_out4_kernel<<<grid, 128, 0, s>>>(a->ptr, a->ld, a->C, w, bias, reinterpret_cast<const float4*>(addend4),
+    snrse_launch(conv_out4_kernel, dim3(grid), dim3(128), 0, s, a->ptr, a->ld, a->C, w, bias, reinterpret_cast<const float4*>(addend4),
                                           reinterpret_cast<float4*>(out4), a->H, a->W);
     SNRSE_LAUNCH_CHECK();
     return SNRSE_OK;
@@ -271,7 +275,7 @@ int combine4_launch(const float* p4, const ActView* h, const float* w, const flo
                     cudaStream_t s) {
     const int64_t npix = (int64_t)h->B * h->H * h->W;
     const int tpp = h->C / 8, nthr = tpp * (256 / tpp), slots = nthr / tpp;
-    combine4_kernel<<<(unsigned)cdiv64(npix, (int64_t)slots * CB_PIX), nthr, 0, s>>>(reinterpret_cast<const float4*>(p4), h->ptr, h->ld,
+    snrse_launch(combine4_kernel, dim3((unsigned)cdiv64(npix, (int64_t)slots * CB_PIX)), dim3(nthr), 0, s, reinterpret_cast<const float4*>(p4), h->ptr, h->ld,
                                                                  reinterpret_cast<const float4*>(w), bias, out->ptr,
                                                                  out->ld, h->C, npix);
     SNRSE_LAUNCH_CHECK();
@@ -283,7 +287,7 @@ int conv_simt_launch(const ActView* a0, int taps0, const ActView* a1, const bf16
                      cudaStream_t s) {
     SNRSE_CHECK_ARG(N <= 256 && a0->C <= 512 && (!a1 || a1->C <= 512), "conv_simt: shape out of range");
     dim3 grid(cdiv(a0->W, 8), a0->H, a0->B);
-    conv_simt_kernel<<<grid, 128, 0, s>>>(a0->ptr, a0->ld, a0->C, taps0, a1 ? a1->ptr : nullptr, a1 ? a1->ld : 0,
+    snrse_launch(conv_simt_kernel, dim3(grid), dim3(128), 0, s, a0->ptr, a0->ld, a0->C, taps0, a1 ? a1->ptr : nullptr, a1 ? a1->ld : 0,
                                           a1 ? a1->C : 0, wt, N, bias, tbias, tb_stride, res ? res->ptr : nullptr,
                                           res ? res->ld : 0, scale, out, out_ld, a0->H, a0->W);
     SNRSE_LAUNCH_CHECK();

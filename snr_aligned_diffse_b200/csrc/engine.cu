@@ -872,6 +872,7 @@ int record_plan(Plan& P) {
 }
 
 __global__ void tap_bf16_kernel(const bf16* __restrict__ x, int ld, int C, int64_t hw, float* __restrict__ out, int64_t total) {
+    pdl_sync();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
     const int64_t p = i % hw;
@@ -881,6 +882,7 @@ __global__ void tap_bf16_kernel(const bf16* __restrict__ x, int ld, int C, int64
     out[i] = __bfloat162float(x[(b * hw + p) * ld + c]);
 }
 __global__ void tap_f32_kernel(const float* __restrict__ x, int C, int64_t hw, float* __restrict__ out, int64_t total) {
+    pdl_sync();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
     const int64_t p = i % hw;
@@ -1093,9 +1095,9 @@ int snrse_ncsnpp_read_tap(void* handle, int B, int F, int T, int module_idx, flo
     const int64_t hw = (int64_t)t.H * t.W;
     if (t.esize == 2) {
         const ActView v = p->view(it->second);
-        tap_bf16_kernel<<<(unsigned)cdiv64(total, 256), 256, 0, s>>>(v.ptr, v.ld, v.C, hw, out, total);
+        snrse_launch(tap_bf16_kernel, dim3((unsigned)cdiv64(total, 256)), dim3(256), 0, s, v.ptr, v.ld, v.C, hw, out, total);
     } else {
-        tap_f32_kernel<<<(unsigned)cdiv64(total, 256), 256, 0, s>>>(p->fptr(it->second), t.C, hw, out, total);
+        snrse_launch(tap_f32_kernel, dim3((unsigned)cdiv64(total, 256)), dim3(256), 0, s, p->fptr(it->second), t.C, hw, out, total);
     }
     SNRSE_LAUNCH_CHECK();
     return SNRSE_OK;

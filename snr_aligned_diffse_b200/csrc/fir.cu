@@ -213,12 +213,14 @@ template <bool NORM>
 __global__ void __launch_bounds__(256)
 fir_down2_kernel(const bf16* __restrict__ x, int ld, int C, int H, int W, bf16* __restrict__ out, int out_ld, int band,
                  const float* __restrict__ scsh) {
+    pdl_sync();
     fir_down2_body<NORM>(x, ld, C, H, W, out, out_ld, band, scsh);
 }
 template <bool NORM>
 __global__ void __launch_bounds__(256)
 fir_up2_kernel(const bf16* __restrict__ x, int ld, int C, int H, int W, bf16* __restrict__ out, int out_ld, int band,
                const float* __restrict__ scsh) {
+    pdl_sync();
     fir_up2_body<NORM>(x, ld, C, H, W, out, out_ld, band, scsh);
 }
 
@@ -232,18 +234,21 @@ fir_up2_kernel(const bf16* __restrict__ x, int ld, int C, int H, int W, bf16* __
 __global__ void __launch_bounds__(256)
 fir_down2_dual_kernel(const bf16* __restrict__ x, int ld, int C, int H, int W, bf16* __restrict__ out_n, int out_n_ld,
                       bf16* __restrict__ out_r, int out_r_ld, int band, const float* __restrict__ scsh) {
+    pdl_sync();
     fir_down2_body<true>(x, ld, C, H, W, out_n, out_n_ld, band, scsh);
     fir_down2_body<false>(x, ld, C, H, W, out_r, out_r_ld, band, nullptr);
 }
 __global__ void __launch_bounds__(256)
 fir_up2_dual_kernel(const bf16* __restrict__ x, int ld, int C, int H, int W, bf16* __restrict__ out_n, int out_n_ld,
                     bf16* __restrict__ out_r, int out_r_ld, int band, const float* __restrict__ scsh) {
+    pdl_sync();
     fir_up2_body<true>(x, ld, C, H, W, out_n, out_n_ld, band, scsh);
     fir_up2_body<false>(x, ld, C, H, W, out_r, out_r_ld, band, nullptr);
 }
 
 __global__ void __launch_bounds__(256)
 fir_down2_f4_kernel(const float4* __restrict__ x, int H, int W, float4* __restrict__ out, int64_t total) {
+    pdl_sync();
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
     const int Ho = H >> 1, Wo = W >> 1;
@@ -275,6 +280,7 @@ fir_down2_f4_kernel(const float4* __restrict__ x, int H, int W, float4* __restri
 
 __global__ void __launch_bounds__(256)
 fir_up2_f4_kernel(const float4* __restrict__ x, int H, int W, float4* __restrict__ out, int64_t total) {
+    pdl_sync();
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
     const int Ho = H * 2, Wo = W * 2;
@@ -318,6 +324,7 @@ __global__ void __launch_bounds__(256)
 upfirdn2d_kernel(const float* __restrict__ x, const float* __restrict__ k, float* __restrict__ out, int in_h, int in_w,
                  int kh, int kw, int up_x, int up_y, int down_x, int down_y, int pad_x0, int pad_y0, int out_h, int out_w,
                  int64_t total) {
+    pdl_sync();
     extern __shared__ float ks[];
     for (int i = threadIdx.x; i < kh * kw; i += blockDim.x) ks[i] = k[i];
     __syncthreads();
@@ -363,7 +370,7 @@ int upfirdn2d_launch(const float* x, const float* kernel, float* out, int64_t ma
     SNRSE_CHECK_ARG(in_h * up_y + pad_y0 + pad_y1 >= kh && in_w * up_x + pad_x0 + pad_x1 >= kw && out_h > 0 && out_w > 0,
                     "upfirdn2d: padded input smaller than the kernel");
     const int64_t total = major * out_h * out_w;
-    upfirdn2d_kernel<<<(unsigned)cdiv64(total, 256), 256, kh * kw * sizeof(float), s>>>(
+    snrse_launch(upfirdn2d_kernel, dim3((unsigned)cdiv64(total, 256)), dim3(256), kh * kw * sizeof(float), s, 
         x, kernel, out, in_h, in_w, kh, kw, up_x, up_y, down_x, down_y, pad_x0, pad_y0, out_h, out_w, total);
     SNRSE_LAUNCH_CHECK();
     return SNRSE_OK;
@@ -377,8 +384,8 @@ int fir_down2_launch(const ActView* x, const ActView* out, cudaStream_t s, const
     int band = FIR_BAND;
     while (band > 1 && (int64_t)cdiv(x->W / 2, cols) * cdiv(x->H / 2, band) * x->B < 592) band >>= 1;
     dim3 grid((unsigned)cdiv(x->W / 2, cols), (unsigned)cdiv(x->H / 2, band), (unsigned)x->B);
-    if (scsh) fir_down2_kernel<true><<<grid, nthr, 0, s>>>(x->ptr, x->ld, x->C, x->H, x->W, out->ptr, out->ld, band, scsh);
-    else fir_down2_kernel<false><<<grid, nthr, 0, s>>>(x->ptr, x->ld, x->C, x->H, x->W, out->ptr, out->ld, band, scsh);
+    if (scsh) snrse_launch(fir_down2_kernel<true>, dim3(grid), dim3(nthr), 0, s, x->ptr, x->ld, x->C, x->H, x->W, out->ptr, out->ld, band, scsh);
+    else snrse_launch(fir_down2_kernel<false>, dim3(grid), dim3(nthr), 0, s, x->ptr, x->ld, x->C, x->H, x->W, out->ptr, out->ld, band, scsh);
     SNRSE_LAUNCH_CHECK();
     return SNRSE_OK;
 }
@@ -390,8 +397,8 @@ int fir_up2_launch(const ActView* x, const ActView* out, cudaStream_t s, const f
     int band = FIR_BAND;
     while (band > 1 && (int64_t)cdiv(x->W, cols) * cdiv(x->H, band) * x->B < 592) band >>= 1;
     dim3 grid((unsigned)cdiv(x->W, cols), (unsigned)cdiv(x->H, band), (unsigned)x->B);
-    if (scsh) fir_up2_kernel<true><<<grid, nthr, 0, s>>>(x->ptr, x->ld, x->C, x->H, x->W, out->ptr, out->ld, band, scsh);
-    else fir_up2_kernel<false><<<grid, nthr, 0, s>>>(x->ptr, x->ld, x->C, x->H, x->W, out->ptr, out->ld, band, scsh);
+    if (scsh) snrse_launch(fir_up2_kernel<true>, dim3(grid), dim3(nthr), 0, s, x->ptr, x->ld, x->C, x->H, x->W, out->ptr, out->ld, band, scsh);
+    else snrse_launch(fir_up2_kernel<false>, dim3(grid), dim3(nthr), 0, s, x->ptr, x->ld, x->C, x->H, x->W, out->ptr, out->ld, band, scsh);
     SNRSE_LAUNCH_CHECK();
     return SNRSE_OK;
 }
@@ -405,8 +412,8 @@ int fir_dual_launch(const ActView* x, const ActView* out_n, const ActView* out_r
     int band = FIR_BAND;
     while (band > 1 && (int64_t)cdiv(wcols, cols) * cdiv(hrows, band) * x->B < 592) band >>= 1;
     dim3 grid((unsigned)cdiv(wcols, cols), (unsigned)cdiv(hrows, band), (unsigned)x->B);
-    if (up) fir_up2_dual_kernel<<<grid, nthr, 0, s>>>(x->ptr, x->ld, x->C, x->H, x->W, out_n->ptr, out_n->ld, out_r->ptr, out_r->ld, band, scsh);
-    else fir_down2_dual_kernel<<<grid, nthr, 0, s>>>(x->ptr, x->ld, x->C, x->H, x->W, out_n->ptr, out_n->ld, out_r->ptr, out_r->ld, band, scsh);
+    if (up) snrse_launch(fir_up2_dual_kernel, dim3(grid), dim3(nthr), 0, s, x->ptr, x->ld, x->C, x->H, x->W, out_n->ptr, out_n->ld, out_r->ptr, out_r->ld, band, scsh);
+    else snrse_launch(fir_down2_dual_kernel, dim3(grid), dim3(nthr), 0, s, x->ptr, x->ld, x->C, x->H, x->W, out_n->ptr, out_n->ld, out_r->ptr, out_r->ld, band, scsh);
     SNRSE_LAUNCH_CHECK();
     return SNRSE_OK;
 }
@@ -414,7 +421,7 @@ int fir_dual_launch(const ActView* x, const ActView* out_n, const ActView* out_r
 int fir_down2_f4_launch(const float* x, float* out, int B, int H, int W, cudaStream_t s) {
     SNRSE_CHECK_ARG(H % 2 == 0 && W % 2 == 0, "fir_down2_f4: H, W must be even");
     const int64_t total = (int64_t)B * (H / 2) * (W / 2);
-    fir_down2_f4_kernel<<<(unsigned)cdiv64(total, 256), 256, 0, s>>>(reinterpret_cast<const float4*>(x), H, W,
+    snrse_launch(fir_down2_f4_kernel, dim3((unsigned)cdiv64(total, 256)), dim3(256), 0, s, reinterpret_cast<const float4*>(x), H, W,
                                                                      reinterpret_cast<float4*>(out), total);
     SNRSE_LAUNCH_CHECK();
     return SNRSE_OK;
@@ -422,7 +429,7 @@ int fir_down2_f4_launch(const float* x, float* out, int B, int H, int W, cudaStr
 
 int fir_up2_f4_launch(const float* x, float* out, int B, int H, int W, cudaStream_t s) {
     const int64_t total = (int64_t)B * (H * 2) * (W * 2);
-    fir_up2_f4_kernel<<<(unsigned)cdiv64(total, 256), 256, 0, s>>>(reinterpret_cast<const float4*>(x), H, W,
+    snrse_launch(fir_up2_f4_kernel, dim3((unsigned)cdiv64(total, 256)), dim3(256), 0, s, reinterpret_cast<const float4*>(x), H, W,
                                                                    reinterpret_cast<float4*>(out), total);
     SNRSE_LAUNCH_CHECK();
     return SNRSE_OK;

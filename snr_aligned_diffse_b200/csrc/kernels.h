@@ -68,6 +68,7 @@ struct ConvHaloPlan {
     CUtensorMap mapA0, mapA1, mapB, mapOut, mapRes;   // mapOut / mapRes: 2-CTA kernel only (TMA epilogue)
     int c0_chunks, c1_chunks, B, H, W, sub, tiles_h, tiles_w, n_tiles, N, na, nb, acc_bufs, stg_bufs, grid, smem_bytes;
     int nsplit, n_total;   // 2-CTA kernel: N = n_total / nsplit output channels per cluster (nsplit 2 on small maps)
+    int nsc;               // 2-CTA kernel: slots of the separate ring for the 1x1 shortcut operand (0: it shares the halo ring)
     const float* bias;
     const float* tbias;
     int tb_stride;

@@ -24,6 +24,7 @@ constexpr int GN_MAX_CHUNKS = 128;
 __global__ void __launch_bounds__(256)
 gn_stats_kernel(const bf16* __restrict__ x, int ld, int C, int64_t hw, int pix_per_chunk,
                 unsigned long long* __restrict__ ustats) {
+    pdl_sync();
     const int tpp = C >> 3;
     const int ppb = blockDim.x / tpp;
     const int vec = threadIdx.x % tpp, prow = threadIdx.x / tpp;
@@ -85,6 +86,7 @@ __global__ void __launch_bounds__(256)
 gn_finalize_kernel(const unsigned long long* __restrict__ src0, int U0, const unsigned long long* __restrict__ src1, int U1,
                    double inv_count, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                    float* __restrict__ scsh) {
+    pdl_sync();
     __shared__ float s_mean[GN_GROUPS], s_rstd[GN_GROUPS];
     const int b = blockIdx.x;
     const int U = U0 + U1, C = 4 * U;
@@ -117,6 +119,7 @@ gn_finalize_kernel(const unsigned long long* __restrict__ src0, int U0, const un
 __global__ void __launch_bounds__(256)
 gn_apply_kernel(const bf16* __restrict__ x, int ld, int C, int64_t hw, const float* __restrict__ scsh, int silu,
                 bf16* __restrict__ out, int out_ld, int pix_per_block) {
+    pdl_sync();
     const int tpp = C >> 3;
     const int ppb = blockDim.x / tpp;
     const int vec = threadIdx.x % tpp, prow = threadIdx.x / tpp;
@@ -174,7 +177,7 @@ int gn_stats_launch(const ActView* x, unsigned long long* ustats, cudaStream_t s
     // the chunking depends on the image size only: a sample's statistics do not depend on its batch
     const int ppc = (int)cdiv64(hw, chunks);
     dim3 grid(chunks, x->B);
-    gn_stats_kernel<<<grid, gn_threads(x->C), 0, s>>>(x->ptr, x->ld, x->C, hw, ppc, ustats);
+    snrse_launch(gn_stats_kernel, dim3(grid), dim3(gn_threads(x->C)), 0, s, x->ptr, x->ld, x->C, hw, ppc, ustats);
     SNRSE_LAUNCH_CHECK();
     return SNRSE_OK;
 }
@@ -184,7 +187,7 @@ int gn_finalize_launch(const unsigned long long* src0, int U0, const unsigned lo
                        cudaStream_t s) {
     const int C = 4 * (U0 + U1);
     SNRSE_CHECK_ARG(C % 128 == 0 && C <= 512 && src0 && (U1 == 0 || src1), "GroupNorm finalize: bad sources");
-    gn_finalize_kernel<<<B, 256, 0, s>>>(src0, U0, src1, U1, 1.0 / (double)count_per_group, gamma, beta, eps, scsh);
+    snrse_launch(gn_finalize_kernel, dim3(B), dim3(256), 0, s, src0, U0, src1, U1, 1.0 / (double)count_per_group, gamma, beta, eps, scsh);
     SNRSE_LAUNCH_CHECK();
     return SNRSE_OK;
 }
@@ -198,7 +201,7 @@ int gn_apply_launch(const ActView* x, const float* scsh, int silu, const ActView
     if (blocks_per_img < 1) blocks_per_img = 1;
     const int pix_per_block = (int)cdiv64(hw, blocks_per_img);
     dim3 grid((unsigned)blocks_per_img, x->B);
-    gn_apply_kernel<<<grid, nthr, 0, s>>>(x->ptr, x->ld, x->C, hw, scsh, silu, out->ptr, out->ld, pix_per_block);
+    snrse_launch(gn_apply_kernel, dim3(grid), dim3(nthr), 0, s, x->ptr, x->ld, x->C, hw, scsh, silu, out->ptr, out->ld, pix_per_block);
     SNRSE_LAUNCH_CHECK();
     return SNRSE_OK;
 }

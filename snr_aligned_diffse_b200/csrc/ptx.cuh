@@ -34,6 +34,19 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
         : "memory");
     return done;
 }
+// Non-blocking probe (try_wait may suspend the warp for an implementation-defined time; a loop that polls two barriers
+// in turn must not)
+__device__ __forceinline__ uint32_t mbar_test_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return done;
+}
 // Bounded wait: a protocol bug must fault the launch (trap -> cudaErrorLaunchFailure), never hang the GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins) {

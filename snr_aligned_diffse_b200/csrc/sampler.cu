@@ -13,6 +13,7 @@ namespace {
 
 __global__ void __launch_bounds__(256)
 pack_input_kernel(const float2* __restrict__ x, const float2* __restrict__ y, float4* __restrict__ x4, int64_t total) {
+    pdl_sync();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
     const float2 a = x[i], b = y[i];
@@ -25,6 +26,7 @@ pack_input_kernel(const float2* __restrict__ x, const float2* __restrict__ y, fl
 __global__ void __launch_bounds__(256)
 pack_input64_kernel(const float2* __restrict__ x, const float2* __restrict__ y, float4* __restrict__ x4,
                     uint4* __restrict__ x64, int64_t total) {
+    pdl_sync();
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t i = idx >> 3;
     if (i >= total) return;
@@ -50,6 +52,7 @@ __global__ void __launch_bounds__(256)
 final_kernel(const float4* __restrict__ p4, const float* __restrict__ t, const float* __restrict__ w,
              const float* __restrict__ bias, const float2* __restrict__ xres, float2* __restrict__ out, int64_t n,
              int mode) {
+    pdl_sync();
     const int b = blockIdx.y;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -76,6 +79,7 @@ __global__ void __launch_bounds__(256)
 lincomb_kernel(const float2* __restrict__ x, const float2* __restrict__ y, const float2* __restrict__ sc,
                const float2* __restrict__ z, const float* __restrict__ a, const float* __restrict__ bq,
                const float* __restrict__ c, const float* __restrict__ d, float2* out_mean, float2* out_x, int64_t n) {
+    pdl_sync();
     const int b = blockIdx.y;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -95,6 +99,7 @@ lincomb_kernel(const float2* __restrict__ x, const float2* __restrict__ y, const
 __global__ void v3_scalars_kernel(const float* __restrict__ ratio, const float* __restrict__ peak, double snr_scale,
                                   float nf_const, const double* __restrict__ t30, float* __restrict__ t_out,
                                   float* __restrict__ nf_out, int* __restrict__ idx_out, int B) {
+    pdl_sync();
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     const float t_raw = ratio[b] / (float)snr_scale;
@@ -116,6 +121,7 @@ __global__ void v3_scalars_kernel(const float* __restrict__ ratio, const float* 
 }
 
 __global__ void snr_ratio_kernel(const float* __restrict__ g, float* __restrict__ ratio, int B) {
+    pdl_sync();
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b < B) ratio[b] = g[b] / (1.0f - g[b]);
 }
@@ -130,6 +136,7 @@ struct RKCoef {
 __global__ void __launch_bounds__(256)
 rk_combine_kernel(const float2* __restrict__ y, const float2* __restrict__ K, int nk, float h, RKCoef c,
                   float2* __restrict__ out, int64_t n) {
+    pdl_sync();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float re = 0.f, im = 0.f;
@@ -149,6 +156,7 @@ rk_combine_kernel(const float2* __restrict__ y, const float2* __restrict__ K, in
 __global__ void __launch_bounds__(256)
 rk_scaled_sqnorm_kernel(const float2* __restrict__ K, int nk, float h, RKCoef c, const float2* __restrict__ y,
                         const float2* __restrict__ y2, float atol, float rtol, double* __restrict__ partial, int64_t n) {
+    pdl_sync();
     __shared__ double sm[8];
     double acc = 0.0;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -185,7 +193,7 @@ int rk_combine_launch(const float2* y, const float2* K, int nk, int64_t n, float
     SNRSE_CHECK_ARG(K && out && coef && nk >= 1 && nk <= 8 && n > 0, "rk_combine: bad arguments (1..8 stages)");
     RKCoef c;
     for (int j = 0; j < 8; ++j) c.v[j] = j < nk ? coef[j] : 0.f;
-    rk_combine_kernel<<<(unsigned)cdiv64(n, 256), 256, 0, s>>>(y, K, nk, h, c, out, n);
+    snrse_launch(rk_combine_kernel, dim3((unsigned)cdiv64(n, 256)), dim3(256), 0, s, y, K, nk, h, c, out, n);
     SNRSE_LAUNCH_CHECK();
     return SNRSE_OK;
 }
@@ -197,7 +205,7 @@ int rk_scaled_sqnorm_launch(const float2* K, int nk, int64_t n, float h, const f
     SNRSE_CHECK_ARG(K && y && coef && partial && nk >= 1 && nk <= 8 && n > 0, "rk_scaled_sqnorm: bad arguments");
     RKCoef c;
     for (int j = 0; j < 8; ++j) c.v[j] = j < nk ? coef[j] : 0.f;
-    rk_scaled_sqnorm_kernel<<<rk_partials(n), 256, 0, s>>>(K, nk, h, c, y, y2, atol, rtol, partial, n);
+    snrse_launch(rk_scaled_sqnorm_kernel, dim3(rk_partials(n)), dim3(256), 0, s, K, nk, h, c, y, y2, atol, rtol, partial, n);
     SNRSE_LAUNCH_CHECK();
     return SNRSE_OK;
 }
@@ -205,27 +213,27 @@ int rk_scaled_sqnorm_launch(const float2* K, int nk, int64_t n, float h, const f
 
 int v3_scalars_launch(const float* ratio, const float* peak, double snr_scale, float nf_const, const double* t30,
                       float* t_out, float* nf_out, int* idx_out, int B, cudaStream_t s) {
-    v3_scalars_kernel<<<cdiv(B, 128), 128, 0, s>>>(ratio, peak, snr_scale, nf_const, t30, t_out, nf_out, idx_out, B);
+    snrse_launch(v3_scalars_kernel, dim3(cdiv(B, 128)), dim3(128), 0, s, ratio, peak, snr_scale, nf_const, t30, t_out, nf_out, idx_out, B);
     SNRSE_LAUNCH_CHECK();
     return SNRSE_OK;
 }
 
 int snr_ratio_launch(const float* g, float* ratio, int B, cudaStream_t s) {
-    snr_ratio_kernel<<<cdiv(B, 128), 128, 0, s>>>(g, ratio, B);
+    snrse_launch(snr_ratio_kernel, dim3(cdiv(B, 128)), dim3(128), 0, s, g, ratio, B);
     SNRSE_LAUNCH_CHECK();
     return SNRSE_OK;
 }
 
 int pack_input_launch(const float2* x, const float2* y, float* x4, int B, int64_t n, cudaStream_t s) {
     const int64_t total = (int64_t)B * n;
-    pack_input_kernel<<<(unsigned)cdiv64(total, 256), 256, 0, s>>>(x, y, reinterpret_cast<float4*>(x4), total);
+    snrse_launch(pack_input_kernel, dim3((unsigned)cdiv64(total, 256)), dim3(256), 0, s, x, y, reinterpret_cast<float4*>(x4), total);
     SNRSE_LAUNCH_CHECK();
     return SNRSE_OK;
 }
 
 int pack_input64_launch(const float2* x, const float2* y, float* x4, bf16* x64, int B, int64_t n, cudaStream_t s) {
     const int64_t total = (int64_t)B * n;
-    pack_input64_kernel<<<(unsigned)cdiv64(total * 8, 256), 256, 0, s>>>(x, y, reinterpret_cast<float4*>(x4),
+    snrse_launch(pack_input64_kernel, dim3((unsigned)cdiv64(total * 8, 256)), dim3(256), 0, s, x, y, reinterpret_cast<float4*>(x4),
                                                                         reinterpret_cast<uint4*>(x64), total);
     SNRSE_LAUNCH_CHECK();
     return SNRSE_OK;
@@ -236,7 +244,7 @@ int final_launch(const float* p4, const float* t, const float* w, const float* b
     SNRSE_CHECK_ARG(mode >= 0 && mode <= 2, "final: bad mode %d", mode);
     SNRSE_CHECK_ARG(mode != 1 || xres, "final: mode 1 needs the residual state");
     dim3 grid((unsigned)cdiv64(n, 256), B);
-    final_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const float4*>(p4), t, w, bias, xres, out, n, mode);
+    snrse_launch(final_kernel, dim3(grid), dim3(256), 0, s, reinterpret_cast<const float4*>(p4), t, w, bias, xres, out, n, mode);
     SNRSE_LAUNCH_CHECK();
     return SNRSE_OK;
 }
@@ -244,7 +252,7 @@ int final_launch(const float* p4, const float* t, const float* w, const float* b
 int lincomb_launch(const float2* x, const float2* y, const float2* sc, const float2* z, const float* a, const float* b,
                    const float* c, const float* d, float2* out_mean, float2* out_x, int B, int64_t n, cudaStream_t s) {
     dim3 grid((unsigned)cdiv64(n, 256), B);
-    lincomb_kernel<<<grid, 256, 0, s>>>(x, y, sc, z, a, b, c, d, out_mean, out_x, n);
+    snrse_launch(lincomb_kernel, dim3(grid), dim3(256), 0, s, x, y, sc, z, a, b, c, d, out_mean, out_x, n);
     SNRSE_LAUNCH_CHECK();
     return SNRSE_OK;
 }

@@ -40,6 +40,7 @@ const float* P(const void* blob, int i) { return reinterpret_cast<const float*>(
 __global__ void __launch_bounds__(256)
 snr_conv5_pool_kernel(const float* __restrict__ feat, const float* __restrict__ w, const float* __restrict__ bias,
                       float* __restrict__ a1, int T16) {
+    pdl_sync();
     __shared__ float sw[32 * 50];
     __shared__ float sx[2][20][20];  // input patch: 16 freq rows (+4 halo) x 16 frames (+4 halo)
     const int nc = blockIdx.y, clusters = T16 / 16;
@@ -84,6 +85,7 @@ constexpr int C3_ROWS = 16;
 __global__ void __launch_bounds__(256)
 snr_conv3_pool_kernel(const float* __restrict__ a1, const float* __restrict__ w, const float* __restrict__ bias,
                       float* __restrict__ a2) {
+    pdl_sync();
     extern __shared__ __align__(16) float sm3[];
     float* sw = sm3;                       // [ci][k][co]   32*9*32 floats = 36 KB
     float* sx = sm3 + 32 * 9 * 32;         // [ci][18][10]  23 KB
@@ -191,6 +193,7 @@ __device__ __forceinline__ void snr_convt_body(const float* __restrict__ a2, con
 
 __global__ void __launch_bounds__(256)
 snr_convt_kernel(const float* __restrict__ a2, ConvtW cw, float* __restrict__ feats, int64_t ncl) {
+    pdl_sync();
     __shared__ __align__(16) float sx[8][32][8];     // [cluster][r][frame]      8 KB
     __shared__ __align__(16) float sw[32 * 8 * 32];  // [r][dt][co]           <= 32 KB
     const int ki = blockIdx.y;                       // weights packed [r (2048)][dt (k)][co (32)]
@@ -206,6 +209,7 @@ __global__ void __launch_bounds__(256)
 snr_lstm_pre_kernel(const float* __restrict__ feats, const float* __restrict__ wih0, const float* __restrict__ bih0,
                     const float* __restrict__ bhh0, const float* __restrict__ wih1, const float* __restrict__ bih1,
                     const float* __restrict__ bhh1, float* __restrict__ pre, int64_t rows) {
+    pdl_sync();
     __shared__ float sx[8][128];
     const int64_t row0 = (int64_t)blockIdx.x * 8;
     for (int i = threadIdx.x; i < 8 * 128; i += 256) {
@@ -241,6 +245,7 @@ snr_lstm_pre_kernel(const float* __restrict__ feats, const float* __restrict__ w
 __global__ void __launch_bounds__(512, 1)
 snr_lstm_rec_kernel(const float* __restrict__ pre, const float* __restrict__ whh0, const float* __restrict__ whh1,
                     float* __restrict__ hout, int S, int64_t rows) {
+    pdl_sync();
     extern __shared__ float sm[];
     float* sw = sm;                  // [64][512]  second half of every W_hh row, transposed
     float* sh = sm + 64 * 512;       // [128] h
@@ -281,6 +286,7 @@ snr_lstm_rec_kernel(const float* __restrict__ pre, const float* __restrict__ whh
 __global__ void __launch_bounds__(256)
 snr_head_kernel(const float* __restrict__ hout, const float* __restrict__ fcw, const float* __restrict__ fcb,
                 float* __restrict__ out, int S) {
+    pdl_sync();
     __shared__ float red[8];
     const int b = blockIdx.x, j = threadIdx.x;
     float sum = 0.f, mn = INFINITY, mx = -INFINITY;
@@ -362,9 +368,9 @@ int snrse_snrnet_forward(const void* weights, const float* feat, float* out, int
                                         (64 * 512 + 128 + 512) * 4));
         attr_set = true;
     }
-    snr_conv5_pool_kernel<<<dim3(16, (unsigned)nc), 256, 0, s>>>(feat, P(weights, 0), P(weights, 1), a1, T16);
+    snrse_launch(snr_conv5_pool_kernel, dim3(dim3(16, (unsigned)nc)), dim3(256), 0, s, feat, P(weights, 0), P(weights, 1), a1, T16);
     SNRSE_LAUNCH_CHECK();
-    snr_conv3_pool_kernel<<<dim3(128 / C3_ROWS, (unsigned)nc), 256, (32 * 9 * 32 + 32 * 18 * 10) * 4, s>>>(
+    snrse_launch(snr_conv3_pool_kernel, dim3(dim3(128 / C3_ROWS, (unsigned)nc)), dim3(256), (32 * 9 * 32 + 32 * 18 * 10) * 4, s, 
         a1, P(weights, 2), P(weights, 3), a2);
     SNRSE_LAUNCH_CHECK();
     ConvtW cw;
@@ -372,14 +378,14 @@ int snrse_snrnet_forward(const void* weights, const float* feat, float* out, int
         cw.w[i] = P(weights, 4 + 2 * i);
         cw.b[i] = P(weights, 5 + 2 * i);
     }
-    snr_convt_kernel<<<dim3((unsigned)cdiv64(nc, 8), 4), 256, 0, s>>>(a2, cw, feats, nc);
+    snrse_launch(snr_convt_kernel, dim3(dim3((unsigned)cdiv64(nc, 8), 4)), dim3(256), 0, s, a2, cw, feats, nc);
     SNRSE_LAUNCH_CHECK();
-    snr_lstm_pre_kernel<<<(unsigned)cdiv64(nc, 8), 256, 0, s>>>(feats, P(weights, 12), P(weights, 14), P(weights, 15), P(weights, 16),
+    snrse_launch(snr_lstm_pre_kernel, dim3((unsigned)cdiv64(nc, 8)), dim3(256), 0, s, feats, P(weights, 12), P(weights, 14), P(weights, 15), P(weights, 16),
                                                      P(weights, 18), P(weights, 19), pre, nc);
     SNRSE_LAUNCH_CHECK();
-    snr_lstm_rec_kernel<<<dim3(B, 2), 512, (64 * 512 + 128 + 512) * 4, s>>>(pre, P(weights, 13), P(weights, 17), hout, S, nc);
+    snrse_launch(snr_lstm_rec_kernel, dim3(dim3(B, 2)), dim3(512), (64 * 512 + 128 + 512) * 4, s, pre, P(weights, 13), P(weights, 17), hout, S, nc);
     SNRSE_LAUNCH_CHECK();
-    snr_head_kernel<<<B, 256, 0, s>>>(hout, P(weights, 20), P(weights, 21), out, S);
+    snrse_launch(snr_head_kernel, dim3(B), dim3(256), 0, s, hout, P(weights, 20), P(weights, 21), out, S);
     SNRSE_LAUNCH_CHECK();
     return SNRSE_OK;
 }

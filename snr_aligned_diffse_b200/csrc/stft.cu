@@ -150,6 +150,7 @@ __global__ void __launch_bounds__(256)
 stft_kernel(const float* __restrict__ wave, const int* __restrict__ len, const float* __restrict__ scale,
             int scale_is_divisor, float* __restrict__ out, int lstride, int tpad, int transform, float alpha,
             float beta, int planar, int npass) {
+    pdl_sync();
     __shared__ __align__(16) float2 X[FT * FS];
     __shared__ __align__(16) float xs[SPAN + 2];
     const int b = blockIdx.y, tid = threadIdx.x;
@@ -265,6 +266,7 @@ constexpr int ISTFT_SMEM = (FT * FS + FT * TS) * 8 + OLA_SPAN * 4 + NFFT * 4 + 6
 __global__ void __launch_bounds__(256)
 istft_kernel(const float2* __restrict__ spec, const int* __restrict__ len, const float* __restrict__ scale,
              float* __restrict__ wave, int lstride, int tpad, int transform, float alpha, float beta) {
+    pdl_sync();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* X = reinterpret_cast<float2*>(smem_raw);                 // transform buffer [FT][FS]
     float2* T = X + FT * FS;                                          // spectrogram tile [FT][TS], later frames [FT][512 floats]
@@ -381,6 +383,7 @@ istft_kernel(const float2* __restrict__ spec, const int* __restrict__ len, const
 constexpr int ABSMAX_CHUNK = 8192;
 __global__ void __launch_bounds__(256)
 absmax_kernel(const float* __restrict__ wave, const int* __restrict__ len, int lstride, float* __restrict__ out) {
+    pdl_sync();
     __shared__ float sm[8];
     const int b = blockIdx.y;
     const int L = len ? len[b] : lstride;
@@ -402,6 +405,7 @@ absmax_kernel(const float* __restrict__ wave, const int* __restrict__ len, int l
 __global__ void __launch_bounds__(256)
 spec_transform_kernel(const float2* __restrict__ in, float2* __restrict__ out, int64_t n, int inverse, int transform,
                       float alpha, float beta) {
+    pdl_sync();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float2 z = in[i];
@@ -437,6 +441,7 @@ __device__ __forceinline__ double block_sum_256(double v, double* sm) {
 __global__ void __launch_bounds__(256)
 si_sdr_kernel(const float* __restrict__ ref, const float* __restrict__ est, const int* __restrict__ len, int lstride,
               double* __restrict__ out) {
+    pdl_sync();
     __shared__ double sm[8];
     const int b = blockIdx.x;
     const int L = len ? len[b] : lstride;
@@ -466,7 +471,7 @@ si_sdr_kernel(const float* __restrict__ ref, const float* __restrict__ est, cons
 
 int si_sdr_launch(const float* ref, const float* est, const int* len, int B, int lstride, double* out, cudaStream_t s) {
     SNRSE_CHECK_ARG(ref && est && out && B > 0 && lstride > 0, "si_sdr: bad arguments");
-    si_sdr_kernel<<<B, 256, 0, s>>>(ref, est, len, lstride, out);
+    snrse_launch(si_sdr_kernel, dim3(B), dim3(256), 0, s, ref, est, len, lstride, out);
     SNRSE_LAUNCH_CHECK();
     return SNRSE_OK;
 }
@@ -475,7 +480,7 @@ int si_sdr_launch(const float* ref, const float* est, const int* len, int B, int
 int spec_transform_launch(const float2* in, float2* out, int64_t n, int inverse, int transform, float alpha, float beta,
                           cudaStream_t s) {
     SNRSE_CHECK_ARG(transform == 1 || transform == 2, "spec_transform: transform must be 1 (exponent) or 2 (log)");
-    spec_transform_kernel<<<(unsigned)cdiv64(n, 256), 256, 0, s>>>(in, out, n, inverse, transform, alpha, beta);
+    snrse_launch(spec_transform_kernel, dim3((unsigned)cdiv64(n, 256)), dim3(256), 0, s, in, out, n, inverse, transform, alpha, beta);
     SNRSE_LAUNCH_CHECK();
     return SNRSE_OK;
 }
@@ -489,7 +494,7 @@ int stft_launch(const float* wave, const int* len, const float* scale, int scale
     // load / barrier latency, not by those constants -- and a longer critical path on small problems.)
     const int npass = 1;
     dim3 grid(cdiv(tpad, FT * npass), B);
-    stft_kernel<<<grid, 256, 0, s>>>(wave, len, scale, scale_is_divisor, out, lstride, tpad, transform, alpha, beta, planar,
+    snrse_launch(stft_kernel, dim3(grid), dim3(256), 0, s, wave, len, scale, scale_is_divisor, out, lstride, tpad, transform, alpha, beta, planar,
                                      npass);
     SNRSE_LAUNCH_CHECK();
     return SNRSE_OK;
@@ -505,14 +510,14 @@ int istft_launch(const float2* spec, const int* len, const float* scale, float* 
         attr_set = true;
     }
     dim3 grid(cdiv(tpad, NEWF), B);
-    istft_kernel<<<grid, 256, ISTFT_SMEM, s>>>(spec, len, scale, wave, lstride, tpad, transform, alpha, beta);
+    snrse_launch(istft_kernel, dim3(grid), dim3(256), ISTFT_SMEM, s, spec, len, scale, wave, lstride, tpad, transform, alpha, beta);
     SNRSE_LAUNCH_CHECK();
     return SNRSE_OK;
 }
 
 int absmax_launch(const float* wave, const int* len, int B, int lstride, float* out, cudaStream_t s) {
     SNRSE_CUDA(cudaMemsetAsync(out, 0, (size_t)B * sizeof(float), s));
-    absmax_kernel<<<dim3((unsigned)cdiv(lstride, ABSMAX_CHUNK), (unsigned)B), 256, 0, s>>>(wave, len, lstride, out);
+    snrse_launch(absmax_kernel, dim3(dim3((unsigned)cdiv(lstride, ABSMAX_CHUNK), (unsigned)B)), dim3(256), 0, s, wave, len, lstride, out);
     SNRSE_LAUNCH_CHECK();
     return SNRSE_OK;
 }

@@ -9,6 +9,7 @@ namespace {
 // Gaussian Fourier features of log(t): emb[b] = [sin(p), cos(p)], p = log(t_b) * W * 2*pi  (layerspp.py:32-43),
 // evaluated in the reference's order.  grid = B, block = nf.
 __global__ void temb_fourier_kernel(const float* __restrict__ t, int nf, const float* __restrict__ fw, float* __restrict__ emb) {
+    pdl_sync();
     const int b = blockIdx.x, tid = threadIdx.x;
     if (tid >= nf) return;
     const float proj = logf(t[b]) * fw[tid] * 2.0f * 3.14159265358979323846f;
@@ -22,6 +23,7 @@ template <int SILU>
 __global__ void __launch_bounds__(256)
 dense_rows_kernel(const float* __restrict__ in, int B, int d, const float* __restrict__ w, const float* __restrict__ bias,
                   int rows, float* __restrict__ out) {
+    pdl_sync();
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= rows) return;
@@ -54,14 +56,14 @@ int temb_launch(const float* t, int B, int nf, const float* fourier_w, const flo
     float* act = scratch;
     float* emb = scratch + (int64_t)B * d;
     float* h1 = emb + (int64_t)B * 2 * nf;
-    temb_fourier_kernel<<<B, nf, 0, s>>>(t, nf, fourier_w, emb);
+    snrse_launch(temb_fourier_kernel, dim3(B), dim3(nf), 0, s, t, nf, fourier_w, emb);
     SNRSE_LAUNCH_CHECK();
     // Linear(2nf -> 4nf) -> SiLU -> Linear(4nf -> 4nf) -> SiLU (the activation every Dense_0 applies to temb, ncsnpp.py:256-275)
-    dense_rows_kernel<1><<<cdiv(d, 8), 256, 0, s>>>(emb, B, 2 * nf, w1, b1, d, h1);
+    snrse_launch(dense_rows_kernel<1>, dim3(cdiv(d, 8)), dim3(256), 0, s, emb, B, 2 * nf, w1, b1, d, h1);
     SNRSE_LAUNCH_CHECK();
-    dense_rows_kernel<1><<<cdiv(d, 8), 256, 0, s>>>(h1, B, d, w2, b2, d, act);
+    snrse_launch(dense_rows_kernel<1>, dim3(cdiv(d, 8)), dim3(256), 0, s, h1, B, d, w2, b2, d, act);
     SNRSE_LAUNCH_CHECK();
-    dense_rows_kernel<0><<<cdiv(rows, 8), 256, 0, s>>>(act, B, d, dense_w, dense_b, rows, tb_out);
+    snrse_launch(dense_rows_kernel<0>, dim3(cdiv(rows, 8)), dim3(256), 0, s, act, B, d, dense_w, dense_b, rows, tb_out);
     SNRSE_LAUNCH_CHECK();
     return SNRSE_OK;
 }

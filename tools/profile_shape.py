@@ -23,7 +23,8 @@ x = torch.view_as_complex(torch.randn(B, 256, T, 2, generator=g)).cuda()
 y = torch.view_as_complex(torch.randn(B, 256, T, 2, generator=g)).cuda()
 t = torch.full((B,), 0.5, device="cuda")
 names = {0: "other", 1: "conv_tcgen05", 2: "groupnorm", 3: "fir", 4: "attention", 5: "thin_conv", 6: "pack_temb_head"}
-for _ in range(3):
+# STEADY=n: n untimed profiled passes first (~25 ms each), so the table below is the power-capped steady state
+for _ in range(3 + int(os.environ.get("STEADY", "0"))):
     prof = eng.profile_forward(x, y, t, mode=1, flags=flags)
 runs = [eng.profile_forward(x, y, t, mode=1, flags=flags) for _ in range(5)]
 runs.sort(key=lambda pr: sum(q["ms"] for q in pr))
@@ -49,7 +50,7 @@ for p in prof:
 PEAK = 1414.8e12
 rows = sorted(sig.items(), key=lambda kv: -(kv[1][1] - kv[0][0] * kv[1][0] / PEAK * 1e3))
 print("  conv signatures (GFLOP, MB, launches, ms total, TFLOP/s, ms above the sustained-peak time):")
-for (fl, by), (n, ms) in rows[:24]:
+for (fl, by), (n, ms) in rows:
     print(f"    {fl / 1e9:9.1f} GF {by / 1e6:8.1f} MB x{n:3d} {ms:7.3f} ms {fl * n / (ms * 1e-3) / 1e12:7.0f} TF/s "
           f"{ms - fl * n / PEAK * 1e3:+7.3f} ms")
 # time by launch size class (latency-bound small maps vs throughput-bound large maps)

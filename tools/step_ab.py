@@ -16,7 +16,8 @@ import bench  # noqa: E402
 from snr_aligned_diffse_b200.pipeline import GraphedEnhancer  # noqa: E402
 
 from snr_aligned_diffse_b200 import _lib  # noqa: E402
-# a variant is FLAGS or FLAGS:PREFETCH (L2 prefetch switch of the 2-CTA convolution kernel, read when the graph is captured)
+# a variant is FLAGS[:PREFETCH[:PDL]] (L2 prefetch switch of the 2-CTA convolution kernel; programmatic dependent launch
+# on / off -- both are read when the graph is captured)
 variants = sys.argv[1:] or ["0", "128", "64", "192"]
 flags = variants
 dev = torch.device("cuda", 0)
@@ -25,8 +26,9 @@ L = int(bench.SECONDS * bench.SR)
 y = bench.synth_waves(bench.BATCH, L, seed=1000).to(dev)
 pipes = []
 for i, v in enumerate(variants):
-    f, pf = (v.split(":") + ["0"])[:2]
+    f, pf, pdl = (v.split(":") + ["0", "1"])[:3]     # FLAGS[:PREFETCH[:PDL]]
     _lib.load().snrse_conv_halo_set_prefetch(int(pf))
+    _lib.load().snrse_set_pdl(int(pdl))
     model, _ = bench.build_models(dev, with_estimator=(i == 0))
     model.dnn._ensure_device_weights()
     model.dnn.engine.default_flags = int(f)
