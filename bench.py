@@ -426,6 +426,15 @@ def run_b200(args):
 
         # ---- sustained figure: the same alternating replay for >= 2 s (every rank, so the clocks line sees load)
         barrier()
+        nv, j0 = None, None
+        if rank == 0:                      # board energy over the sustained region (NVML total-energy counter, mJ)
+            try:
+                import pynvml
+                pynvml.nvmlInit()
+                nv = pynvml.nvmlDeviceGetHandleByIndex(torch.cuda._get_nvml_device_index(local) if hasattr(torch.cuda, "_get_nvml_device_index") else local)
+                j0, tj0 = pynvml.nvmlDeviceGetTotalEnergyConsumption(nv), time.perf_counter()
+            except Exception:
+                nv = None
         n_sus, e0, e1 = 0, torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         for p in pipes[1:]:
@@ -438,6 +447,17 @@ def run_b200(args):
             stream.wait_stream(p.stream)
         e1.record(stream)
         barrier()
+        energy = None
+        if nv is not None:
+            try:
+                joule = (pynvml.nvmlDeviceGetTotalEnergyConsumption(nv) - j0) * 1e-3
+                energy = dict(J_per_step=round(joule / n_sus, 3), avg_watts=round(joule / (time.perf_counter() - tj0), 1),
+                              steps=n_sus, source="NVML total-energy counter over the sustained region, rank 0's GPU",
+                              note="the sustained region sits at the board's power cap (clocks.reasons: sw_power_cap): time per "
+                                   "step ~ Joules per step / cap.  tools/energy_bench.py (profiles/r02_energy.md): cuBLAS bf16 "
+                                   "8192^3 under the same cap 0.70 pJ/FLOP at 1386 TFLOP/s, idle board 258 W")
+            except Exception:
+                energy = None
         ms_sus = torch.tensor([e0.elapsed_time(e1)], device=dev)
         if world > 1:
             dist.all_reduce(ms_sus, op=dist.ReduceOp.MAX)
@@ -459,6 +479,8 @@ def run_b200(args):
         except Exception:
             pass
         roof = profile_roofline(model, pipe, y_dev, peaks) if rank == 0 else None
+        if energy and roof:
+            energy["pJ_per_algorithmic_FLOP"] = round(energy["J_per_step"] / roof["algorithmic_tflop_per_step"], 4)
         parity = None
         if rank == 0:
             pipe.replay()
@@ -548,7 +570,7 @@ def run_b200(args):
                                     note="same alternating replay after 1 s of idle (boost clocks until the power cap bites): "
                                          "how r01 measured its 17.6 ms; for comparison only"),
                     gpu_launches=launches_per_step * args.steps, launches_per_step=launches_per_step,
-                    clocks=clk, roofline=roof, parity=parity, cpu_baseline=cpu, gpu_eager_baseline=eager, impl="b200",
+                    clocks=clk, energy=energy, roofline=roof, parity=parity, cpu_baseline=cpu, gpu_eager_baseline=eager, impl="b200",
                     **extras)
         print(json.dumps(line), flush=True)
         if parity is not None and not parity["ok"]:
