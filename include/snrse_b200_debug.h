@@ -29,7 +29,8 @@ int snrse_ncsnpp_read_tap(void* handle, int B, int F, int T, int module_idx, flo
 void snrse_conv_halo_set_debug(long long* dev_counters);
 /* measurement switches of the 2-CTA convolution kernel.  bit0: L2 prefetch of the next tile's operand and residual boxes
  * (default 0: measured +0.1 ms per step); bit1: two A slots + double-buffered staging on the GroupNorm-in-flight layers;
- * bit2: 4 KB smaller shared-memory budget.  See profiles/r02_step_ab.md. */
+ * bit2: 4 KB smaller shared-memory budget; bit3: the 1x1 shortcut operand of the 128-channel layers shares the halo ring
+ * (the r02 schedule before the separate shortcut ring; different K order, so not bit-identical).  See profiles/r02_step_ab.md. */
 void snrse_conv_halo_set_prefetch(int on);
 
 #ifdef __cplusplus

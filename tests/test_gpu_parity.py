@@ -248,7 +248,10 @@ def test_conv_fused_shortcut_residual_tbias(ops, impl):
 
 
 @pytest.mark.parametrize("case", [(2, 32, 64, 128, 128, 0), (2, 40, 20, 256, 256, 0), (1, 16, 24, 384, 128, 384),
-                                  (3, 72, 12, 128, 256, 0), (16, 64, 64, 256, 256, 0), (2, 8, 8, 512, 256, 512)])
+                                  (3, 72, 12, 128, 256, 0), (16, 64, 64, 256, 256, 0), (2, 8, 8, 512, 256, 512),
+                                  # 128 output channels + shortcut: the shortcut operand's own ring, two sub-tiles, more
+                                  # cluster tiles than clusters (persistent walk); ragged with an odd tile count
+                                  (2, 160, 128, 128, 128, 256), (3, 72, 20, 128, 128, 128)])
 def test_gn_silu_conv3x3_fused_equals_unfused(ops, case):
     """GroupNorm+SiLU applied inside the convolution (2-CTA kernel) == separate GroupNorm pass + convolution, bit for
     bit, and both match the fp32 PyTorch chain (layerspp.py:245-271)."""
@@ -279,6 +282,39 @@ def test_gn_silu_conv3x3_fused_equals_unfused(ops, case):
     got = fused.float().cpu().permute(0, 3, 1, 2)
     err = (got - ref).abs()
     assert (err <= 2 ** -6 * ref.abs() + 3e-2 * ref.abs().mean()).all(), float(err.max())
+
+
+def test_shortcut_ring_batch_invariance_and_shared_ring_agreement(ops):
+    """The 128-channel fused-shortcut layers stream the 1x1 operand through its own ring with an interleaved K order
+    (conv_halo2.cu).  (a) The K order depends on the layer only: every sample of a batch equals the same sample run
+    alone, bit for bit, although the batch of 6 walks two sub-tiles per weight tile and the single sample one.
+    (b) Against the shared-ring schedule (measurement switch bit3, different accumulation order) the result agrees to
+    bf16 rounding, and both match the fp32 convolution."""
+    from snr_aligned_diffse_b200 import _lib
+    g = torch.Generator().manual_seed(5)
+    B, H, W, C0, C1, Co = 6, 96, 64, 128, 256, 128
+    a = torch.randn(B, C0, H, W, generator=g).to(torch.bfloat16)
+    x = torch.randn(B, C1, H, W, generator=g).to(torch.bfloat16)
+    w1 = (torch.randn(Co, C0, 3, 3, generator=g) / math.sqrt(9 * C0)).to(torch.bfloat16)
+    w2 = (torch.randn(Co, C1, 1, 1, generator=g) / math.sqrt(C1)).to(torch.bfloat16)
+    bias = torch.randn(Co, generator=g) * 0.1
+    wt = torch.cat([_pack_w3(w1), w2.reshape(Co, C1)], dim=1).contiguous().to(DEV)
+    an, xn = _nhwc(a).to(DEV), _nhwc(x).to(DEV)
+    full = ops.conv_nhwc(an, wt, 9, x1=xn, bias=bias.to(DEV), impl=0)
+    for b in (0, 5):
+        alone = ops.conv_nhwc(an[b:b + 1].contiguous(), wt, 9, x1=xn[b:b + 1].contiguous(), bias=bias.to(DEV), impl=0)
+        assert torch.equal(alone[0], full[b]), b
+    lib = _lib.load()
+    lib.snrse_conv_halo_set_prefetch(8)
+    try:
+        shared = ops.conv_nhwc(an, wt, 9, x1=xn, bias=bias.to(DEV), impl=0)
+    finally:
+        lib.snrse_conv_halo_set_prefetch(0)
+    ref = (torch.nn.functional.conv2d(a.float(), w1.float(), bias, padding=1) + torch.nn.functional.conv2d(x.float(), w2.float()))
+    for out in (full, shared):
+        got = out.float().cpu().permute(0, 3, 1, 2)
+        assert ((got - ref).abs() <= 2 ** -7 * ref.abs() + 2e-2 * ref.abs().mean()).all()
+    assert ((full.float() - shared.float()).abs() <= 2 ** -7 * full.float().abs() + 1e-3).all()
 
 
 @pytest.mark.parametrize("case", [(2, 32, 64, 128, 128), (3, 40, 20, 128, 256), (16, 64, 64, 256, 256), (1, 24, 12, 256, 128),
