@@ -44,6 +44,21 @@ __device__ __forceinline__ float spec_gain_back(float mag, int transform, float 
     if (alpha == 1.0f) return 1.0f;
     return (alpha == 0.5f) ? mag : powf(mag, 1.0f / alpha - 1.0f);
 }
+// The configuration every checkpoint uses (transform "exponent", alpha = 0.5) without IEEE square roots / divisions and
+// without per-element branching on the transform parameters (the generic path above cost ~100 instructions per bin and
+// frame: more than half of the forward kernel's instruction count).  m2 = |X|^2.
+//   forward : g = beta |X|^-1/2 = beta * rsqrt(sqrt(m2));   inverse: g = |S/beta| = sqrt(m2).   0 -> 0.
+// rsqrt.approx has a relative error of 2^-22.9; |X|^2 below 1e-30 (|X| < 1e-15) is treated as 0.
+__device__ __forceinline__ float fast_rsqrt(float x) {
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float gain_fwd_half(float m2, float beta) {
+    const float mag = m2 * fast_rsqrt(m2);
+    return m2 > 1e-30f ? beta * fast_rsqrt(mag) : 0.f;
+}
+__device__ __forceinline__ float gain_back_half(float m2) { return m2 > 1e-30f ? m2 * fast_rsqrt(m2) : 0.f; }
 constexpr int SPAN = (FT - 1) * HOP + NFFT;   // samples touched by FT consecutive frames (1406)
 
 __device__ constexpr float C3[3] = {1.f, -0.5f, -0.5f};
@@ -171,26 +186,22 @@ stft_kernel(const float* __restrict__ wave, const int* __restrict__ len, const f
     const int ia = pfa_output_index(k == M255 ? 0 : k), ib = pfa_output_index((M255 - k) % M255);
     float es, ec;
     sincospif((float)k / (float)M255, &es, &ec);
+    const bool fast_half = transform == 1 && alpha == 0.5f;
+    const float rsc = (scale && scale_is_divisor) ? 1.0f / sc : sc;     // y / norm as y * (1 / norm): one rounding apart
     for (int pass = 0; pass < npass; ++pass) {
         const int f0 = (blockIdx.x * npass + pass) * FT;
         if (f0 >= tpad) break;                                   // block-uniform
         if (pass) __syncthreads();                               // the previous pass has read X
         const int s0 = f0 * HOP - HALF;
         if (s0 >= 0 && s0 + SPAN <= L) {                         // interior: no reflection
-            for (int e = tid; e < SPAN; e += 256) {
-                float v = wb[s0 + e];
-                if (scale) v = scale_is_divisor ? v / sc : v * sc;
-                xs[e] = v;
-            }
+            for (int e = tid; e < SPAN; e += 256) xs[e] = wb[s0 + e] * rsc;
         } else {
             for (int e = tid; e < SPAN; e += 256) {
                 int i = s0 + e;
                 if (i < 0) i = -i;
                 if (i >= L) i = 2 * (L - 1) - i;
                 i = max(0, min(i, L - 1));  // beyond one reflection: only frames >= nframes (written as zeros) or len <= 255
-                float v = wb[i];
-                if (scale) v = scale_is_divisor ? v / sc : v * sc;
-                xs[e] = v;
+                xs[e] = wb[i] * rsc;
             }
         }
         __syncthreads();
@@ -215,6 +226,10 @@ stft_kernel(const float* __restrict__ wave, const int* __restrict__ len, const f
             if (f0 + f >= nframes) {
                 r = 0.f;
                 i = 0.f;
+            } else if (fast_half) {
+                const float g = gain_fwd_half(fmaf(r, r, i * i), beta);
+                r *= g;
+                i *= g;
             } else if (transform != 0) {
                 // beta * |X|^alpha * e^{i arg X} = X * beta * |X|^(alpha-1), 0 -> 0  (data_module.py:241-251)
                 const float g = spec_gain_fwd(sqrtf(r * r + i * i), transform, alpha, beta);
@@ -278,6 +293,7 @@ istft_kernel(const float2* __restrict__ spec, const int* __restrict__ len, const
     for (int i = tid; i < OLA_SPAN; i += 256) ola[i] = 0.f;
     const float2* sb = spec + (int64_t)b * NBINS * tpad;
     const float inv_beta = 1.0f / beta;
+    const bool fast_half = transform == 1 && alpha == 0.5f;
     const bool vec_ok = (tpad & 1) == 0;
     // merge: thread t < 255 produces transform input element t, i.e. Z'[k] for k = pfa_input_pos(t), from the bins
     // k and 255-k (k = 0 pairs with the Nyquist row 255):  e^{+i pi k/255} = (ec, es)
@@ -303,7 +319,11 @@ istft_kernel(const float2* __restrict__ spec, const int* __restrict__ len, const
                     if (t + 1 < tpad) { v.z = p[1].x; v.w = p[1].y; }
                 }
             }
-            if (transform != 0) {
+            if (fast_half) {
+                v.x *= inv_beta; v.y *= inv_beta; v.z *= inv_beta; v.w *= inv_beta;
+                const float g0 = gain_back_half(fmaf(v.x, v.x, v.y * v.y)), g1 = gain_back_half(fmaf(v.z, v.z, v.w * v.w));
+                v.x *= g0; v.y *= g0; v.z *= g1; v.w *= g1;
+            } else if (transform != 0) {
                 v.x *= inv_beta; v.y *= inv_beta; v.z *= inv_beta; v.w *= inv_beta;
                 const float g0 = spec_gain_back(sqrtf(v.x * v.x + v.y * v.y), transform, alpha);
                 const float g1 = spec_gain_back(sqrtf(v.z * v.z + v.w * v.w), transform, alpha);
