@@ -33,7 +33,8 @@ long long snrse_launch_count(void);       /* kernels launched by this library si
 /* Programmatic dependent launch (griddepcontrol.launch_dependents / .wait in every kernel): `mask` selects the launches that
  * carry the programmatic-stream-serialization attribute, i.e. may become resident while their predecessor in the stream /
  * captured graph drains (prologue, TMEM allocation and the weight ring's first loads overlap the predecessor's tail; results
- * are unchanged).  bit0: the memory-bound / small kernels, bit1: the two tcgen05 convolution kernels.  Read at launch
+ * are unchanged).  bit0: the memory-bound / small kernels, bit1: the two tcgen05 convolution kernels, bit2: the GroupNorm
+ * finalize launches alone (measured neutral).  Read at launch
  * (== graph capture) time.  Returns the previous mask; mask < 0 only queries.  Default: environment variable SNRSE_PDL when
  * set, else 2 (measured on the graphed 16 x 4 s step: 0 -> 20.13 ms, 2 -> 20.00 ms, 1 and 3 -> +0.1 ms; profiles/r02_step_ab.md). */
 int snrse_set_pdl(int mask);

@@ -11,7 +11,7 @@ static thread_local char g_err[512] = "";
 long long g_snrse_launches = 0;
 static int pdl_default() {
     const char* e = getenv("SNRSE_PDL");
-    return e ? (atoi(e) & 3) : 2;
+    return e ? (atoi(e) & 7) : 2;
 }
 int g_snrse_pdl = pdl_default();
 
@@ -37,7 +37,7 @@ int snrse_version(void) { return 100; }
 long long snrse_launch_count(void) { return g_snrse_launches; }
 int snrse_set_pdl(int on) {
     const int prev = g_snrse_pdl;
-    if (on >= 0) g_snrse_pdl = on & 3;
+    if (on >= 0) g_snrse_pdl = on & 7;
     return prev;
 }
 const char* snrse_last_error(void) { return g_err; }

@@ -187,7 +187,7 @@ int gn_finalize_launch(const unsigned long long* src0, int U0, const unsigned lo
                        cudaStream_t s) {
     const int C = 4 * (U0 + U1);
     SNRSE_CHECK_ARG(C % 128 == 0 && C <= 512 && src0 && (U1 == 0 || src1), "GroupNorm finalize: bad sources");
-    snrse_launch(gn_finalize_kernel, dim3(B), dim3(256), 0, s, src0, U0, src1, U1, 1.0 / (double)count_per_group, gamma, beta, eps, scsh);
+    snrse_launch_m(1 | 4, gn_finalize_kernel, dim3(B), dim3(256), 0, s, src0, U0, src1, U1, 1.0 / (double)count_per_group, gamma, beta, eps, scsh);
     SNRSE_LAUNCH_CHECK();
     return SNRSE_OK;
 }
