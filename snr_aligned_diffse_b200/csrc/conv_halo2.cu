@@ -17,7 +17,12 @@
 // Super-tile = SUB (1 or 2) sub-tiles stacked in H sharing every weight tile; SUB accumulators of 128 lanes x N
 // columns per CTA in TMEM, double-buffered when SUB*N <= 256 so the epilogue of tile i overlaps tile i+1.
 // Two TMA rings: A (halo tiles, one per channel chunk) and B (per-tap weight tiles, N/2 rows per CTA); both
-// CTAs' loads complete on the LEADER's barriers, tcgen05.commit multicasts to both CTAs.
+// CTAs' loads complete on the LEADER's barriers, tcgen05.commit multicasts to both CTAs.  The 128-output-channel
+// layers with a fused 1x1 shortcut add a third ring for the shortcut operand's bare tiles (16 KB per sub-tile) and
+// interleave those chunks behind the 3x3 chunks in the K loop; the A producer walks both rings with non-blocking
+// barrier probes (see conv_halo2_make_plan).
+// Programmatic dependent launch: the kernel triggers its successor at once and waits for its predecessor only after
+// its own prologue; the weight producer never waits (weights are constants of the captured graph).
 //
 // Warp roles (12 warps): 0..7 = epilogue (TMEM lane quarter = warp & 3: 4 image rows x 8 pixels; column half =
 // warp >> 2), 8 = A producer, 9 = B producer, 10 / 11 = MMA issuers of sub-tile 0 / 1 (11 owns TMEM).
@@ -33,7 +38,8 @@
 #include "tma_host.h"
 
 // Measurement switches (snrse_conv_halo_set_prefetch, include/snrse_b200_debug.h).  bit0: L2 prefetch of the next tile's
-// boxes -- measured on the graphed step, interleaved: 20.05 ms with, 19.95 ms without (profiles/r02_step_ab.md), so OFF.
+// boxes -- measured on the graphed step, interleaved: 20.05 ms with, 19.95 ms without (profiles/r02_step_ab.md), so OFF;
+// bit1 / bit2: ring-depth variants of the GroupNorm layers; bit3: shared ring for the shortcut operand (the r02 schedule).
 int g_halo2_prefetch = 0;
 
 namespace {
