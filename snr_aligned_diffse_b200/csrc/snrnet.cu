@@ -36,44 +36,80 @@ int64_t param_offset(int i) {  // bytes, 256-aligned slots
 }
 const float* P(const void* blob, int i) { return reinterpret_cast<const float*>(static_cast<const uint8_t*>(blob) + param_offset(i)); }
 
+__device__ __forceinline__ void cp_async4_zfill(float* smem_dst, const float* gsrc, bool valid) {
+    // 4-byte asynchronous copy; !valid: nothing is read and the destination is zero-filled (src-size 0)
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc),
+                 "r"(valid ? 4 : 0) : "memory");
+}
+
 // ---- conv5x5 (2->32, pad 2) + maxpool 2x2.  feat [B][2][256][T16] -> a1 [NC][32][128][8], NC = B*T16/16
+// Block = one cluster x C5_TILES consecutive tiles of 16 input rows (-> 8 pooled rows each); the weights are staged once,
+// the input patches are double-buffered with cp.async so that the next tile streams in while this one is computed.
+// Thread = (group of 8 output channels, pooled position): the 2 x 6 x 6 input patch under its 2x2 convolution outputs
+// sits in registers and every weight is ONE broadcast shared-memory load for four FMAs.  Accumulation order per output:
+// bias, then c, ky, kx (as a direct loop).
+constexpr int C5_TILES = 4;
 __global__ void __launch_bounds__(256)
 snr_conv5_pool_kernel(const float* __restrict__ feat, const float* __restrict__ w, const float* __restrict__ bias,
                       float* __restrict__ a1, int T16) {
     pdl_sync();
     __shared__ float sw[32 * 50];
-    __shared__ float sx[2][20][20];  // input patch: 16 freq rows (+4 halo) x 16 frames (+4 halo)
+    __shared__ float sbias[32];
+    __shared__ float sxb[2][2 * 20 * 20];  // two stages of the input patch: 16 freq rows (+4 halo) x 16 frames (+4 halo)
     const int nc = blockIdx.y, clusters = T16 / 16;
     const int b = nc / clusters, cl = nc % clusters;
-    const int f0 = blockIdx.x * 16;  // 16 input rows -> 8 pooled rows
+    auto load_tile = [&](int buf, int f0) {
+        for (int i = threadIdx.x; i < 2 * 20 * 20; i += 256) {
+            const int c = i / 400, r = (i / 20) % 20, t = i % 20;
+            const int f = f0 + r - 2, tt = t - 2;
+            const bool ok = f >= 0 && f < 256 && tt >= 0 && tt < 16;
+            const float* src = feat + (((int64_t)b * 2 + c) * 256 + (ok ? f : 0)) * T16 + cl * 16 + (ok ? tt : 0);
+            cp_async4_zfill(&sxb[buf][i], src, ok);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    const int tile0 = blockIdx.x * C5_TILES;
+    load_tile(0, tile0 * 16);
     for (int i = threadIdx.x; i < 32 * 50; i += 256) sw[i] = w[i];
-    for (int i = threadIdx.x; i < 2 * 20 * 20; i += 256) {
-        const int c = i / 400, r = (i / 20) % 20, t = i % 20;
-        const int f = f0 + r - 2, tt = t - 2;
-        float v = 0.f;
-        if (f >= 0 && f < 256 && tt >= 0 && tt < 16) v = feat[(((int64_t)b * 2 + c) * 256 + f) * T16 + cl * 16 + tt];
-        sx[c][r][t] = v;
-    }
-    __syncthreads();
-    // 32 co x 8 pooled rows x 8 pooled cols = 2048 outputs, 8 per thread
-    for (int o = threadIdx.x; o < 2048; o += 256) {
-        const int co = o >> 6, pr = (o >> 3) & 7, pc = o & 7;
-        float best = -INFINITY;
+    if (threadIdx.x < 32) sbias[threadIdx.x] = bias[threadIdx.x];
+    const int cg = threadIdx.x >> 6, pos = threadIdx.x & 63, pr = pos >> 3, pc = pos & 7;
+    for (int ti = 0; ti < C5_TILES; ++ti) {
+        const int f0 = (tile0 + ti) * 16;
+        if (ti + 1 < C5_TILES) {
+            load_tile((ti + 1) & 1, f0 + 16);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncthreads();
+        const float* sx = sxb[ti & 1];
+        float patch[2][6][6];
 #pragma unroll
-        for (int dy = 0; dy < 2; ++dy)
+        for (int c = 0; c < 2; ++c)
 #pragma unroll
-            for (int dx = 0; dx < 2; ++dx) {
-                float acc = bias[co];
-                const int r0 = pr * 2 + dy, c0 = pc * 2 + dx;
-                for (int c = 0; c < 2; ++c)
+            for (int i = 0; i < 6; ++i)
 #pragma unroll
-                    for (int ky = 0; ky < 5; ++ky)
+                for (int j = 0; j < 6; ++j) patch[c][i][j] = sx[c * 400 + (2 * pr + i) * 20 + 2 * pc + j];
+        for (int j = 0; j < 8; ++j) {
+            const int co = cg * 8 + j;
+            const float b0 = sbias[co];
+            float a00 = b0, a01 = b0, a10 = b0, a11 = b0;
+            const float* wc = sw + co * 50;
 #pragma unroll
-                        for (int kx = 0; kx < 5; ++kx)
-                            acc = fmaf(sx[c][r0 + ky][c0 + kx], sw[co * 50 + c * 25 + ky * 5 + kx], acc);
-                best = fmaxf(best, acc);
-            }
-        a1[(((int64_t)nc * 32 + co) * 128 + (f0 / 2 + pr)) * 8 + pc] = best;
+            for (int c = 0; c < 2; ++c)
+#pragma unroll
+                for (int ky = 0; ky < 5; ++ky)
+#pragma unroll
+                    for (int kx = 0; kx < 5; ++kx) {
+                        const float wv = wc[c * 25 + ky * 5 + kx];
+                        a00 = fmaf(patch[c][ky][kx], wv, a00);
+                        a01 = fmaf(patch[c][ky][kx + 1], wv, a01);
+                        a10 = fmaf(patch[c][ky + 1][kx], wv, a10);
+                        a11 = fmaf(patch[c][ky + 1][kx + 1], wv, a11);
+                    }
+            a1[(((int64_t)nc * 32 + co) * 128 + (f0 / 2 + pr)) * 8 + pc] = fmaxf(fmaxf(a00, a01), fmaxf(a10, a11));
+        }
+        __syncthreads();   // the stage is free again before the load of the trip after next overwrites it
     }
 }
 
@@ -81,62 +117,86 @@ snr_conv5_pool_kernel(const float* __restrict__ feat, const float* __restrict__ 
 // Block = one cluster x 16 conv rows x all 32 output channels.  Thread = 4 output channels x a 2x2 patch of
 // conv outputs (-> 2 pooled values per channel): per input channel 16 activations + 9 weight vectors are
 // loaded for 144 FMA (register tiling keeps the kernel FMA-bound instead of LDS-bound).
-constexpr int C3_ROWS = 16;
+// A block walks C3_TILES row tiles of one cluster: the weights are staged once, the input tiles are double-buffered with
+// cp.async (staging 59 KB between two barriers per 16 rows left the FMA pipe idle for about a third of a block's life).
+constexpr int C3_ROWS = 16, C3_TILES = 2;
+constexpr int C3_SX = 32 * 18 * 10;
+constexpr int C3_SMEM = (32 * 9 * 32 + 2 * C3_SX) * 4;
 __global__ void __launch_bounds__(256)
 snr_conv3_pool_kernel(const float* __restrict__ a1, const float* __restrict__ w, const float* __restrict__ bias,
                       float* __restrict__ a2) {
     pdl_sync();
     extern __shared__ __align__(16) float sm3[];
     float* sw = sm3;                       // [ci][k][co]   32*9*32 floats = 36 KB
-    float* sx = sm3 + 32 * 9 * 32;         // [ci][18][10]  23 KB
-    const int nc = blockIdx.y, f0 = blockIdx.x * C3_ROWS;
+    float* sxb = sm3 + 32 * 9 * 32;        // 2 x [ci][18][10]  2 x 23 KB
+    const int nc = blockIdx.y, tile0 = blockIdx.x * C3_TILES;
+    auto load_tile = [&](int buf, int f0) {
+        float* dst = sxb + buf * C3_SX;
+        for (int i = threadIdx.x; i < C3_SX; i += 256) {
+            const int c = i / 180, r = (i / 10) % 18, t = i % 10;
+            const int f = f0 + r - 1, tt = t - 1;
+            const bool ok = f >= 0 && f < 128 && tt >= 0 && tt < 8;
+            cp_async4_zfill(dst + i, a1 + (((int64_t)nc * 32 + c) * 128 + (ok ? f : 0)) * 8 + (ok ? tt : 0), ok);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    load_tile(0, tile0 * C3_ROWS);
     {   // weights pre-packed [ci][tap][co] (transform 2): a straight, conflict-free copy
         const float4* src = reinterpret_cast<const float4*>(w);
         float4* dst = reinterpret_cast<float4*>(sw);
         for (int i = threadIdx.x; i < 32 * 32 * 9 / 4; i += 256) dst[i] = __ldg(src + i);
     }
-    for (int i = threadIdx.x; i < 32 * 18 * 10; i += 256) {
-        const int c = i / 180, r = (i / 10) % 18, t = i % 10;
-        const int f = f0 + r - 1, tt = t - 1;
-        float v = 0.f;
-        if (f >= 0 && f < 128 && tt >= 0 && tt < 8) v = a1[(((int64_t)nc * 32 + c) * 128 + f) * 8 + tt];
-        sx[i] = v;
-    }
-    __syncthreads();
     const int cg = threadIdx.x & 7, pg = threadIdx.x >> 3;  // channel group (4 co), position group
     const int pr = pg >> 2, pc2 = pg & 3;                    // pooled row 0..7, column pair 0..3
-    float acc[4][4];                                         // [co][pos: (dy,dx)]
+    float bv[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
+    for (int j = 0; j < 4; ++j) bv[j] = bias[cg * 4 + j];
+    for (int ti = 0; ti < C3_TILES; ++ti) {
+        const int f0 = (tile0 + ti) * C3_ROWS;
+        if (ti + 1 < C3_TILES) {
+            load_tile((ti + 1) & 1, f0 + C3_ROWS);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncthreads();
+        const float* sx = sxb + (ti & 1) * C3_SX;
+        float acc[4][4];                                         // [co][pos: (dy,dx)]
 #pragma unroll
-        for (int q = 0; q < 4; ++q) acc[j][q] = bias[cg * 4 + j];
-    for (int ci = 0; ci < 32; ++ci) {
-        float xv[4][4];
+        for (int j = 0; j < 4; ++j)
 #pragma unroll
-        for (int r = 0; r < 4; ++r)
+            for (int q = 0; q < 4; ++q) acc[j][q] = bv[j];
+        for (int ci = 0; ci < 32; ++ci) {
+            float xv[4][4];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) xv[r][c] = sx[(ci * 18 + pr * 2 + r) * 10 + pc2 * 2 + c];
-#pragma unroll
-        for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-            for (int kx = 0; kx < 3; ++kx) {
-                const float4 wv = *reinterpret_cast<const float4*>(&sw[(ci * 9 + ky * 3 + kx) * 32 + cg * 4]);
-                const float ww[4] = {wv.x, wv.y, wv.z, wv.w};
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-#pragma unroll
-                    for (int dy = 0; dy < 2; ++dy)
-#pragma unroll
-                        for (int dx = 0; dx < 2; ++dx)
-                            acc[j][dy * 2 + dx] = fmaf(xv[dy + ky][dx + kx], ww[j], acc[j][dy * 2 + dx]);
+            for (int r = 0; r < 4; ++r) {   // four consecutive floats at an even offset: two 8-byte loads
+                const float2 lo = *reinterpret_cast<const float2*>(&sx[(ci * 18 + pr * 2 + r) * 10 + pc2 * 2]);
+                const float2 hi = *reinterpret_cast<const float2*>(&sx[(ci * 18 + pr * 2 + r) * 10 + pc2 * 2 + 2]);
+                xv[r][0] = lo.x; xv[r][1] = lo.y; xv[r][2] = hi.x; xv[r][3] = hi.y;
             }
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+                    const float4 wv = *reinterpret_cast<const float4*>(&sw[(ci * 9 + ky * 3 + kx) * 32 + cg * 4]);
+                    const float ww[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+#pragma unroll
+                        for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+                            for (int dx = 0; dx < 2; ++dx)
+                                acc[j][dy * 2 + dx] = fmaf(xv[dy + ky][dx + kx], ww[j], acc[j][dy * 2 + dx]);
+                }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int dx = 0; dx < 2; ++dx)
+                a2[(((int64_t)nc * 32 + cg * 4 + j) * 64 + (f0 / 2 + pr)) * 8 + pc2 * 2 + dx] =
+                    fmaxf(acc[j][dx], acc[j][2 + dx]);
+        __syncthreads();   // the stage is free again before a later load overwrites it
     }
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-#pragma unroll
-        for (int dx = 0; dx < 2; ++dx)
-            a2[(((int64_t)nc * 32 + cg * 4 + j) * 64 + (f0 / 2 + pr)) * 8 + pc2 * 2 + dx] =
-                fmaxf(acc[j][dx], acc[j][2 + dx]);
 }
 
 // ---- four (64 x k) convolutions + max over time.  a2 [NC][32][64][8] -> feats [NC][128]
@@ -147,34 +207,53 @@ struct ConvtW {
     const float* w[4];
     const float* b[4];
 };
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+constexpr int CONVT_SX = 8 * 32 * 8;                       // floats of one activation stage
+constexpr int CONVT_STAGE = CONVT_SX + 32 * 8 * 32;        // + the widest (k = 8) weight chunk
+constexpr int CONVT_SMEM = 2 * CONVT_STAGE * 4;            // two stages, 80 KB
+
 template <int K>   // kernel width in frames (1, 2, 4, 8): compile-time so that only the K * (9-K) useful FMAs per row are issued
 __device__ __forceinline__ void snr_convt_body(const float* __restrict__ a2, const float* __restrict__ wg,
                                                const float* __restrict__ bg, float* __restrict__ feats, int64_t ncl, int ki,
-                                               float (*sx)[32][8], float* sw) {
+                                               float* smem) {
     constexpr int NOUT = 9 - K;
     const int64_t nc0 = (int64_t)blockIdx.x * 8;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float acc[NOUT];
 #pragma unroll
     for (int t = 0; t < NOUT; ++t) acc[t] = 0.f;
-    for (int r0 = 0; r0 < 2048; r0 += 32) {
-        __syncthreads();
-        for (int i = threadIdx.x; i < 8 * 32 * 8; i += 256) {
-            const int cl = i >> 8, rr = (i >> 3) & 31, t = i & 7;
+    // Two stages filled with cp.async: chunk i+1 streams in while chunk i is consumed (staging with plain loads between two
+    // barriers exposed the global-memory latency 64 times per block: 287 us for the 16 x 4 s batch).
+    auto load_stage = [&](int buf, int r0) {
+        float* sx = smem + buf * CONVT_STAGE;
+        float* sw = sx + CONVT_SX;
+        for (int i = threadIdx.x; i < CONVT_SX / 4; i += 256) {     // per cluster 32 rows x 8 frames = 64 contiguous float4
+            const int cl = i >> 6, q = i & 63;
             const int64_t nc = nc0 + cl;
-            sx[cl][rr][t] = nc < ncl ? a2[nc * 16384 + (int64_t)(r0 + rr) * 8 + t] : 0.f;
+            if (nc < ncl) cp_async16(sx + cl * 256 + q * 4, a2 + nc * 16384 + (int64_t)r0 * 8 + q * 4);
+            else *reinterpret_cast<float4*>(sx + cl * 256 + q * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
         }
         // weights are pre-packed [r][dt][co]: the 32*K*32 floats of this chunk are one contiguous block
-        {
-            const float4* src = reinterpret_cast<const float4*>(wg + (int64_t)r0 * K * 32);
-            float4* dst = reinterpret_cast<float4*>(sw);
-            for (int i = threadIdx.x; i < 8 * 32 * K; i += 256) dst[i] = __ldg(src + i);
+        for (int i = threadIdx.x; i < 8 * 32 * K; i += 256) cp_async16(sw + i * 4, wg + (int64_t)r0 * K * 32 + i * 4);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    load_stage(0, 0);
+    for (int it = 0; it < 64; ++it) {
+        if (it + 1 < 64) {
+            load_stage((it + 1) & 1, (it + 1) * 32);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
         __syncthreads();
+        const float* sx = smem + (it & 1) * CONVT_STAGE + warp * 256;
+        const float* sw = smem + (it & 1) * CONVT_STAGE + CONVT_SX;
 #pragma unroll 4
         for (int rr = 0; rr < 32; ++rr) {
-            const float4 xa = *reinterpret_cast<const float4*>(&sx[warp][rr][0]);
-            const float4 xb = *reinterpret_cast<const float4*>(&sx[warp][rr][4]);
+            const float4 xa = *reinterpret_cast<const float4*>(sx + rr * 8);
+            const float4 xb = *reinterpret_cast<const float4*>(sx + rr * 8 + 4);
             const float xf[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
 #pragma unroll
             for (int dt = 0; dt < K; ++dt) {
@@ -183,6 +262,7 @@ __device__ __forceinline__ void snr_convt_body(const float* __restrict__ a2, con
                 for (int t = 0; t < NOUT; ++t) acc[t] = fmaf(xf[t + dt], wv, acc[t]);
             }
         }
+        __syncthreads();      // everyone is done with this stage before the load issued in the next trip overwrites it
     }
     float best = -INFINITY;
 #pragma unroll
@@ -194,13 +274,12 @@ __device__ __forceinline__ void snr_convt_body(const float* __restrict__ a2, con
 __global__ void __launch_bounds__(256)
 snr_convt_kernel(const float* __restrict__ a2, ConvtW cw, float* __restrict__ feats, int64_t ncl) {
     pdl_sync();
-    __shared__ __align__(16) float sx[8][32][8];     // [cluster][r][frame]      8 KB
-    __shared__ __align__(16) float sw[32 * 8 * 32];  // [r][dt][co]           <= 32 KB
+    extern __shared__ __align__(16) float convt_smem[];
     const int ki = blockIdx.y;                       // weights packed [r (2048)][dt (k)][co (32)]
-    if (ki == 0) snr_convt_body<1>(a2, cw.w[0], cw.b[0], feats, ncl, 0, sx, sw);
-    else if (ki == 1) snr_convt_body<2>(a2, cw.w[1], cw.b[1], feats, ncl, 1, sx, sw);
-    else if (ki == 2) snr_convt_body<4>(a2, cw.w[2], cw.b[2], feats, ncl, 2, sx, sw);
-    else snr_convt_body<8>(a2, cw.w[3], cw.b[3], feats, ncl, 3, sx, sw);
+    if (ki == 0) snr_convt_body<1>(a2, cw.w[0], cw.b[0], feats, ncl, 0, convt_smem);
+    else if (ki == 1) snr_convt_body<2>(a2, cw.w[1], cw.b[1], feats, ncl, 1, convt_smem);
+    else if (ki == 2) snr_convt_body<4>(a2, cw.w[2], cw.b[2], feats, ncl, 2, convt_smem);
+    else snr_convt_body<8>(a2, cw.w[3], cw.b[3], feats, ncl, 3, convt_smem);
 }
 
 // ---- LSTM input projections for both directions: pre[dir][B*S][512] = W_ih x + b_ih + b_hh
@@ -362,15 +441,15 @@ int snrse_snrnet_forward(const void* weights, const float* feat, float* out, int
     float* hout = pre + nc * 1024;
     static bool attr_set = false;
     if (!attr_set) {
-        SNRSE_CUDA(cudaFuncSetAttribute(snr_conv3_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (32 * 9 * 32 + 32 * 18 * 10) * 4));
+        SNRSE_CUDA(cudaFuncSetAttribute(snr_conv3_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C3_SMEM));
         SNRSE_CUDA(cudaFuncSetAttribute(snr_lstm_rec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (64 * 512 + 128 + 512) * 4));
+        SNRSE_CUDA(cudaFuncSetAttribute(snr_convt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CONVT_SMEM));
         attr_set = true;
     }
-    snrse_launch(snr_conv5_pool_kernel, dim3(dim3(16, (unsigned)nc)), dim3(256), 0, s, feat, P(weights, 0), P(weights, 1), a1, T16);
+    snrse_launch(snr_conv5_pool_kernel, dim3(dim3(16 / C5_TILES, (unsigned)nc)), dim3(256), 0, s, feat, P(weights, 0), P(weights, 1), a1, T16);
     SNRSE_LAUNCH_CHECK();
-    snrse_launch(snr_conv3_pool_kernel, dim3(dim3(128 / C3_ROWS, (unsigned)nc)), dim3(256), (32 * 9 * 32 + 32 * 18 * 10) * 4, s, 
+    snrse_launch(snr_conv3_pool_kernel, dim3(dim3(128 / (C3_ROWS * C3_TILES), (unsigned)nc)), dim3(256), C3_SMEM, s, 
         a1, P(weights, 2), P(weights, 3), a2);
     SNRSE_LAUNCH_CHECK();
     ConvtW cw;
@@ -378,7 +457,7 @@ int snrse_snrnet_forward(const void* weights, const float* feat, float* out, int
         cw.w[i] = P(weights, 4 + 2 * i);
         cw.b[i] = P(weights, 5 + 2 * i);
     }
-    snrse_launch(snr_convt_kernel, dim3(dim3((unsigned)cdiv64(nc, 8), 4)), dim3(256), 0, s, a2, cw, feats, nc);
+    snrse_launch(snr_convt_kernel, dim3(dim3((unsigned)cdiv64(nc, 8), 4)), dim3(256), CONVT_SMEM, s, a2, cw, feats, nc);
     SNRSE_LAUNCH_CHECK();
     snrse_launch(snr_lstm_pre_kernel, dim3((unsigned)cdiv64(nc, 8)), dim3(256), 0, s, feats, P(weights, 12), P(weights, 14), P(weights, 15), P(weights, 16),
                                                      P(weights, 18), P(weights, 19), pre, nc);
