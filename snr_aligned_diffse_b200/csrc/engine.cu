@@ -577,10 +577,11 @@ int rec_resblock(Plan& P, const Mod& m, int x) {
             rec_gn_finalize(P, x, m.o[0], m.o[1]);
             a = rec_fir(P, x, m.up ? 1 : 0, 1);
             xs = rec_fir(P, x, m.up ? 1 : 0, 0);
-        } else if ((m.up || m.down) && (P.flags & 64) && !(P.flags & 16)) {
-            // bit6: one dual-output FIR launch over x produces both branches (x comes from DRAM once instead of three
-            // times).  Measured neutral on the graphed step (19.92 vs 19.90 ms, profiles/r02_step_ab.md): the FIR kernels are
-            // issue-bound on the redundant SiLU evaluations, so the three-pass form stays the default.
+        } else if ((m.up || m.down) && !(P.flags & 64) && !(P.flags & 16)) {
+            // default: one dual-output FIR launch over x produces both branches; every row segment is staged in shared
+            // memory once, raw and normalised, so x comes from DRAM once instead of three times and SiLU is evaluated once
+            // per element.  Measured against the three-pass form (flag bit6): GroupNorm + FIR launches 2.63 -> 2.37 ms per
+            // step, graphed step 20.04 -> 19.98 ms (profiles/r02_step_ab.md); bit-identical.
             rec_gn_finalize(P, x, m.o[0], m.o[1]);
             rec_fir_dual(P, x, m.up ? 1 : 0, &a, &xs);
         } else {

@@ -225,25 +225,233 @@ fir_up2_kernel(const bf16* __restrict__ x, int ld, int C, int H, int W, bf16* __
 }
 
 // ---- dual-output variants for the up / down residual blocks (layerspp.py:245-257): the block filters BOTH
-// h = silu(GroupNorm(x)) and the raw x with the same FIR.  One launch produces FIR(h) and FIR(x): every thread runs the
-// normalising filter over its band and then the plain filter over the SAME band, whose rows are then still in L1 / L2,
-// so x comes from DRAM once.  Against the three-pass form (gn_apply: read x, write h; FIR: read h; FIR: read x) the
-// DRAM traffic per element of x drops from 3 reads + 1 write (+ outputs) to 1 read (+ outputs), and the register
-// footprint stays that of the single-output kernels (a one-pass version holding both windows needed 156 / 242).
-// Same arithmetic and rounding points as the separate passes: bit-identical results.
-__global__ void __launch_bounds__(256)
+// h = silu(GroupNorm(x)) and the raw x with the same FIR.  One launch produces FIR(h) and FIR(x) from ONE pass over x:
+// every input row segment of the block (its columns + halo, all channels) is staged in shared memory once, raw and
+// normalised (silu(x*scale + shift) rounded to bf16 -- what the separate GroupNorm pass would have stored), and both
+// filters read their taps from there.  Each element is loaded and normalised once per block (the single-output kernels
+// with the normalisation on load evaluate SiLU 2x (down) / 3x (up) per element and are issue-bound on it).  Against the
+// three-pass form (gn_apply: read x, write h; FIR: read h; FIR: read x) the DRAM traffic per element of x drops from
+// 3 reads + 1 write (+ outputs) to 1 read (+ outputs).  Same arithmetic and rounding points: bit-identical results.
+// Staging is split in two so that the global loads of the NEXT rows are in flight while the current rows are filtered:
+// fir_stage_load issues up to MAXI 16-byte loads of a row segment into registers (nothing depends on them yet),
+// fir_stage_store normalises them and writes the raw and the normalised copy to shared memory.
+template <int MAXI>
+struct StageRegs {
+    uint4 raw[MAXI];
+    unsigned ok;      // bit i: item i lies inside the image (others are stored as zeros)
+};
+template <int MAXI>
+__device__ __forceinline__ void fir_stage_load(const bf16* __restrict__ img, int ld, int H, int W, int hh, int wbase, int ncol,
+                                               int tpp, int chunk, StageRegs<MAXI>& r) {
+    const bool row_ok = hh >= 0 && hh < H;
+    const int cstep = blockDim.x / tpp;
+    r.ok = 0;
+#pragma unroll
+    for (int i = 0; i < MAXI; ++i) {
+        const int col = threadIdx.x / tpp + i * cstep, ww = wbase + col;
+        r.raw[i] = make_uint4(0, 0, 0, 0);
+        if (col < ncol && row_ok && ww >= 0 && ww < W) {
+            r.raw[i] = __ldg(reinterpret_cast<const uint4*>(img + ((int64_t)hh * W + ww) * ld + chunk * 8));
+            r.ok |= 1u << i;
+        }
+    }
+}
+template <int MAXI>
+__device__ __forceinline__ void fir_stage_store(const StageRegs<MAXI>& r, int ncol, int tpp, int chunk, const Norm8& nm,
+                                                uint4* __restrict__ s_raw, uint4* __restrict__ s_nrm) {
+    const int cstep = blockDim.x / tpp;
+#pragma unroll
+    for (int i = 0; i < MAXI; ++i) {
+        const int col = threadIdx.x / tpp + i * cstep;
+        if (col < ncol) {
+            uint4 nr = make_uint4(0, 0, 0, 0);
+            if ((r.ok >> i) & 1u) {
+                float f[8];
+                unpack_norm<true>(r.raw[i], nm, true, f);
+                nr = pack8(f);                     // already bf16 values: exact
+            }
+            s_raw[col * tpp + chunk] = r.raw[i];
+            s_nrm[col * tpp + chunk] = nr;
+        }
+    }
+}
+// horizontal [1,3,3,1]/8 over four staged columns (stride tpp); zeros stand for positions outside the image
+__device__ __forceinline__ void hfilt_down_s(const uint4* __restrict__ p, int tpp, float* r) {
+    float f0[8], f1[8], f2[8], f3[8];
+    unpack8(p[0], f0);
+    unpack8(p[tpp], f1);
+    unpack8(p[2 * tpp], f2);
+    unpack8(p[3 * tpp], f3);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] = fmaf(0.125f, f3[j], fmaf(0.375f, f2[j], fmaf(0.375f, f1[j], fmaf(0.125f, f0[j], 0.f))));
+}
+
+__global__ void __launch_bounds__(256, 2)
 fir_down2_dual_kernel(const bf16* __restrict__ x, int ld, int C, int H, int W, bf16* __restrict__ out_n, int out_n_ld,
                       bf16* __restrict__ out_r, int out_r_ld, int band, const float* __restrict__ scsh) {
     pdl_sync();
-    fir_down2_body<true>(x, ld, C, H, W, out_n, out_n_ld, band, scsh);
-    fir_down2_body<false>(x, ld, C, H, W, out_r, out_r_ld, band, nullptr);
+    extern __shared__ __align__(16) uint4 fir_sm[];
+    const int tpp = C >> 3, cols = blockDim.x / tpp;
+    const int chunk = threadIdx.x % tpp, tcol = threadIdx.x / tpp, c0 = chunk * 8;
+    const int Ho = H >> 1, Wo = W >> 1;
+    const int wo = blockIdx.x * cols + tcol;          // >= Wo: the thread only helps staging
+    const int b = blockIdx.z;
+    const bf16* img = x + (int64_t)b * H * W * ld;
+    const int ho0 = blockIdx.y * band, ho1 = min(ho0 + band, Ho);
+    const Norm8 nm = load_norm(scsh, b, C, c0);
+    const int ncol = 2 * cols + 2, wbase = 2 * blockIdx.x * cols - 1, rowsz = ncol * tpp;
+    // [slot 2][row of the pair 2][raw | normalised][rowsz]
+    auto S = [&](int slot, int r, int kind) { return fir_sm + ((slot * 2 + r) * 2 + kind) * rowsz; };
+    StageRegs<3> ga, gb;                              // ncol = 2 cols + 2 <= 3 cols for cols >= 2 (checked by the launcher)
+    auto load_pair = [&](int hh) {
+        fir_stage_load<3>(img, ld, H, W, hh, wbase, ncol, tpp, chunk, ga);
+        fir_stage_load<3>(img, ld, H, W, hh + 1, wbase, ncol, tpp, chunk, gb);
+    };
+    auto store_pair = [&](int slot) {
+        fir_stage_store<3>(ga, ncol, tpp, chunk, nm, S(slot, 0, 0), S(slot, 0, 1));
+        fir_stage_store<3>(gb, ncol, tpp, chunk, nm, S(slot, 1, 0), S(slot, 1, 1));
+    };
+    const int my = 2 * tcol * tpp + chunk;            // first of this thread's four staged columns
+    load_pair(2 * ho0 - 1);
+    store_pair(0);
+    load_pair(2 * ho0 + 1);
+    store_pair(1);
+    __syncthreads();
+    float n0[8], n1[8], q0[8], q1[8];                 // horizontally filtered rows 2ho-1, 2ho (normalised / raw)
+    hfilt_down_s(S(0, 0, 1) + my, tpp, n0);
+    hfilt_down_s(S(0, 1, 1) + my, tpp, n1);
+    hfilt_down_s(S(0, 0, 0) + my, tpp, q0);
+    hfilt_down_s(S(0, 1, 0) + my, tpp, q1);
+    const bool live = wo < Wo;
+    bf16* on = out_n + (((int64_t)b * Ho + ho0) * Wo + (live ? wo : 0)) * out_n_ld + c0;
+    bf16* orw = out_r + (((int64_t)b * Ho + ho0) * Wo + (live ? wo : 0)) * out_r_ld + c0;
+    for (int ho = ho0; ho < ho1; ++ho, on += (int64_t)Wo * out_n_ld, orw += (int64_t)Wo * out_r_ld) {
+        const int slot = (ho - ho0 + 1) & 1;          // the pair holding rows 2ho+1, 2ho+2
+        __syncthreads();                              // that pair is complete; the other slot is no longer being read
+        const bool more = ho + 1 < ho1;               // block-uniform
+        if (more) load_pair(2 * ho + 3);              // next pair's loads are in flight while this row is finished
+        float t2[8], t3[8], o[8];
+        hfilt_down_s(S(slot, 0, 1) + my, tpp, t2);
+        hfilt_down_s(S(slot, 1, 1) + my, tpp, t3);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = 0.125f * (n0[j] + t3[j]) + 0.375f * (n1[j] + t2[j]);
+        if (live) *reinterpret_cast<uint4*>(on) = pack8(o);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { n0[j] = t2[j]; n1[j] = t3[j]; }
+        hfilt_down_s(S(slot, 0, 0) + my, tpp, t2);
+        hfilt_down_s(S(slot, 1, 0) + my, tpp, t3);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = 0.125f * (q0[j] + t3[j]) + 0.375f * (q1[j] + t2[j]);
+        if (live) *reinterpret_cast<uint4*>(orw) = pack8(o);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { q0[j] = t2[j]; q1[j] = t3[j]; }
+        if (more) store_pair(slot ^ 1);
+    }
 }
-__global__ void __launch_bounds__(256)
+
+// horizontal interpolation of a staged row at this thread's column (p: the column left of it): ea -> output column 2wi,
+// eb -> 2wi+1; the same operations in the same order as hfilt_up
+__device__ __forceinline__ void hfilt_up_s(const uint4* __restrict__ p, int tpp, bool row_ok, bool has_l, bool has_r, float* ea,
+                                           float* eb) {
+    zero8(ea);
+    zero8(eb);
+    if (!row_ok) return;
+    float m[8];
+    unpack8(p[tpp], m);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { ea[j] = 0.75f * m[j]; eb[j] = 0.75f * m[j]; }
+    if (has_l) {
+        float l[8];
+        unpack8(p[0], l);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ea[j] = fmaf(0.25f, l[j], ea[j]);
+    }
+    if (has_r) {
+        float rr[8];
+        unpack8(p[2 * tpp], rr);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) eb[j] = fmaf(0.25f, rr[j], eb[j]);
+    }
+}
+
+__global__ void __launch_bounds__(256, 2)
 fir_up2_dual_kernel(const bf16* __restrict__ x, int ld, int C, int H, int W, bf16* __restrict__ out_n, int out_n_ld,
                     bf16* __restrict__ out_r, int out_r_ld, int band, const float* __restrict__ scsh) {
     pdl_sync();
-    fir_up2_body<true>(x, ld, C, H, W, out_n, out_n_ld, band, scsh);
-    fir_up2_body<false>(x, ld, C, H, W, out_r, out_r_ld, band, nullptr);
+    extern __shared__ __align__(16) uint4 fir_sm[];
+    const int tpp = C >> 3, cols = blockDim.x / tpp;
+    const int chunk = threadIdx.x % tpp, tcol = threadIdx.x / tpp, c0 = chunk * 8;
+    const int wi = blockIdx.x * cols + tcol;          // >= W: the thread only helps staging
+    const int b = blockIdx.z, Wo = 2 * W;
+    const bf16* img = x + (int64_t)b * H * W * ld;
+    const int h0 = blockIdx.y * band, h1 = min(h0 + band, H);
+    const Norm8 nm = load_norm(scsh, b, C, c0);
+    const int ncol = cols + 2, wbase = blockIdx.x * cols - 1, rowsz = ncol * tpp;
+    // ring of three rows: row r lives in slot (r - (h0 - 1)) % 3;  [slot 3][raw | normalised][rowsz]
+    auto S = [&](int row, int kind) { return fir_sm + (((row - (h0 - 1)) % 3) * 2 + kind) * rowsz; };
+    StageRegs<2> gr;                                  // ncol = cols + 2 <= 2 cols for cols >= 2 (checked by the launcher)
+    auto stage_load = [&](int row) { fir_stage_load<2>(img, ld, H, W, row, wbase, ncol, tpp, chunk, gr); };
+    auto stage_store = [&](int row) { fir_stage_store<2>(gr, ncol, tpp, chunk, nm, S(row, 0), S(row, 1)); };
+    auto stage = [&](int row) { stage_load(row); stage_store(row); };
+    const int my = tcol * tpp + chunk;                // the column left of this thread's input column
+    const bool live = wi < W, has_l = wi > 0, has_r = wi + 1 < W;
+    stage(h0 - 1);
+    stage(h0);
+    stage(h0 + 1);
+    __syncthreads();
+    float pa[8], pb[8], ca[8], cb[8], qa[8], qb[8], da[8], db[8];   // rows hi-1 / hi, normalised (p, c) and raw (q, d)
+    hfilt_up_s(S(h0 - 1, 1) + my, tpp, h0 - 1 >= 0, has_l, has_r, pa, pb);
+    hfilt_up_s(S(h0, 1) + my, tpp, true, has_l, has_r, ca, cb);
+    hfilt_up_s(S(h0 - 1, 0) + my, tpp, h0 - 1 >= 0, has_l, has_r, qa, qb);
+    hfilt_up_s(S(h0, 0) + my, tpp, true, has_l, has_r, da, db);
+    bf16* on = out_n + (int64_t)b * (2 * H) * Wo * out_n_ld + c0;
+    bf16* orw = out_r + (int64_t)b * (2 * H) * Wo * out_r_ld + c0;
+    for (int hi = h0; hi < h1; ++hi) {
+        __syncthreads();                              // row hi+1 is complete; the slot of row hi-1's predecessor is free
+        const bool more = hi + 2 <= h1;               // block-uniform: row hi+2 is needed by the next trip
+        if (more) stage_load(hi + 2);                 // its loads overlap this row's arithmetic
+        float na[8], nb[8], o[8];
+        const bool nrow = hi + 1 < H;
+        hfilt_up_s(S(hi + 1, 1) + my, tpp, nrow, has_l, has_r, na, nb);
+        if (live) {
+            bf16* r_even = on + ((int64_t)(2 * hi) * Wo + 2 * wi) * out_n_ld;
+            bf16* r_odd = r_even + (int64_t)Wo * out_n_ld;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = fmaf(0.25f, pa[j], 0.75f * ca[j]);
+            *reinterpret_cast<uint4*>(r_even) = pack8(o);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = fmaf(0.25f, pb[j], 0.75f * cb[j]);
+            *reinterpret_cast<uint4*>(r_even + out_n_ld) = pack8(o);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = fmaf(0.25f, na[j], 0.75f * ca[j]);
+            *reinterpret_cast<uint4*>(r_odd) = pack8(o);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = fmaf(0.25f, nb[j], 0.75f * cb[j]);
+            *reinterpret_cast<uint4*>(r_odd + out_n_ld) = pack8(o);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { pa[j] = ca[j]; pb[j] = cb[j]; ca[j] = na[j]; cb[j] = nb[j]; }
+        hfilt_up_s(S(hi + 1, 0) + my, tpp, nrow, has_l, has_r, na, nb);
+        if (live) {
+            bf16* r_even = orw + ((int64_t)(2 * hi) * Wo + 2 * wi) * out_r_ld;
+            bf16* r_odd = r_even + (int64_t)Wo * out_r_ld;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = fmaf(0.25f, qa[j], 0.75f * da[j]);
+            *reinterpret_cast<uint4*>(r_even) = pack8(o);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = fmaf(0.25f, qb[j], 0.75f * db[j]);
+            *reinterpret_cast<uint4*>(r_even + out_r_ld) = pack8(o);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = fmaf(0.25f, na[j], 0.75f * da[j]);
+            *reinterpret_cast<uint4*>(r_odd) = pack8(o);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = fmaf(0.25f, nb[j], 0.75f * db[j]);
+            *reinterpret_cast<uint4*>(r_odd + out_r_ld) = pack8(o);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { qa[j] = da[j]; qb[j] = db[j]; da[j] = na[j]; db[j] = nb[j]; }
+        if (more) stage_store(hi + 2);
+    }
 }
 
 __global__ void __launch_bounds__(256)
@@ -405,15 +613,24 @@ int fir_up2_launch(const ActView* x, const ActView* out, cudaStream_t s, const f
 
 int fir_dual_launch(const ActView* x, const ActView* out_n, const ActView* out_r, int up, const float* scsh, cudaStream_t s) {
     SNRSE_CHECK_ARG(scsh != nullptr, "fir_dual: GroupNorm scale / shift required");
-    SNRSE_CHECK_ARG(x->C % 8 == 0 && x->C <= 2048 && x->B <= 65535, "fir_dual: C %% 8 == 0, C <= 2048, B <= 65535");
+    SNRSE_CHECK_ARG(x->C % 8 == 0 && x->C <= 1024 && x->B <= 65535, "fir_dual: C %% 8 == 0, C <= 1024, B <= 65535");
     SNRSE_CHECK_ARG(up || (x->H % 2 == 0 && x->W % 2 == 0), "fir_dual (down): H, W must be even");
     const int tpp = x->C / 8, nthr = tpp * (256 / tpp > 0 ? 256 / tpp : 1), cols = nthr / tpp;
     const int wcols = up ? x->W : x->W / 2, hrows = up ? x->H : x->H / 2;
     int band = FIR_BAND;
     while (band > 1 && (int64_t)cdiv(wcols, cols) * cdiv(hrows, band) * x->B < 592) band >>= 1;
     dim3 grid((unsigned)cdiv(wcols, cols), (unsigned)cdiv(hrows, band), (unsigned)x->B);
-    if (up) snrse_launch(fir_up2_dual_kernel, dim3(grid), dim3(nthr), 0, s, x->ptr, x->ld, x->C, x->H, x->W, out_n->ptr, out_n->ld, out_r->ptr, out_r->ld, band, scsh);
-    else snrse_launch(fir_down2_dual_kernel, dim3(grid), dim3(nthr), 0, s, x->ptr, x->ld, x->C, x->H, x->W, out_n->ptr, out_n->ld, out_r->ptr, out_r->ld, band, scsh);
+    // staged rows: down 2 slots x 2 rows, up a ring of 3 rows; raw + normalised copies, 16 bytes per (column, 8 channels)
+    const size_t smem = (size_t)(up ? 3 * 2 * (cols + 2) : 2 * 2 * 2 * (2 * cols + 2)) * tpp * 16;
+    static bool attr_set = false;
+    if (!attr_set) {
+        SNRSE_CUDA(cudaFuncSetAttribute(fir_down2_dual_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        SNRSE_CUDA(cudaFuncSetAttribute(fir_up2_dual_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        attr_set = true;
+    }
+    SNRSE_CHECK_ARG(smem <= 160 * 1024, "fir_dual: row staging does not fit shared memory");
+    if (up) snrse_launch(fir_up2_dual_kernel, dim3(grid), dim3(nthr), smem, s, x->ptr, x->ld, x->C, x->H, x->W, out_n->ptr, out_n->ld, out_r->ptr, out_r->ld, band, scsh);
+    else snrse_launch(fir_down2_dual_kernel, dim3(grid), dim3(nthr), smem, s, x->ptr, x->ld, x->C, x->H, x->W, out_n->ptr, out_n->ld, out_r->ptr, out_r->ld, band, scsh);
     SNRSE_LAUNCH_CHECK();
     return SNRSE_OK;
 }

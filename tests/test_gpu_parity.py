@@ -497,7 +497,7 @@ def _network_report(engine, sd, x, t, flags):
 
 
 @pytest.mark.parametrize("flags", [2, 4, 16, 32, 192, 0], ids=["cuda-core-conv", "tcgen05gemm-conv", "tcgen05-unfused-gn",
-                                                         "tcgen05-gn-in-single-fir", "tcgen05-dual-fir-in-kernel-finalize", "tcgen05-conv"])
+                                                         "tcgen05-gn-in-single-fir", "tcgen05-three-pass-fir-in-kernel-finalize", "tcgen05-conv"])
 def test_ncsnpp_forward_vs_golden(engine, sd, golden_dir, flags):
     z = np.load(os.path.join(golden_dir, "ncsnpp_forward.npz"))
     x, t = _c(z["x"]), _c(z["t"])
@@ -515,7 +515,7 @@ def test_in_kernel_groupnorm_finalize_equals_finalize_launches(engine, B, T):
     """Flag bit7: the normalising convolutions derive GroupNorm scale / shift from the fixed-point statistics inside the
     kernel (one or two sources for concatenated inputs, recomputed when a CTA moves to the next image) instead of
     reading the table of a gn_finalize launch.  Same arithmetic -> the network output is bit-identical; so is the
-    dual-output FIR pass of the up / down blocks (bit6) against GroupNorm pass + two FIR passes."""
+    dual-output FIR pass of the up / down blocks (the default) against GroupNorm pass + two FIR passes (bit6)."""
     g = torch.Generator().manual_seed(B * 1000 + T)
     x = torch.view_as_complex(torch.randn(B, 2, 256, T, 2, generator=g) * 0.3)
     t = torch.linspace(0.05, 0.9, B)

@@ -2,7 +2,7 @@
 """A/B of engine plan flags on the REAL step: one captured CUDA graph of the full 16 x 4 s sebridge_v3 pass per variant
 (own model, own activation arena), replayed back to back; the variants are interleaved round-robin so that thermal /
 power drift hits them equally.  Usage: python tools/step_ab.py [flags ...]   (default: 0 128 64 192)
-  bit6 (64): dual-output FIR launch in the up / down blocks instead of GroupNorm pass + two FIR passes
+  bit6 (64): GroupNorm pass + two FIR passes in the up / down blocks instead of the dual-output FIR launch (default)
   bit7 (128): in-kernel GroupNorm finalize of the normalising convolutions instead of gn_finalize launches"""
 import json
 import os
