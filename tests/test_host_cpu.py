@@ -32,6 +32,20 @@ def test_abi_exports_every_declared_symbol():
     assert lib.snrse_version() == 100
 
 
+def test_pdl_mask_round_trip():
+    """snrse_set_pdl is host-only state: returns the previous mask, keeps three bits, a negative argument only queries."""
+    from snr_aligned_diffse_b200 import _lib
+    lib = _lib.load()
+    prev = lib.snrse_set_pdl(-1)
+    try:
+        assert 0 <= prev <= 7
+        assert lib.snrse_set_pdl(5) == prev and lib.snrse_set_pdl(-1) == 5
+        assert lib.snrse_set_pdl(0xFF) == 5 and lib.snrse_set_pdl(-1) == 7
+        assert lib.snrse_set_pdl(0) == 7 and lib.snrse_set_pdl(-1) == 0
+    finally:
+        lib.snrse_set_pdl(prev)
+
+
 def test_product_has_no_oracle_or_fallback_imports():
     pkg = os.path.join(ROOT, "snr_aligned_diffse_b200")
     for dp, _, fs in os.walk(pkg):

@@ -9,11 +9,11 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from oracle.topology import snrnet_param_specs  # noqa: E402  (parameter shapes only)
 from snr_aligned_diffse_b200 import ops  # noqa: E402
 from snr_aligned_diffse_b200.synth import synth_state_dict  # noqa: E402
 
-net = ops.SNRNetEngine().load_state_dict(synth_state_dict(snrnet_param_specs(), seed=1), "cuda")
+net = ops.SNRNetEngine()
+net.load_state_dict(synth_state_dict(net.param_shapes(), seed=1), "cuda")
 feat = torch.randn(16, 2, 256, 512, generator=torch.Generator().manual_seed(0)).cuda()
 for _ in range(3):
     out = net.forward(feat)
